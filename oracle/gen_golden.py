@@ -1,0 +1,322 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference renderer (CPU, fp32).
+
+Run in the build container only (needs /root/reference; it does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/gen_golden.py
+
+The reference imports two off-path packages (pycolmap, imageio) at module import; they are
+stubbed with empty modules exactly as the survey did.  Weights come from
+oracle/weights.py (seeded hash), so fixtures store only inputs, random draws, intermediates
+and outputs.  Intermediates are captured by wrapping the two module-level functions that
+``renderer.render_rays`` calls (sample_smth_along_rays / volume_render_radiance_field).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from argparse import Namespace as NS
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.dont_write_bytecode = True
+
+REF = "/root/reference"
+
+
+def import_reference():
+    import torch  # noqa: F401
+
+    sys.path.insert(0, REF)
+    for m in ("pycolmap", "imageio"):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    import nerfmatch.nerf.renderer as r
+
+    return r
+
+
+def ref_config(embed="mip", nc=64, nf=128, app=False, white_bg=False):
+    # mirrors configs/nerf/nerf_7scenes_mip_sfm.yaml:24-55
+    emb = NS(xyz_num_freqs=15, dirs_num_freqs=4, appearance_embed=app)
+    if embed is not None:
+        emb.type = embed
+    return NS(
+        data=NS(img_wh=[160, 120]),
+        render=NS(chunksize=16384, use_disp=False, perturb=True, noise_std=1.0, white_bg=white_bg, use_viewdirs=True),
+        embedding=emb,
+        coarse_nerf=NS(method="NeRF", layer_num=8, hid_dim=256, output_dim=4, skips=[4], num_pts=nc),
+        fine_nerf=NS(method="NeRF", layer_num=8, hid_dim=256, output_dim=4, skips=[4], num_pts=nf),
+        loss=NS(),
+    )
+
+
+CASES = {
+    # sigma_target = (mean, std) the raw density is calibrated to on this view (see calibrate_sigma)
+    "mip64": dict(embed="mip", nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False, sigma_target=(2.0, 1.0), ds=48, seed=0),
+    "mip128_peaky": dict(embed="mip", nc=128, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False, sigma_target=(5.0, 40.0), ds=60, seed=1),
+    "normal_64_128": dict(embed="normal", nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False, sigma_target=(2.0, 1.0), ds=48, seed=2),
+    "normal_64_128_peaky": dict(embed="normal", nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False, sigma_target=(5.0, 40.0), ds=60, seed=3),
+    "mip64_app_max_white": dict(embed="mip", nc=64, nf=128, app=True, stop_layer=-1, feat_comb="max", white_bg=True, sigma_target=(5.0, 40.0), ds=60, seed=4),
+    "normal_app_stop5": dict(embed="normal", nc=64, nf=128, app=True, stop_layer=5, feat_comb="lin", white_bg=False, sigma_target=(5.0, 40.0), ds=80, seed=5),
+}
+
+
+def calibrate_sigma(c, rays):
+    """Default-init densities are all slightly negative (every weight would be 0): measure the raw sigma
+    of each net on this view's coarse samples and return the (gain, bias) pairs that map it to the
+    case's target mean / std.  Rounded to 4 significant digits so the case dict reproduces them."""
+    from oracle import nerf_oracle as O
+    from oracle.weights import make_state_dict
+
+    app = 16 if c["app"] else 0
+    sd = make_state_dict(c["seed"], embed_type=c["embed"], app_dim=app, num_frames=7 if c["app"] else 0)
+    cfg = O.RenderConfig(embed_type=c["embed"], num_pts_coarse=c["nc"], app_dim=app, stop_layer=c["stop_layer"])
+    n = rays.shape[0]
+    if c["embed"] == "mip":
+        _, pts, var = O.sample_gaus_along_rays(rays, c["nc"], None)
+    else:
+        pts, _ = O.sample_pts_init(rays, c["nc"])
+        var = None
+    appv = sd["embedding_a.weight"][np.arange(n) % 7] if app else None
+    x = O.encode_points(cfg, pts, var, rays[:, 8:11], appv, c["nc"])
+    gains, biases = [], []
+    for net in ("nerf_coarse.", "nerf_fine."):
+        raw, _ = O.mlp_forward(O.split_state_dict(sd, net), x, cfg)
+        m, s = float(raw[:, 3].mean()), float(raw[:, 3].std())
+        g = float(f"{c['sigma_target'][1] / s:.4g}")
+        gains.append(g)
+        biases.append(float(f"{c['sigma_target'][0] - g * m:.4g}"))
+    return tuple(gains), tuple(biases)
+
+
+def run_case(r, name, c):
+    import torch
+
+    from oracle.weights import K_7SCENES, make_pose, make_state_dict, make_unnorm_scene
+
+    c = dict(c)
+    rays0 = r.sample_nerf_rays(480, 640, torch.from_numpy(K_7SCENES), torch.from_numpy(make_pose(c["seed"])), ds=c["ds"], embed_type=c["embed"])
+    c["sigma_gain"], c["sigma_bias"] = calibrate_sigma(c, rays0.numpy())
+
+    torch.set_grad_enabled(False)
+    torch.manual_seed(0)
+    num_frames = 7 if c["app"] else None
+    ren = r.NerfRenderer(
+        ref_config(c["embed"], c["nc"], c["nf"], c["app"], c["white_bg"]),
+        num_frames=num_frames, training=False, stop_layer=c["stop_layer"],
+    ).eval()
+    sd = make_state_dict(
+        c["seed"], embed_type=c["embed"], app_dim=16 if c["app"] else 0, num_frames=num_frames or 0,
+        sigma_gain=c["sigma_gain"], sigma_bias=c["sigma_bias"],
+    )
+    missing = ren.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+    ren.ret_pfeat = True
+    ren.feat_comb = c["feat_comb"]
+
+    H, W = 480, 640
+    K = torch.from_numpy(K_7SCENES)
+    c2w = torch.from_numpy(make_pose(c["seed"]))
+    rays = r.sample_nerf_rays(H, W, K, c2w, ds=c["ds"], embed_type=c["embed"])
+    n = rays.shape[0]
+    h, w = len(range(c["ds"] // 2, H, c["ds"])), len(range(c["ds"] // 2, W, c["ds"]))
+    assert h * w == n
+    ray_id = None
+    if c["app"]:
+        ray_id = torch.from_numpy((np.arange(n) % 7).astype(np.int64))
+
+    # capture intermediates
+    cap = {"z": [], "w": [], "raw": []}
+    orig_sample, orig_vol = r.sample_smth_along_rays, r.volume_render_radiance_field
+
+    def sample_wrap(*a, **k):
+        out = orig_sample(*a, **k)
+        cap["z"].append(out[1].clone().numpy())
+        return out
+
+    def vol_wrap(raw, *a, **k):
+        out = orig_vol(raw, *a, **k)
+        cap["raw"].append(raw.clone().numpy())
+        cap["w"].append(out[3].clone().numpy())
+        return out
+
+    r.sample_smth_along_rays, r.volume_render_radiance_field = sample_wrap, vol_wrap
+    try:
+        torch.manual_seed(7)
+        preds = ren.predict(rays, w, h, ray_id=ray_id)
+    finally:
+        r.sample_smth_along_rays, r.volume_render_radiance_field = orig_sample, orig_vol
+
+    out = {
+        "rays": rays.numpy(), "hw": np.array([h, w]), "H": H, "W": W, "ds": c["ds"],
+        "K": K.numpy(), "c2w": c2w.numpy(),
+    }
+    if ray_id is not None:
+        out["ray_id"] = ray_id.numpy()
+    if c["embed"] == "mip":
+        # replay the two draws the reference consumed (render_utils.py:444, 483-485)
+        S1 = c["nc"] + 1
+        torch.manual_seed(7)
+        t_rand = torch.rand(n, S1)
+        s = 1 / S1
+        u_jit = torch.empty(n, S1).uniform_(to=(s - torch.finfo(torch.float32).eps))
+        out["t_rand"], out["u_jitter"] = t_rand.numpy(), u_jit.numpy()
+    for key in ("coarse", "fine"):
+        i = 0 if key == "coarse" else 1
+        out[f"z_{key}"] = cap["z"][i]
+        out[f"weights_{key}"] = cap["w"][i]
+        out[f"raw_{key}"] = cap["raw"][i]
+        out[f"feat_{key}"] = preds[f"feat_{key}"].numpy()
+        out[f"pts_{key}"] = preds[f"pts_{key}"].numpy()
+        out[f"rgb_{key}"] = preds[f"rgb_{key}"].reshape(n, 3).numpy()
+        out[f"depth_{key}"] = preds[f"depth_{key}"].reshape(n).numpy()
+    # un-normalised points as render_novel_view returns them (renderer.py:327)
+    un = make_unnorm_scene()
+    from nerfmatch.utils.geometry import unnormaliz_pts
+
+    out["unnorm_scene"] = un
+    out["pt3d"] = unnormaliz_pts(preds["pts_fine"][None], torch.from_numpy(un)[None])[0].numpy()
+    out["case"] = np.array(repr(c))
+    return out
+
+
+def raygen_cases(r):
+    import torch
+
+    from oracle.weights import K_7SCENES, K_CAMBRIDGE, make_pose
+
+    out = {}
+    for tag, (H, W, K, ds, embed) in {
+        "7s_ds8_mip": (480, 640, K_7SCENES, 8, "mip"),
+        "7s_ds8_normal": (480, 640, K_7SCENES, 8, "normal"),
+        "small_ds1_mip": (24, 40, np.array([[30.0, 0, 20], [0, 31.0, 12], [0, 0, 1]], np.float32), 1, "mip"),
+        "cam_ds16_mip": (480, 854, K_CAMBRIDGE, 16, "mip"),
+    }.items():
+        c2w = make_pose(11)
+        rays = r.sample_nerf_rays(H, W, torch.from_numpy(K), torch.from_numpy(c2w), ds=ds, embed_type=embed)
+        out[f"{tag}.rays"] = rays.numpy()
+        out[f"{tag}.meta"] = np.array([H, W, ds, 1 if embed == "mip" else 0])
+        out[f"{tag}.K"] = K
+        out[f"{tag}.c2w"] = c2w
+    return out
+
+
+def stage_cases(r):
+    """Direct calls of reference stage functions on synthetic inputs (peaky weights etc.)."""
+    import torch
+    from nerfmatch.nerf import render_utils as ru
+    from nerfmatch.nerf.embedding import FourierEmbedding, PositionalEncodingMIP
+
+    from oracle.weights import uniform01
+
+    out = {}
+    n, S = 96, 64
+    # --- mip resampling on hand-made weights: near-delta, zeros, uniform, random
+    t = np.sort(uniform01(3, 1, n * (S + 1)).reshape(n, S + 1) * 1.3 + 0.01, -1).astype(np.float32)
+    w = uniform01(3, 2, n * S).reshape(n, S).astype(np.float32) ** 8
+    w[0] = 0.0
+    w[1] = 1.0 / S
+    w[2] = 0.0
+    w[2, 17] = 0.9
+    w[3] = 0.0
+    w[3, 0] = 0.7
+    w[4] = 0.0
+    w[4, -1] = 0.99
+    origins = (uniform01(3, 3, n * 3).reshape(n, 3) * 0.4 - 0.2).astype(np.float32)
+    d = uniform01(3, 4, n * 3).reshape(n, 3) - 0.5
+    d = (d / np.linalg.norm(d, axis=-1, keepdims=True)).astype(np.float32)
+    radii = (uniform01(3, 5, n).reshape(n, 1) * 1e-3 + 5e-4).astype(np.float32)
+    torch.manual_seed(5)
+    s = 1 / (S + 1)
+    u_jit = torch.empty(n, S + 1).uniform_(to=(s - torch.finfo(torch.float32).eps))
+    for randomized in (True, False):
+        torch.manual_seed(5)
+        new_t, (mean, cov) = ru.resample_gaus_along_rays(
+            torch.from_numpy(origins), torch.from_numpy(d), torch.from_numpy(radii), torch.from_numpy(t.copy()),
+            torch.from_numpy(w.copy()), randomized=randomized, stop_grad=True, resample_padding=0.01, ray_shape="cone",
+        )
+        tag = "rand" if randomized else "det"
+        out[f"mip_resample.{tag}.new_t"] = new_t.numpy()
+        out[f"mip_resample.{tag}.mean"] = mean.numpy()
+        out[f"mip_resample.{tag}.cov"] = cov.numpy()
+    out["mip_resample.t"], out["mip_resample.w"], out["mip_resample.u_jitter"] = t, w, u_jit.numpy()
+    # reference-side interval indices: the same torch ops as render_utils.py:456-490, 583-590 (so the
+    # row sum has torch's own order), then the searchsorted form of find_interval.
+    tw = torch.from_numpy(w.copy())
+    wp = torch.cat([tw[..., :1], tw, tw[..., -1:]], dim=-1)
+    wm = torch.maximum(wp[..., :-1], wp[..., 1:])
+    wb = 0.5 * (wm[..., :-1] + wm[..., 1:]) + 0.01
+    wsum = torch.sum(wb, dim=-1, keepdim=True)
+    pad = torch.maximum(torch.zeros_like(wsum), 1e-5 - wsum)
+    wb = wb + pad / wb.shape[-1]
+    wsum = wsum + pad
+    cdf = torch.minimum(torch.ones(()), torch.cumsum((wb / wsum)[..., :-1], dim=-1))
+    cdf = torch.cat([torch.zeros(n, 1), cdf, torch.ones(n, 1)], dim=-1)
+    uu = (torch.arange(S + 1) * s)[None, ...]
+    uu = torch.minimum(uu + uu + u_jit, torch.full_like(u_jit, 1.0 - torch.finfo(torch.float32).eps))
+    out["mip_resample.rand.idx_ref"] = (torch.searchsorted(cdf, uu.contiguous(), right=True) - 1).numpy().astype(np.int32)
+    out["mip_resample.rand.cdf_ref"] = cdf.numpy()
+    out["mip_resample.o"], out["mip_resample.d"], out["mip_resample.radii"] = origins, d, radii
+
+    # --- classic sample_pdf + sort
+    z = np.sort(uniform01(4, 1, n * S).reshape(n, S) * 1.2 + 0.01, -1).astype(np.float32)
+    wn = uniform01(4, 2, n * S).reshape(n, S).astype(np.float32) ** 6
+    wn[0] = 0
+    wn[1] = 0
+    wn[1, 30] = 0.8
+    wn[2] = 0
+    wn[2, 1] = 0.5
+    wn[2, 62] = 0.5
+    rays = np.concatenate([origins, d, np.full((n, 1), 0.01, np.float32), np.full((n, 1), 1.2, np.float32), d], -1).astype(np.float32)
+    pts, z_new = ru.sample_pts_fine(torch.from_numpy(origins), torch.from_numpy(d), torch.from_numpy(z), torch.from_numpy(wn), num_pts=128, perturb=False)
+    out["normal_resample.z"], out["normal_resample.w"], out["normal_resample.rays"] = z, wn, rays
+    out["normal_resample.z_new"], out["normal_resample.pts"] = z_new.numpy(), pts.numpy()
+
+    # --- encodings at large arguments
+    x = (uniform01(6, 1, 200 * 3).reshape(200, 3) * 2 - 1).astype(np.float32)
+    v = (uniform01(6, 2, 200 * 3).reshape(200, 3) * 1e-4).astype(np.float32)
+    mipenc = PositionalEncodingMIP(15)
+    out["enc.x"], out["enc.var"] = x, v
+    out["enc.ipe"] = mipenc(torch.from_numpy(x), y=torch.from_numpy(v))[0].numpy()
+    out["enc.pe_dirs"] = PositionalEncodingMIP(4)(torch.from_numpy(x)).numpy()
+    out["enc.fourier15"] = FourierEmbedding(15)(torch.from_numpy(x)).numpy()
+    out["enc.fourier4"] = FourierEmbedding(4)(torch.from_numpy(x)).numpy()
+
+    # --- volume rendering (both modes, white bg) on synthetic raw
+    raw = (uniform01(7, 1, n * S * 4).reshape(n, S, 4)).astype(np.float32)
+    raw[..., 3] = (raw[..., 3] - 0.4) * 60.0
+    raw[5, :, 3] = -1.0  # empty ray
+    raw[6, :, 3] = 1e4  # opaque at first sample
+    for mode, zz in (("mip", t), ("normal", z)):
+        for wb in (False, True):
+            res = ru.volume_render_radiance_field(
+                torch.from_numpy(raw), torch.from_numpy(zz), torch.from_numpy(d), noise_std=0.0, white_bg=wb, embed_type=mode,
+            )
+            tag = f"volrender.{mode}.{'white' if wb else 'black'}"
+            out[tag + ".rgb"], out[tag + ".disp"], out[tag + ".acc"] = res[0].numpy(), res[1].numpy(), res[2].numpy()
+            out[tag + ".weights"], out[tag + ".depth"] = res[3].numpy(), res[4].numpy()
+    out["volrender.raw"] = raw
+    return out
+
+
+def main():
+    r = import_reference()
+    gdir = os.path.join(os.path.dirname(HERE), "tests", "golden")
+    os.makedirs(gdir, exist_ok=True)
+    for name, c in CASES.items():
+        out = run_case(r, name, c)
+        path = os.path.join(gdir, f"render_{name}.npz")
+        np.savez_compressed(path, **out)
+        print(name, "n =", out["rays"].shape[0], "->", path, os.path.getsize(path) // 1024, "KiB",
+              "acc_c %.3f acc_f %.3f" % (out["weights_coarse"].sum(-1).mean(), out["weights_fine"].sum(-1).mean()),
+              "wmax_f %.3f" % out["weights_fine"].max(-1).mean(), str(out["case"]))
+    for fname, fn in (("raygen.npz", raygen_cases), ("stages.npz", stage_cases)):
+        out = fn(r)
+        path = os.path.join(gdir, fname)
+        np.savez_compressed(path, **out)
+        print(fname, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
