@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Benchmark of the scene-feature render hot path (BASELINE.json: rays/sec, feature render, 64+128 samples).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+A "step" renders one full 480x640 view (307 200 rays, classic 64 coarse + 128 fine samples = 256 MLP
+evaluations per ray, feature tap at layer 3, all reference outputs incl. feat_coarse) per GPU with
+random-init weights (oracle/weights.py) and a synthetic pose.  Prints ONE JSON line (rank 0):
+
+  value     rays/s of the whole job with the rays already resident in HBM (CUDA events, max over ranks)
+  e2e       rays/s through the C-ABI host entry (nmr_render_host): pinned host rays in, host outputs back
+  roofline  the MLP kernels' achieved TFLOP/s (algorithmic FLOPs / CUDA-event time) vs the measured bf16 peak
+  cpu_baseline  the oracle port on the host cores, on a bounded sample of the same workload (rank 0, N=1)
+
+`--impl reference` times the CPU implementation only (the oracle port: the reference is Python and cannot
+travel to the GPU box) on the same config / metric / unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 480, 640
+METRIC = "rays/sec (feature render, 64+128 samples)"
+FLOP_PER_EVAL = {"normal": 1217536, "mip": 1214464}   # 2 x weights-only MACs, un-padded
+
+
+def workload(embed="normal"):
+    return dict(embed=embed, nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host cores (bounded sample)
+# --------------------------------------------------------------------------------------------
+def cpu_render_rate(embed, n_sample, seed=0):
+    from concurrent.futures import ThreadPoolExecutor
+
+    from threadpoolctl import threadpool_limits
+
+    from oracle import nerf_oracle as O
+    from oracle.weights import K_7SCENES, make_pose, make_state_dict, uniform01
+
+    cores = os.cpu_count() or 1
+    cfg = O.RenderConfig(embed_type=embed, num_pts_coarse=64, num_pts_fine=128, stop_layer=3)
+    sd = make_state_dict(seed, embed_type=embed, sigma_gain=120.0, sigma_bias=(8.0, -2.0))
+    ds = max(1, int(np.sqrt(H * W / n_sample)))
+    rays = O.sample_nerf_rays(H, W, K_7SCENES, make_pose(seed), ds=ds, embed_type=embed)[:n_sample]
+    n = rays.shape[0]
+    tr = uj = None
+    if embed == "mip":
+        tr = uniform01(seed, 5, n * 65).reshape(n, 65)
+        uj = (uniform01(seed, 6, n * 65).reshape(n, 65) * (1 / 65 - 1.2e-7)).astype(np.float32)
+    ch = 64
+
+    def work(i):
+        return O.render_rays(cfg, sd, rays[i:i + ch], None if tr is None else tr[i:i + ch], None if uj is None else uj[i:i + ch], chunk=ch)
+
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            list(ex.map(work, range(0, n, ch)))
+        dt = time.perf_counter() - t0
+    return n / dt, cores, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    embed = args.embed
+    rates = []
+    n_sample = args.cpu_rays
+    for i in range(args.warmup + args.steps):
+        rate, cores, n, dt = cpu_render_rate(embed, n_sample)
+        if i >= args.warmup:
+            rates.append((rate, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([d for _, d in rates])) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": config_block(embed, "fp32-cpu"),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"{n_sample} rays of the {H}x{W} view per step (numpy oracle port of nerfmatch/nerf, one thread per core)"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def config_block(embed, precision):
+    return {"workload": f"7-Scenes {H}x{W} full-res feature render, {embed} embedding, 64 coarse + 128 fine samples "
+                        f"({256 if embed == 'normal' else 128} MLP evals/ray), stop_layer=3, random-init weights",
+            "rays_per_step_per_gpu": H * W, "precision": precision, "parallelism": "rays sharded by view, weights replicated",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set is also >> 126 MB"}
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from nerfmatch_b200.config import build_renderer
+    from nerfmatch_b200.synthetic import K_7SCENES, make_pose, make_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    embed = args.embed
+    c = workload(embed)
+    sd = make_state_dict(0, embed_type=embed, sigma_gain=120.0, sigma_bias=(8.0, -2.0))
+    ren = build_renderer(c, sd, precision=args.precision, device=dev)
+    ren.rng = "philox"      # mip mode: draws generated inside the kernels
+    eng = ren.engine(dev)
+    n = H * W
+    # rank r renders query pose r: rays are sharded by view, weights replicated
+    rays, (h, w), _ = eng.raygen(K_7SCENES, make_pose(100 + rank), H, W, 1)
+    assert rays.shape[0] == n
+    flags = ren._flags()
+    outs = eng.alloc_outputs(n, True, True)
+    un = np.eye(4, dtype=np.float32); un[:3, :3] *= 3.0
+    from nerfmatch_b200 import _lib as L
+    rng_mode = L.NMR_RNG_PHILOX if embed == "mip" else L.NMR_RNG_NONE
+    dargs, keep = eng.make_args(n, rays.shape[1], rays=rays, flags=flags, rng_mode=rng_mode, seed=1234, unnorm=un, outs=outs)
+    # host-side buffers for the end-to-end arm
+    rays_h = rays.cpu().pin_memory()
+    outs_h = eng.alloc_outputs(n, True, True, device="cpu", pin=True)
+    hargs, keep_h = eng.make_args(n, rays.shape[1], rays=rays_h, flags=flags, rng_mode=rng_mode, seed=1234, unnorm=un, outs=outs_h)
+    h2d = rays_h.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in outs_h.values())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0 = time.time()
+        for a, b in ev:
+            flush.fill_(1)
+            a.record(); fn(); b.record()
+        barrier()
+        t1 = time.time()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), t0, t1
+
+    # ---- device-resident arm ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.set_timing(False)
+    l0 = eng.launch_count()
+    ms_dev, t0, t1 = timed(lambda: eng.render(dargs), args.steps, args.warmup)
+    launches = (eng.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    # ---- per-stage split (separate pass, CUDA events on the launch stream inside the library) ----
+    eng.set_timing(True)
+    for _ in range(args.steps):
+        flush.fill_(1)
+        eng.render(dargs)
+    stage = eng.last_stage_ms()
+    eng.set_timing(False)
+    # ---- end-to-end arm ----
+    ms_e2e, _, _ = timed(lambda: eng.render_host(hargs), args.steps, max(1, args.warmup // 2))
+
+    total_rays = n * world
+    value = total_rays * args.steps / (ms_dev / 1e3)
+    e2e = total_rays * args.steps / (ms_e2e / 1e3)
+    pk = peaks()
+    evals = 256 if embed == "normal" else 128
+    flops_step = n * evals * FLOP_PER_EVAL[embed]
+    mlp_s = stage["mlp"] / 1e3 / args.steps
+    achieved = flops_step / mlp_s / 1e12 if mlp_s > 0 else 0.0
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": config_block(embed, args.precision),
+        "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "NeRF MLP (coarse + fine nets)", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " sustained bf16 (MEASURED_PEAKS.json)",
+                     "flops_per_launch_set": flops_step, "ms_per_step": mlp_s * 1e3},
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+    }
+    # compositing kernel: HBM-bound side of the path (SURVEY.md 8d byte counts, bf16 | fp32 features)
+    bf = 2 if args.precision == "bf16" else 4
+    by = 0
+    for S in ((64, 192) if embed == "normal" else (64, 64)):
+        by += n * (S * (256 * bf + 16 + 4 + 12) + 256 * 4 + 12 + 12 + 4 + S * 4)
+    comp_s = stage["composite"] / 1e3 / args.steps
+    line["roofline_composite"] = {"bound": "hbm", "achieved": by / comp_s / 1e9 if comp_s > 0 else 0.0, "peak": pk["hbm"], "unit": "GB/s",
+                                  "frac": (by / comp_s / 1e9 / pk["hbm"]) if comp_s > 0 else 0.0, "bytes_per_step": by}
+    if world == 1 and not args.no_cpu:
+        rate, cores, ns, dt = cpu_render_rate(embed, args.cpu_rays)
+        line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
+                                "sample": f"{ns} rays of the same {H}x{W} view, {dt:.1f} s (numpy oracle port, one thread per core)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("NMR_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--embed", default="normal", choices=["normal", "mip"])
+    ap.add_argument("--cpu-rays", type=int, default=8192)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

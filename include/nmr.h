@@ -1,0 +1,202 @@
+/*
+ * nmr.h  --  C ABI of libnmr.so, the B200-native NeRFMatch scene-feature renderer.
+ *
+ * The reference (nv-dvl/nerfmatch) has no FFI of its own: its boundary for this path is the
+ * Python class nerfmatch/nerf/renderer.py:26 `NerfRenderer` plus a few free functions in
+ * nerfmatch/nerf/render_utils.py.  Each entry point below names the reference interface it
+ * replaces; nerfmatch_b200/renderer.py binds them with ctypes and re-creates that class on
+ * top (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross the boundary.
+ *   - every function returns NMR_OK (0) or a negative nmr_status; nmr_last_error() gives text.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (torch tensors in the shim),
+ *     row-major, fp32 unless stated; "host" pointers are ordinary (ideally pinned) host memory.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is
+ *     enqueued on it and the call returns without synchronising unless stated.
+ *   - a handle is bound to the CUDA device current at nmr_create() and is not thread-safe.
+ *   - there is NO CPU fallback: every entry point fails (NMR_ERR_CUDA) without a device.
+ */
+#ifndef NMR_H_
+#define NMR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMR_ABI_VERSION 1
+#if defined(__GNUC__)
+#define NMR_API __attribute__((visibility("default")))
+#else
+#define NMR_API
+#endif
+
+typedef enum nmr_status {
+  NMR_OK = 0,
+  NMR_ERR_INVALID = -1,     /* bad argument / unsupported configuration                      */
+  NMR_ERR_CUDA = -2,        /* CUDA runtime error (no device, launch failure, OOM)           */
+  NMR_ERR_STATE = -3,       /* e.g. render before weights were set                           */
+  NMR_ERR_UNSUPPORTED = -4  /* configuration valid for the reference but not built here      */
+} nmr_status;
+
+enum { NMR_EMBED_NORMAL = 0, NMR_EMBED_MIP = 1 };          /* config.embedding.type, renderer.py:40 */
+enum { NMR_NET_COARSE = 0, NMR_NET_FINE = 1 };             /* nerf_coarse / nerf_fine               */
+enum { NMR_PREC_FP32 = 0, NMR_PREC_BF16 = 1 };             /* SIMT fp32 (parity) | tcgen05 bf16     */
+enum { NMR_RNG_NONE = 0, NMR_RNG_PHILOX = 1 };             /* draws when t_rand/u_jitter are NULL   */
+
+/* per-call flags: the attributes callers poke on the reference object */
+#define NMR_FLAG_RET_PFEAT   (1u << 0)  /* NerfRenderer.ret_pfeat  (renderer.py:110, 224)            */
+#define NMR_FLAG_FEAT_MAX    (1u << 1)  /* NerfRenderer.feat_comb == "max" (renderer.py:257-260)     */
+#define NMR_FLAG_WHITE_BG    (1u << 2)  /* config.render.white_bg (renderer.py:36, render_utils:224) */
+#define NMR_FLAG_SKIP_COARSE_FEAT (1u << 3) /* do not composite feat_coarse (no caller reads it)     */
+
+/* Static configuration; mirrors what NerfRenderer.__init__ reads (renderer.py:27-114). */
+typedef struct nmr_config {
+  int32_t abi_version;        /* = NMR_ABI_VERSION                                              */
+  int32_t embed_type;         /* NMR_EMBED_*                                                    */
+  int32_t xyz_num_freqs;      /* config.embedding.xyz_num_freqs (15)                            */
+  int32_t dirs_num_freqs;     /* config.embedding.dirs_num_freqs (4)                            */
+  int32_t num_pts_coarse;     /* config.coarse_nerf.num_pts                                     */
+  int32_t num_pts_fine;       /* config.fine_nerf.num_pts (ignored by the mip fine pass, as in
+                                 render_utils.py:592-597)                                       */
+  int32_t hid_dim;            /* 256                                                            */
+  int32_t layer_num;          /* 8                                                              */
+  int32_t skip_layer;         /* 4   (config.*_nerf.skips == [4])                               */
+  int32_t app_dim;            /* 0, or 16 with config.embedding.appearance_embed                */
+  int32_t stop_layer_coarse;  /* -1 (renderer.py:99 sets stop_layer on the fine net only)       */
+  int32_t stop_layer_fine;    /* NerfRenderer(stop_layer=...), models/nerf.py:103-104           */
+  int32_t use_disp;           /* config.render.use_disp (normal mode, render_utils.py:111-113)  */
+  int32_t precision;          /* NMR_PREC_*                                                     */
+  float mip_var_scale;        /* config.embedding.mip_var_scale (<=0: off), render_utils:311    */
+  float resample_padding;     /* 0.01, render_utils.py:277                                      */
+  int64_t max_chunk_points;   /* workspace bound: MLP evaluations in flight (0 = default)       */
+} nmr_config;
+
+/* fp32 nn.Linear parameters of one NeRF (models/nerf.py:44-64), weight = [out, in] row-major.
+ * Pointers may be host or device memory (copied with cudaMemcpyDefault). */
+typedef struct nmr_weight_ptrs {
+  const float* pts_w[8];   /* pts_linears.{i}.weight: [256,xyz] | [256,256] | i==skip+1: [256,xyz+256] */
+  const float* pts_b[8];   /* pts_linears.{i}.bias   [256]                                     */
+  const float* views_w;    /* views_linears.0.weight [128, 256+dirs+app]                       */
+  const float* views_b;    /* [128]                                                            */
+  const float* feature_w;  /* feature_linear.weight  [256,256]                                 */
+  const float* feature_b;  /* [256]                                                            */
+  const float* alpha_w;    /* alpha_linear.weight    [1,256]                                   */
+  const float* alpha_b;    /* [1]                                                              */
+  const float* rgb_w;      /* rgb_linear.weight      [3,128]                                   */
+  const float* rgb_b;      /* [3]                                                              */
+} nmr_weight_ptrs;
+
+/* One render call == NerfRenderer.render_rays(validation=True) (renderer.py:182-295) followed,
+ * if `unnorm` is given, by unnormaliz_pts (utils/geometry.py:76-85) on the fine points.
+ * Output pointers may be NULL (that output is skipped). */
+typedef struct nmr_render_args {
+  const float* rays;        /* [n, ncols]: o(3) d(3) near far viewdirs(3) [radius]             */
+  int64_t n;
+  int32_t ncols;            /* 12 mip, 11 normal; 8..10 -> viewdirs = rays_d (renderer.py:188) */
+  uint32_t flags;           /* NMR_FLAG_*                                                      */
+  const int64_t* ray_id;    /* [n] appearance ids or NULL (-> 1 for every ray, renderer.py:299) */
+  const float* t_rand;      /* mip coarse jitter  [n, Sc+1] in [0,1)   (render_utils.py:444)   */
+  const float* u_jitter;    /* mip fine jitter    [n, Sc+1] in [0, 1/(Sc+1)-eps) (:483-485)    */
+  int32_t rng_mode;         /* NMR_RNG_* used when the two pointers above are NULL             */
+  uint64_t seed;            /* Philox seed for NMR_RNG_PHILOX                                  */
+  const float* unnorm;      /* HOST 3x4 row-major affine (top rows of unnorm_scene) or NULL    */
+
+  float* feat_coarse;       /* [n,256]  preds["feat_coarse"]                                   */
+  float* feat_fine;         /* [n,256]  preds["feat_fine"]  -> pt_feat                         */
+  float* pts_coarse;        /* [n,3]                                                           */
+  float* pts_fine;          /* [n,3]    normalised scene units                                 */
+  float* rgb_coarse;        /* [n,3]                                                           */
+  float* rgb_fine;          /* [n,3]    -> im_pred                                             */
+  float* depth_coarse;      /* [n]                                                             */
+  float* depth_fine;        /* [n]                                                             */
+  float* pt3d;              /* [n,3]    unnorm @ [pts_fine;1]  (needs `unnorm`)                */
+  /* intermediates for parity tests (all optional) */
+  float* z_coarse;          /* mip [n,Sc+1] | normal [n,Sc]                                    */
+  float* z_fine;            /* mip [n,Sc+1] | normal [n,Sc+Nf]                                 */
+  float* weights_coarse;    /* [n,Sc]                                                          */
+  float* weights_fine;      /* mip [n,Sc] | normal [n,Sc+Nf]                                   */
+  float* raw_coarse;        /* [n,Sc,4]  (rgb after sigmoid, raw sigma)                        */
+  float* raw_fine;
+  int32_t* idx_fine;        /* mip [n,Sc+1] interval index | normal [n,Nf] searchsorted result */
+} nmr_render_args;
+
+typedef struct nmr_handle nmr_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+/* NerfRenderer.__init__ (renderer.py:27-114).  *out is NULL on failure. */
+NMR_API int nmr_create(const nmr_config* cfg, nmr_handle** out);
+NMR_API void nmr_destroy(nmr_handle* h);
+/* Text of the last error on this handle (or the last nmr_create failure when h == NULL). */
+NMR_API const char* nmr_last_error(const nmr_handle* h);
+NMR_API int nmr_abi_version(void);
+
+/* NerfRenderer.load_state_dict / .to(device) (nerf_evaluator.py:132-140): copies + repacks the
+ * fp32 nn.Linear parameters of one net (fp32 K-padded panels; bf16 UMMA-major tiles for
+ * NMR_PREC_BF16).  Synchronous. */
+NMR_API int nmr_set_weights(nmr_handle* h, int which, const nmr_weight_ptrs* w);
+/* embedding_a.weight [num_frames, app_dim] (renderer.py:104-107); host or device pointer. */
+NMR_API int nmr_set_appearance(nmr_handle* h, const float* table, int32_t num_frames);
+/* Switch NMR_PREC_FP32 <-> NMR_PREC_BF16 on a live handle (weights are kept in both forms). */
+NMR_API int nmr_set_precision(nmr_handle* h, int precision);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* sample_nerf_rays (render_utils.py:56-78) = get_ray_dirs + get_rays_c2w + rays_intersect_sphere
+ * + prepare_rays_data + [ds/2::ds] subsampling, fused in one kernel.  K (3x3) and c2w (3x4,
+ * already normalised: renderer.py:321-322) are HOST row-major.  rays_dev: [(H/ds')*(W/ds'), 12|11].
+ * *far_fallback (host, optional) is set to 1 when a ray misses the unit sphere and far falls back
+ * to 1 for the whole view, as the reference's try/except does (render_utils.py:62-68); reading it
+ * synchronises the stream. */
+NMR_API int nmr_raygen(nmr_handle* h, const float* K, const float* c2w, int32_t H, int32_t W, int32_t ds,
+               float* rays_dev, int32_t* far_fallback, void* stream);
+
+/* NerfRenderer.render_rays / forward / predict (renderer.py:182-313), device buffers. */
+NMR_API int nmr_render(nmr_handle* h, const nmr_render_args* args, void* stream);
+/* Same call with every pointer in `args` a HOST buffer: stages rays host->device, renders, and
+ * copies the requested outputs device->host on `stream`, then synchronises.  This is the
+ * end-to-end entry bench.py times as `e2e`. */
+NMR_API int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void* stream);
+/* NerfRenderer.render_novel_view (renderer.py:315-333) for a HOST pose: raygen + render +
+ * un-normalisation; outputs in `args` are device pointers, args->rays is ignored. */
+NMR_API int nmr_render_view(nmr_handle* h, const float* K, const float* c2w, int32_t H, int32_t W, int32_t ds,
+                    const nmr_render_args* args, void* stream);
+
+/* ---- per-stage entry points (unit parity, ncu, and the reference's free functions) ------ */
+/* sample_smth_along_rays, coarse branch (render_utils.py:267-323 -> 405-450 | 107-129).
+ * mip:    z [n,S+1], pts = means [n,S,3], var [n,S,3];   normal: z [n,S], pts [n,S,3], var NULL. */
+NMR_API int nmr_stage_sample_coarse(nmr_handle* h, const float* rays, int64_t n, int32_t ncols, const float* t_rand,
+                            float* z, float* pts, float* var, void* stream);
+/* sample_smth_along_rays, fine branch (render_utils.py:555-615 | 132-148, 233-264).
+ * mip:    z_in [n,S+1], weights [n,S] -> z_out [n,S+1], idx [n,S+1];
+ * normal: z_in [n,S],   weights [n,S] -> z_out [n,S+Nf] (sorted), idx [n,Nf]. */
+NMR_API int nmr_stage_resample(nmr_handle* h, const float* rays, int64_t n, int32_t ncols, const float* z_in,
+                       const float* weights, const float* u_jitter, float* z_out, int32_t* idx,
+                       float* pts, float* var, void* stream);
+/* xyz_encoder / dirs_encoder (embedding.py:35-46, 66-84).  kind: 0 = xyz (IPE when var != NULL in
+ * mip mode, Fourier in normal mode), 1 = dirs.  out [P, dim]. */
+NMR_API int nmr_stage_encode(nmr_handle* h, int kind, const float* x, const float* var, int64_t P, float* out,
+                     void* stream);
+/* NeRF.forward (models/nerf.py:94-144): x [P, xyz+dirs+app] in the reference column order ->
+ * raw [P,4] (sigmoid rgb, raw sigma), feat [P,256] (tap at stop_layer, <0: last trunk layer). */
+NMR_API int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, float* raw,
+                  float* feat, void* stream);
+/* volume_render_radiance_field (render_utils.py:176-230) + feature / point compositing
+ * (renderer.py:250-281).  feats / pts may be NULL.  z: mip [n,S+1] | normal [n,S]. */
+NMR_API int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z, const float* rays_d, int64_t n,
+                        int32_t S, uint32_t flags, const float* feats, const float* pts, float* rgb,
+                        float* depth, float* acc, float* disp, float* weights, float* feat_out,
+                        float* pts_out, void* stream);
+
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+NMR_API int64_t nmr_launch_count(const nmr_handle* h);
+/* Milliseconds spent in the MLP kernels of the last nmr_render* call on this handle, measured with
+ * CUDA events on `stream` (0 if timing is disabled).  nmr_set_timing(h,1) enables event recording. */
+NMR_API int nmr_set_timing(nmr_handle* h, int enable);
+NMR_API int nmr_last_stage_ms(nmr_handle* h, float* sample_ms, float* mlp_ms, float* composite_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMR_H_ */

@@ -1,0 +1,751 @@
+// C ABI of libnmr.so (include/nmr.h): handle, weight packing, workspace and the orchestration of
+// NerfRenderer.render_rays (nerfmatch/nerf/renderer.py:182-295) over ray chunks.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "nmr_internal.cuh"
+#include "nmr_tc.cuh"
+
+using namespace nmr;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct StageEvent { cudaEvent_t a, b; int stage; };
+
+struct DevBuf {   // grow-only device buffer
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct nmr_handle {
+  nmr_config cfg;
+  Dims d;
+  int device = 0;
+  NetF32 net[2];
+  DevBuf wpool[2];
+  TcNet tc[2];
+  DevBuf app;
+  int num_frames = 0;
+  // workspace (per ray chunk)
+  int64_t ws_points = 0, ws_rays = 0;
+  DevBuf X, B[4], raw, zc, zf, misc, rays_view, tcws;
+  DevBuf stage[24];     // nmr_render_host staging
+  std::string err;
+  int64_t launches = 0;
+  bool timing = false;
+  std::vector<StageEvent> events;
+};
+
+#define NMR_FAIL(h, code, ...)                                   \
+  do {                                                           \
+    char _b[512];                                                \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);                       \
+    (h)->err = _b;                                               \
+    return (code);                                               \
+  } while (0)
+
+#define NMR_CUDA(h, expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) NMR_FAIL(h, NMR_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+static int check_launch(nmr_handle* h, const char* what, int count = 1) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) NMR_FAIL(h, NMR_ERR_CUDA, "launch %s: %s", what, cudaGetErrorString(e));
+  h->launches += count;
+  return NMR_OK;
+}
+#define NMR_LAUNCHED(h, what, ...)                          \
+  do {                                                      \
+    int _r = check_launch(h, what, ##__VA_ARGS__);          \
+    if (_r != NMR_OK) return _r;                            \
+  } while (0)
+
+static Dims make_dims(const nmr_config& c) {
+  Dims d{};
+  d.mip = c.embed_type == NMR_EMBED_MIP;
+  d.fx = c.xyz_num_freqs; d.fd = c.dirs_num_freqs;
+  d.xyz = 6 * d.fx + (d.mip ? 0 : 3);
+  d.xyzp = round_up(d.xyz, 16);
+  d.dirs = 6 * d.fd + 3;
+  d.app = c.app_dim;
+  d.dap = round_up(d.dirs + d.app, 16);
+  d.kx = d.xyzp + d.dap;
+  d.in_dim = d.xyz + d.dirs + d.app;
+  d.sc = c.num_pts_coarse;
+  d.nf = c.num_pts_fine;
+  d.sf = d.mip ? d.sc : d.sc + d.nf;
+  d.zc = d.mip ? d.sc + 1 : d.sc;
+  d.zf = d.mip ? d.sc + 1 : d.sf;
+  return d;
+}
+
+extern "C" int nmr_abi_version(void) { return NMR_ABI_VERSION; }
+
+extern "C" const char* nmr_last_error(const nmr_handle* h) {
+  return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int nmr_create(const nmr_config* cfg, nmr_handle** out) {
+  if (out) *out = nullptr;
+  if (!cfg || !out) { g_create_error = "nmr_create: null argument"; return NMR_ERR_INVALID; }
+  if (cfg->abi_version != NMR_ABI_VERSION) { g_create_error = "nmr_create: ABI version mismatch"; return NMR_ERR_INVALID; }
+  const nmr_config& c = *cfg;
+  if (c.hid_dim != kHid || c.layer_num != kLayers || c.skip_layer != 4) {
+    g_create_error = "nmr_create: only the shipped trunk (8 x 256, skips=[4]) is built";
+    return NMR_ERR_UNSUPPORTED;
+  }
+  if (c.embed_type != NMR_EMBED_MIP && c.embed_type != NMR_EMBED_NORMAL) { g_create_error = "nmr_create: embed_type"; return NMR_ERR_INVALID; }
+  if (c.xyz_num_freqs < 1 || c.xyz_num_freqs > 16 || c.dirs_num_freqs < 1 || c.dirs_num_freqs > 8) {
+    g_create_error = "nmr_create: xyz_num_freqs must be 1..16 and dirs_num_freqs 1..8";
+    return NMR_ERR_UNSUPPORTED;
+  }
+  if (c.app_dim != 0 && c.app_dim != 16) { g_create_error = "nmr_create: app_dim must be 0 or 16"; return NMR_ERR_UNSUPPORTED; }
+  Dims d = make_dims(c);
+  if (d.sc < 4 || d.sf > kMaxSamples || (!d.mip && d.nf < 2)) {
+    g_create_error = "nmr_create: samples per ray must satisfy 4 <= coarse and (coarse + fine) <= 256";
+    return NMR_ERR_UNSUPPORTED;
+  }
+  if (c.stop_layer_coarse >= kLayers || c.stop_layer_fine >= kLayers) { g_create_error = "nmr_create: stop_layer >= layer_num"; return NMR_ERR_INVALID; }
+  if (c.precision != NMR_PREC_FP32 && c.precision != NMR_PREC_BF16) { g_create_error = "nmr_create: precision"; return NMR_ERR_INVALID; }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    g_create_error = std::string("nmr_create: no CUDA device (") + cudaGetErrorString(e) + "); libnmr has no CPU fallback";
+    return NMR_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { g_create_error = std::string("nmr_create: ") + cudaGetErrorString(e); return NMR_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "nmr_create: libnmr is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return NMR_ERR_CUDA;
+  }
+  nmr_handle* h = new nmr_handle();
+  h->cfg = c;
+  if (h->cfg.resample_padding <= 0.f) h->cfg.resample_padding = 0.01f;
+  if (h->cfg.max_chunk_points <= 0) h->cfg.max_chunk_points = (int64_t)1 << 20;
+  h->d = d;
+  h->device = dev;
+  for (int i = 0; i < 2; ++i) { memset(&h->net[i], 0, sizeof(NetF32)); h->tc[i] = TcNet{}; }
+  *out = h;
+  return NMR_OK;
+}
+
+extern "C" void nmr_destroy(nmr_handle* h) {
+  if (!h) return;
+  for (auto& ev : h->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[i]); }
+  h->app.release(); h->X.release(); h->raw.release(); h->zc.release(); h->zf.release(); h->misc.release();
+  h->rays_view.release(); h->tcws.release();
+  for (auto& b : h->B) b.release();
+  for (auto& b : h->stage) b.release();
+  delete h;
+}
+
+extern "C" int64_t nmr_launch_count(const nmr_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int nmr_set_precision(nmr_handle* h, int precision) {
+  if (!h) return NMR_ERR_INVALID;
+  if (precision != NMR_PREC_FP32 && precision != NMR_PREC_BF16) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_set_precision: %d", precision);
+  h->cfg.precision = precision;
+  return NMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------
+static int fetch(nmr_handle* h, std::vector<float>& dst, const float* src, size_t count, const char* name) {
+  if (!src) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_set_weights: %s is NULL", name);
+  dst.resize(count);
+  NMR_CUDA(h, cudaMemcpy(dst.data(), src, count * sizeof(float), cudaMemcpyDefault));
+  return NMR_OK;
+}
+
+extern "C" int nmr_set_weights(nmr_handle* h, int which, const nmr_weight_ptrs* w) {
+  if (!h || !w) return NMR_ERR_INVALID;
+  if (which != NMR_NET_COARSE && which != NMR_NET_FINE) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_set_weights: which=%d", which);
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  const Dims& d = h->d;
+  const int skipl = h->cfg.skip_layer + 1;
+  // host-side packed pool
+  std::vector<float> pool;
+  auto alloc = [&](size_t count) { size_t off = pool.size(); pool.resize(off + ((count + 63) / 64) * 64, 0.f); return off; };
+  size_t oW[kLayers], ob[kLayers], oWsx, oWf, obf, oWa, oba, oWvf, oWvd, obv, oWr, obr;
+  std::vector<float> tmp;
+  int r;
+  HostNet hn;   // unpadded fp32 copies for the tensor-core packer
+  for (int i = 0; i < kLayers; ++i) {
+    int kin = (i == 0) ? d.xyz : (i == skipl ? d.xyz + kHid : kHid);
+    if ((r = fetch(h, tmp, w->pts_w[i], (size_t)kHid * kin, "pts_w")) != NMR_OK) return r;
+    hn.pts_w[i] = tmp;
+    if (i == 0) {
+      oW[i] = alloc((size_t)kHid * d.xyzp);
+      for (int o = 0; o < kHid; ++o) memcpy(&pool[oW[i] + (size_t)o * d.xyzp], &tmp[(size_t)o * kin], d.xyz * sizeof(float));
+    } else if (i == skipl) {
+      oWsx = alloc((size_t)kHid * d.xyzp);
+      oW[i] = alloc((size_t)kHid * kHid);
+      for (int o = 0; o < kHid; ++o) {
+        memcpy(&pool[oWsx + (size_t)o * d.xyzp], &tmp[(size_t)o * kin], d.xyz * sizeof(float));
+        memcpy(&pool[oW[i] + (size_t)o * kHid], &tmp[(size_t)o * kin + d.xyz], kHid * sizeof(float));
+      }
+    } else {
+      oW[i] = alloc((size_t)kHid * kHid);
+      memcpy(&pool[oW[i]], tmp.data(), tmp.size() * sizeof(float));
+    }
+    if ((r = fetch(h, tmp, w->pts_b[i], kHid, "pts_b")) != NMR_OK) return r;
+    hn.pts_b[i] = tmp;
+    ob[i] = alloc(kHid);
+    memcpy(&pool[ob[i]], tmp.data(), kHid * sizeof(float));
+  }
+  if ((r = fetch(h, tmp, w->feature_w, (size_t)kHid * kHid, "feature_w")) != NMR_OK) return r;
+  hn.feature_w = tmp;
+  oWf = alloc(tmp.size()); memcpy(&pool[oWf], tmp.data(), tmp.size() * sizeof(float));
+  if ((r = fetch(h, tmp, w->feature_b, kHid, "feature_b")) != NMR_OK) return r;
+  hn.feature_b = tmp;
+  obf = alloc(kHid); memcpy(&pool[obf], tmp.data(), kHid * sizeof(float));
+  if ((r = fetch(h, tmp, w->alpha_w, kHid, "alpha_w")) != NMR_OK) return r;
+  hn.alpha_w = tmp;
+  oWa = alloc(kHid); memcpy(&pool[oWa], tmp.data(), kHid * sizeof(float));
+  if ((r = fetch(h, tmp, w->alpha_b, 1, "alpha_b")) != NMR_OK) return r;
+  hn.alpha_b = tmp;
+  oba = alloc(1); pool[oba] = tmp[0];
+  const int vin = kHid + d.dirs + d.app;
+  if ((r = fetch(h, tmp, w->views_w, (size_t)kHalf * vin, "views_w")) != NMR_OK) return r;
+  hn.views_w = tmp;
+  oWvf = alloc((size_t)kHalf * kHid);
+  oWvd = alloc((size_t)kHalf * d.dap);
+  for (int o = 0; o < kHalf; ++o) {
+    memcpy(&pool[oWvf + (size_t)o * kHid], &tmp[(size_t)o * vin], kHid * sizeof(float));
+    memcpy(&pool[oWvd + (size_t)o * d.dap], &tmp[(size_t)o * vin + kHid], (d.dirs + d.app) * sizeof(float));
+  }
+  if ((r = fetch(h, tmp, w->views_b, kHalf, "views_b")) != NMR_OK) return r;
+  hn.views_b = tmp;
+  obv = alloc(kHalf); memcpy(&pool[obv], tmp.data(), kHalf * sizeof(float));
+  if ((r = fetch(h, tmp, w->rgb_w, 3 * kHalf, "rgb_w")) != NMR_OK) return r;
+  hn.rgb_w = tmp;
+  oWr = alloc(3 * kHalf); memcpy(&pool[oWr], tmp.data(), 3 * kHalf * sizeof(float));
+  if ((r = fetch(h, tmp, w->rgb_b, 3, "rgb_b")) != NMR_OK) return r;
+  hn.rgb_b = tmp;
+  obr = alloc(4); memcpy(&pool[obr], tmp.data(), 3 * sizeof(float));
+
+  NMR_CUDA(h, h->wpool[which].reserve(pool.size() * sizeof(float)));
+  float* base = (float*)h->wpool[which].p;
+  NMR_CUDA(h, cudaMemcpy(base, pool.data(), pool.size() * sizeof(float), cudaMemcpyHostToDevice));
+  NetF32& n = h->net[which];
+  for (int i = 0; i < kLayers; ++i) { n.W[i] = base + oW[i]; n.b[i] = base + ob[i]; }
+  n.Wskip_x = base + oWsx;
+  n.Wfeat = base + oWf; n.bfeat = base + obf; n.Walpha = base + oWa; n.balpha = base + oba;
+  n.Wview_f = base + oWvf; n.Wview_d = base + oWvd; n.bview = base + obv; n.Wrgb = base + oWr; n.brgb = base + obr;
+  n.set = true;
+  // bf16 UMMA-major tiles for the tcgen05 path
+  std::string terr;
+  if (tc_pack_net(h->d, h->cfg.skip_layer, hn, &h->tc[which], &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_pack_net: %s", terr.c_str());
+  return NMR_OK;
+}
+
+extern "C" int nmr_set_appearance(nmr_handle* h, const float* table, int32_t num_frames) {
+  if (!h) return NMR_ERR_INVALID;
+  if (h->d.app == 0) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_set_appearance: handle was created with app_dim = 0");
+  if (!table || num_frames <= 0) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_set_appearance: empty table");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  size_t bytes = (size_t)num_frames * h->d.app * sizeof(float);
+  NMR_CUDA(h, h->app.reserve(bytes));
+  NMR_CUDA(h, cudaMemcpy(h->app.p, table, bytes, cudaMemcpyDefault));
+  h->num_frames = num_frames;
+  return NMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace
+// ------------------------------------------------------------------------------------------
+static int ensure_workspace(nmr_handle* h, int64_t rays, int64_t points) {
+  const Dims& d = h->d;
+  if (points > h->ws_points) {
+    NMR_CUDA(h, h->X.reserve((size_t)points * d.kx * sizeof(float)));
+    for (auto& b : h->B) NMR_CUDA(h, b.reserve((size_t)points * kHid * sizeof(float)));
+    NMR_CUDA(h, h->raw.reserve((size_t)points * 4 * sizeof(float)));
+    h->ws_points = points;
+  }
+  if (rays > h->ws_rays) {
+    NMR_CUDA(h, h->zc.reserve((size_t)rays * (d.zc + 1) * sizeof(float)));
+    NMR_CUDA(h, h->zf.reserve((size_t)rays * (d.zf + 1) * sizeof(float)));
+    h->ws_rays = rays;
+  }
+  NMR_CUDA(h, h->misc.reserve(256));
+  return NMR_OK;
+}
+
+static void stage_begin(nmr_handle* h, int stage, cudaStream_t s) {
+  if (!h->timing) return;
+  StageEvent ev; ev.stage = stage;
+  cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+  cudaEventRecord(ev.a, s);
+  h->events.push_back(ev);
+}
+static void stage_end(nmr_handle* h, cudaStream_t s) {
+  if (!h->timing) return;
+  cudaEventRecord(h->events.back().b, s);
+}
+
+extern "C" int nmr_set_timing(nmr_handle* h, int enable) {
+  if (!h) return NMR_ERR_INVALID;
+  h->timing = enable != 0;
+  return NMR_OK;
+}
+
+extern "C" int nmr_last_stage_ms(nmr_handle* h, float* sample_ms, float* mlp_ms, float* composite_ms) {
+  if (!h) return NMR_ERR_INVALID;
+  float acc[3] = {0, 0, 0};
+  for (auto& ev : h->events) {
+    NMR_CUDA(h, cudaEventSynchronize(ev.b));
+    float ms = 0;
+    NMR_CUDA(h, cudaEventElapsedTime(&ms, ev.a, ev.b));
+    acc[ev.stage] += ms;
+    cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+  }
+  h->events.clear();
+  if (sample_ms) *sample_ms = acc[0];
+  if (mlp_ms) *mlp_ms = acc[1];
+  if (composite_ms) *composite_ms = acc[2];
+  return NMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the fp32 MLP: NeRF.forward (models/nerf.py:94-144) as a chain of SIMT GEMMs
+// ------------------------------------------------------------------------------------------
+// X: padded input rows [P,kx].  Returns the buffer that holds the tapped features in *feat.
+static int mlp_fp32(nmr_handle* h, int which, const float* X, int64_t P, int stop_layer, float* raw,
+                    const float** feat, cudaStream_t s) {
+  const Dims& d = h->d;
+  const NetF32& n = h->net[which];
+  const int skipl = h->cfg.skip_layer + 1;
+  float* bufs[4] = {(float*)h->B[0].p, (float*)h->B[1].p, (float*)h->B[2].p, (float*)h->B[3].p};
+  const float* in = X; int lda = d.kx;
+  const float* tap = nullptr;
+  auto pick = [&](const float* a, const float* b) -> float* {
+    for (float* c : bufs) if (c != a && c != b) return c;
+    return nullptr;
+  };
+  for (int i = 0; i < kLayers; ++i) {
+    float* out = pick(in, tap);
+    GemmParams g{};
+    if (i == skipl) {
+      g.A1 = X; g.lda1 = d.kx; g.W1 = n.Wskip_x; g.K1 = d.xyzp;
+      g.A2 = in; g.lda2 = lda; g.W2 = n.W[i]; g.K2 = kHid;
+    } else {
+      g.A1 = in; g.lda1 = lda; g.W1 = n.W[i]; g.K1 = (i == 0) ? d.xyzp : kHid;
+    }
+    g.bias = n.b[i]; g.C = out; g.ldc = kHid; g.M = P; g.N = kHid; g.act = 1;
+    launch_sgemm(g, s);
+    NMR_LAUNCHED(h, "sgemm trunk");
+    in = out; lda = kHid;
+    if (i == stop_layer) tap = out;
+  }
+  if (stop_layer < 0) tap = in;   // pt_feat = last trunk activation (models/nerf.py:107, 134-141)
+  {  // alpha_linear -> raw[:,3]
+    GemmParams g{};
+    g.A1 = in; g.lda1 = kHid; g.W1 = n.Walpha; g.K1 = kHid; g.bias = n.balpha;
+    g.C = raw + 3; g.ldc = 4; g.M = P; g.N = 1; g.act = 0;
+    launch_sgemm(g, s);
+    NMR_LAUNCHED(h, "alpha head");
+  }
+  float* F = pick(in, tap);
+  {  // feature_linear (no activation)
+    GemmParams g{};
+    g.A1 = in; g.lda1 = kHid; g.W1 = n.Wfeat; g.K1 = kHid; g.bias = n.bfeat;
+    g.C = F; g.ldc = kHid; g.M = P; g.N = kHid; g.act = 0;
+    launch_sgemm(g, s);
+    NMR_LAUNCHED(h, "feature_linear");
+  }
+  float* V = pick(F, tap);
+  {  // views_linears.0 on [feature | dirs | app] + ReLU
+    GemmParams g{};
+    g.A1 = F; g.lda1 = kHid; g.W1 = n.Wview_f; g.K1 = kHid;
+    g.A2 = X + d.xyzp; g.lda2 = d.kx; g.W2 = n.Wview_d; g.K2 = d.dap;
+    g.bias = n.bview; g.C = V; g.ldc = kHalf; g.M = P; g.N = kHalf; g.act = 1;
+    launch_sgemm(g, s);
+    NMR_LAUNCHED(h, "views_linear");
+  }
+  {  // rgb_linear + sigmoid -> raw[:,0:3]
+    GemmParams g{};
+    g.A1 = V; g.lda1 = kHalf; g.W1 = n.Wrgb; g.K1 = kHalf; g.bias = n.brgb;
+    g.C = raw; g.ldc = 4; g.M = P; g.N = 3; g.act = 2;
+    launch_sgemm(g, s);
+    NMR_LAUNCHED(h, "rgb head");
+  }
+  *feat = tap;
+  return NMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// render
+// ------------------------------------------------------------------------------------------
+static int validate_render(nmr_handle* h, const nmr_render_args* a) {
+  if (!a) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: args is NULL");
+  if (a->n < 0) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: n < 0");
+  if (a->n > 0 && !a->rays) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: rays is NULL");
+  if (a->ncols < 8) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: rays need at least 8 columns (o, d, near, far), got %d", a->ncols);
+  if (h->d.mip && a->ncols < 12) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: mip rays need 12 columns (radius in column 11), got %d", a->ncols);
+  if (!h->net[0].set || !h->net[1].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_render: weights of both nets must be set first");
+  if (h->d.app > 0 && h->num_frames == 0) NMR_FAIL(h, NMR_ERR_STATE, "nmr_render: appearance table not set");
+  if (a->pt3d && !a->unnorm) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: pt3d requested without unnorm");
+  return NMR_OK;
+}
+
+static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s) {
+  int r = validate_render(h, a);
+  if (r != NMR_OK) return r;
+  if (a->n == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  const Dims& d = h->d;
+  const nmr_config& c = h->cfg;
+  const bool bf16 = c.precision == NMR_PREC_BF16;
+  const int smax = std::max(d.sc, d.sf);
+  int64_t chunk_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, c.max_chunk_points / smax));
+  if (bf16) chunk_rays = tc_round_chunk_rays(d, chunk_rays, a->n);
+  if ((r = ensure_workspace(h, chunk_rays, bf16 ? 0 : chunk_rays * smax)) != NMR_OK) return r;
+  if (bf16) {
+    std::string terr;
+    if (tc_ensure_workspace(d, chunk_rays, &h->tcws.p, &h->tcws.cap, &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc workspace: %s", terr.c_str());
+  }
+  const bool pfeat = (a->flags & NMR_FLAG_RET_PFEAT) != 0;
+  float* zc = (float*)h->zc.p;
+  float* zf = (float*)h->zf.p;
+  float* X = (float*)h->X.p;
+  float* raw = (float*)h->raw.p;
+  const float* app_table = (const float*)h->app.p;
+
+  for (int64_t r0 = 0; r0 < a->n; r0 += chunk_rays) {
+    const int64_t nr = std::min<int64_t>(chunk_rays, a->n - r0);
+    const float* rays = a->rays + r0 * a->ncols;
+    const int64_t* rid = a->ray_id ? a->ray_id + r0 : nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+      const int S = pass == 0 ? d.sc : d.sf;
+      const int nz = pass == 0 ? d.zc : d.zf;
+      float* z = pass == 0 ? zc : zf;
+      const int stop = pass == 0 ? c.stop_layer_coarse : c.stop_layer_fine;
+      // ---- sampling + encoding (kernel a) ----
+      stage_begin(h, 0, s);
+      if (pass == 0) {
+        SampleParams sp{};
+        sp.rays = rays; sp.n = nr; sp.ncols = a->ncols; sp.ray0 = r0; sp.S = d.sc; sp.mip = d.mip; sp.use_disp = c.use_disp;
+        sp.t_rand = a->t_rand ? a->t_rand + r0 * (d.sc + 1) : nullptr;
+        sp.rng_mode = a->rng_mode; sp.seed = a->seed; sp.z = zc;
+        launch_sample_coarse(sp, s);
+        NMR_LAUNCHED(h, "sample_coarse");
+      }
+      const float* feat = nullptr; int feat_bf16 = 0;
+      float* raw_pass = raw;
+      if (!bf16) {
+        EncodeParams ep{};
+        ep.rays = rays; ep.n = nr; ep.ncols = a->ncols; ep.S = S; ep.d = d; ep.var_scale = c.mip_var_scale;
+        ep.z = z; ep.ray_id = rid; ep.app_table = app_table; ep.num_frames = h->num_frames; ep.X = X;
+        launch_encode(ep, s);
+        NMR_LAUNCHED(h, "encode");
+        stage_end(h, s);
+        // ---- MLP (kernel b, fp32 reference-precision variant) ----
+        stage_begin(h, 1, s);
+        if ((r = mlp_fp32(h, pass, X, nr * S, stop, raw, &feat, s)) != NMR_OK) return r;
+        stage_end(h, s);
+      } else {
+        stage_end(h, s);
+        stage_begin(h, 1, s);
+        TcRun tr{};
+        tr.rays = rays; tr.n = nr; tr.ncols = a->ncols; tr.S = S; tr.z = z; tr.ray_id = rid;
+        tr.app_table = app_table; tr.num_frames = h->num_frames; tr.var_scale = c.mip_var_scale;
+        tr.stop_layer = stop; tr.want_feat = pfeat; tr.ws = h->tcws.p;
+        std::string terr; int nl = 0;
+        if (tc_run(d, h->tc[pass], tr, &raw_pass, (const void**)&feat, &nl, s, &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_run: %s", terr.c_str());
+        NMR_LAUNCHED(h, "tcgen05 mlp", nl);
+        feat_bf16 = 1;
+        stage_end(h, s);
+      }
+      // ---- volume rendering + compositing (+ fused re-sampling after the coarse pass) (kernel c) ----
+      stage_begin(h, 2, s);
+      CompositeParams cp{};
+      cp.raw = raw_pass; cp.z = z; cp.rays = rays; cp.ncols = a->ncols; cp.n = nr; cp.S = S; cp.mip = d.mip;
+      cp.flags = a->flags;
+      const bool want_feat = pfeat && (pass == 1 ? a->feat_fine != nullptr
+                                                 : (a->feat_coarse != nullptr && !(a->flags & NMR_FLAG_SKIP_COARSE_FEAT)));
+      cp.feats = want_feat ? feat : nullptr; cp.feats_bf16 = feat_bf16;
+      float* fo = pass == 0 ? a->feat_coarse : a->feat_fine;
+      cp.feat_out = (want_feat && fo) ? fo + r0 * kHid : nullptr;
+      float* po = pass == 0 ? a->pts_coarse : a->pts_fine;
+      cp.pts_out = po ? po + r0 * 3 : nullptr;
+      float* ro = pass == 0 ? a->rgb_coarse : a->rgb_fine;
+      cp.rgb = ro ? ro + r0 * 3 : nullptr;
+      float* dp = pass == 0 ? a->depth_coarse : a->depth_fine;
+      cp.depth = dp ? dp + r0 : nullptr;
+      float* wo = pass == 0 ? a->weights_coarse : a->weights_fine;
+      cp.weights = wo ? wo + r0 * S : nullptr;
+      if (pass == 1 && a->pt3d && a->unnorm) {
+        cp.pt3d = a->pt3d + r0 * 3; cp.has_unnorm = 1;
+        memcpy(cp.unnorm, a->unnorm, 12 * sizeof(float));
+      }
+      if (pass == 0) {
+        cp.z_next = zf; cp.nf = d.nf; cp.resample_padding = c.resample_padding;
+        cp.idx_out = a->idx_fine ? a->idx_fine + r0 * (d.mip ? d.sc + 1 : d.nf) : nullptr;
+        cp.u_jitter = a->u_jitter ? a->u_jitter + r0 * (d.sc + 1) : nullptr;
+        cp.rng_mode = a->rng_mode; cp.seed = a->seed; cp.ray0 = r0;
+      }
+      launch_composite(cp, s);
+      NMR_LAUNCHED(h, "composite");
+      stage_end(h, s);
+      // ---- optional intermediates for the parity tests ----
+      float* zo = pass == 0 ? a->z_coarse : a->z_fine;
+      if (zo) NMR_CUDA(h, cudaMemcpyAsync(zo + r0 * nz, z, (size_t)nr * nz * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      float* rawo = pass == 0 ? a->raw_coarse : a->raw_fine;
+      if (rawo) NMR_CUDA(h, cudaMemcpyAsync(rawo + r0 * S * 4, raw_pass, (size_t)nr * S * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  return NMR_OK;
+}
+
+extern "C" int nmr_render(nmr_handle* h, const nmr_render_args* args, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  return render_device(h, args, (cudaStream_t)stream);
+}
+
+static void invert3x3(const float* K, float* out) {
+  double a = K[0], b = K[1], c = K[2], d = K[3], e = K[4], f = K[5], g = K[6], hh = K[7], i = K[8];
+  double A = e * i - f * hh, B = -(d * i - f * g), C = d * hh - e * g;
+  double det = a * A + b * B + c * C;
+  double inv[9] = {A, -(b * i - c * hh), b * f - c * e, B, a * i - c * g, -(a * f - c * d), C, -(a * hh - b * g), a * e - b * d};
+  for (int k = 0; k < 9; ++k) out[k] = (float)(inv[k] / det);
+}
+
+extern "C" int nmr_raygen(nmr_handle* h, const float* K, const float* c2w, int32_t H, int32_t W, int32_t ds,
+                          float* rays_dev, int32_t* far_fallback, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!K || !c2w || !rays_dev) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_raygen: null argument");
+  if (H < 3 || W < 1 || ds < 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_raygen: need H >= 3, W >= 1, ds >= 1");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  NMR_CUDA(h, h->misc.reserve(256));
+  RayGenParams p{};
+  invert3x3(K, p.kinv);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) p.rot[3 * i + j] = c2w[4 * i + j];
+    p.org[i] = c2w[4 * i + 3];
+  }
+  p.H = H; p.W = W; p.ds = ds; p.mip = h->d.mip;
+  p.h = (H - ds / 2 + ds - 1) / ds; p.w = (W - ds / 2 + ds - 1) / ds;   // len(range(ds//2, H, ds))
+  p.rays = rays_dev; p.miss_flag = (int*)h->misc.p;
+  NMR_CUDA(h, cudaMemsetAsync(p.miss_flag, 0, sizeof(int), s));
+  launch_raygen(p, s);
+  NMR_LAUNCHED(h, "raygen");
+  launch_far_fallback(rays_dev, (int64_t)p.h * p.w, h->d.mip ? 12 : 11, p.miss_flag, s);
+  NMR_LAUNCHED(h, "far_fallback");
+  if (far_fallback) {
+    NMR_CUDA(h, cudaMemcpyAsync(far_fallback, p.miss_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NMR_CUDA(h, cudaStreamSynchronize(s));
+  }
+  return NMR_OK;
+}
+
+extern "C" int nmr_render_view(nmr_handle* h, const float* K, const float* c2w, int32_t H, int32_t W, int32_t ds,
+                               const nmr_render_args* args, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!args) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render_view: args is NULL");
+  if (ds < 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render_view: ds < 1");
+  const int hh = (H - ds / 2 + ds - 1) / ds, ww = (W - ds / 2 + ds - 1) / ds;
+  const int ncols = h->d.mip ? 12 : 11;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  NMR_CUDA(h, h->rays_view.reserve((size_t)hh * ww * ncols * sizeof(float)));
+  int r = nmr_raygen(h, K, c2w, H, W, ds, (float*)h->rays_view.p, nullptr, stream);
+  if (r != NMR_OK) return r;
+  nmr_render_args a = *args;
+  a.rays = (const float*)h->rays_view.p; a.n = (int64_t)hh * ww; a.ncols = ncols;
+  return render_device(h, &a, (cudaStream_t)stream);
+}
+
+// host-buffer entry: H2D rays (+ optional draws / ids), render, D2H outputs, synchronise.
+extern "C" int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!args) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render_host: args is NULL");
+  if (args->n < 0 || (args->n > 0 && !args->rays)) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render_host: bad rays");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dims& d = h->d;
+  const int64_t n = args->n;
+  nmr_render_args a = *args;
+  int slot = 0;
+  struct Out { void* host; void* dev; size_t bytes; };
+  std::vector<Out> outs;
+  auto in = [&](const void* host, size_t bytes) -> void* {
+    DevBuf& b = h->stage[slot++];
+    if (!host || bytes == 0) return nullptr;
+    if (b.reserve(bytes) != cudaSuccess) return nullptr;
+    cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, s);
+    return b.p;
+  };
+  auto out = [&](void* host, size_t bytes) -> void* {
+    DevBuf& b = h->stage[slot++];
+    if (!host || bytes == 0) return nullptr;
+    if (b.reserve(bytes) != cudaSuccess) return nullptr;
+    outs.push_back({host, b.p, bytes});
+    return b.p;
+  };
+  const size_t f = sizeof(float);
+  a.rays = (const float*)in(args->rays, (size_t)n * args->ncols * f);
+  a.ray_id = (const int64_t*)in(args->ray_id, (size_t)n * sizeof(int64_t));
+  a.t_rand = (const float*)in(args->t_rand, (size_t)n * (d.sc + 1) * f);
+  a.u_jitter = (const float*)in(args->u_jitter, (size_t)n * (d.sc + 1) * f);
+  a.feat_coarse = (float*)out(args->feat_coarse, (size_t)n * kHid * f);
+  a.feat_fine = (float*)out(args->feat_fine, (size_t)n * kHid * f);
+  a.pts_coarse = (float*)out(args->pts_coarse, (size_t)n * 3 * f);
+  a.pts_fine = (float*)out(args->pts_fine, (size_t)n * 3 * f);
+  a.rgb_coarse = (float*)out(args->rgb_coarse, (size_t)n * 3 * f);
+  a.rgb_fine = (float*)out(args->rgb_fine, (size_t)n * 3 * f);
+  a.depth_coarse = (float*)out(args->depth_coarse, (size_t)n * f);
+  a.depth_fine = (float*)out(args->depth_fine, (size_t)n * f);
+  a.pt3d = (float*)out(args->pt3d, (size_t)n * 3 * f);
+  a.z_coarse = (float*)out(args->z_coarse, (size_t)n * d.zc * f);
+  a.z_fine = (float*)out(args->z_fine, (size_t)n * d.zf * f);
+  a.weights_coarse = (float*)out(args->weights_coarse, (size_t)n * d.sc * f);
+  a.weights_fine = (float*)out(args->weights_fine, (size_t)n * d.sf * f);
+  a.raw_coarse = (float*)out(args->raw_coarse, (size_t)n * d.sc * 4 * f);
+  a.raw_fine = (float*)out(args->raw_fine, (size_t)n * d.sf * 4 * f);
+  a.idx_fine = (int32_t*)out(args->idx_fine, (size_t)n * (d.mip ? d.sc + 1 : d.nf) * sizeof(int32_t));
+  NMR_CUDA(h, cudaGetLastError());
+  if (n > 0 && !a.rays) NMR_FAIL(h, NMR_ERR_CUDA, "nmr_render_host: staging allocation failed");
+  int r = render_device(h, &a, s);
+  if (r != NMR_OK) return r;
+  for (auto& o : outs) NMR_CUDA(h, cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, s));
+  NMR_CUDA(h, cudaStreamSynchronize(s));
+  return NMR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage entry points
+// ------------------------------------------------------------------------------------------
+extern "C" int nmr_stage_sample_coarse(nmr_handle* h, const float* rays, int64_t n, int32_t ncols, const float* t_rand,
+                                       float* z, float* pts, float* var, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!rays || !z))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_sample_coarse: null argument");
+  if (ncols < 8 || (h->d.mip && ncols < 12)) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_sample_coarse: ncols=%d", ncols);
+  if (n == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dims& d = h->d;
+  SampleParams sp{};
+  sp.rays = rays; sp.n = n; sp.ncols = ncols; sp.S = d.sc; sp.mip = d.mip; sp.use_disp = h->cfg.use_disp;
+  sp.t_rand = t_rand; sp.rng_mode = NMR_RNG_NONE; sp.z = z;
+  launch_sample_coarse(sp, s);
+  NMR_LAUNCHED(h, "sample_coarse");
+  if (pts || var) {
+    PointsParams pp{};
+    pp.rays = rays; pp.n = n; pp.ncols = ncols; pp.S = d.sc; pp.mip = d.mip; pp.var_scale = h->cfg.mip_var_scale;
+    pp.z = z; pp.pts = pts; pp.var = var;
+    launch_points(pp, s);
+    NMR_LAUNCHED(h, "points");
+  }
+  return NMR_OK;
+}
+
+extern "C" int nmr_stage_resample(nmr_handle* h, const float* rays, int64_t n, int32_t ncols, const float* z_in,
+                                  const float* weights, const float* u_jitter, float* z_out, int32_t* idx,
+                                  float* pts, float* var, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!rays || !z_in || !weights || !z_out))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_resample: null argument");
+  if (ncols < 8 || (h->d.mip && ncols < 12)) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_resample: ncols=%d", ncols);
+  if (n == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dims& d = h->d;
+  CompositeParams cp{};
+  cp.z = z_in; cp.rays = rays; cp.ncols = ncols; cp.n = n; cp.S = d.sc; cp.mip = d.mip;
+  cp.weights_in = weights; cp.z_next = z_out; cp.idx_out = idx; cp.nf = d.nf;
+  cp.u_jitter = u_jitter; cp.rng_mode = NMR_RNG_NONE; cp.resample_padding = h->cfg.resample_padding;
+  launch_composite(cp, s);
+  NMR_LAUNCHED(h, "resample");
+  if (pts || var) {
+    PointsParams pp{};
+    pp.rays = rays; pp.n = n; pp.ncols = ncols; pp.S = d.sf; pp.mip = d.mip; pp.var_scale = h->cfg.mip_var_scale;
+    pp.z = z_out; pp.pts = pts; pp.var = var;
+    launch_points(pp, s);
+    NMR_LAUNCHED(h, "points");
+  }
+  return NMR_OK;
+}
+
+extern "C" int nmr_stage_encode(nmr_handle* h, int kind, const float* x, const float* var, int64_t P, float* out,
+                                void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (P < 0 || (P > 0 && (!x || !out)) || (kind != 0 && kind != 1)) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_encode: bad argument");
+  if (P == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  launch_encode_stage(kind, h->d, x, var, P, out, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "encode_stage");
+  return NMR_OK;
+}
+
+extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, float* raw,
+                             float* feat, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (which != 0 && which != 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp: which=%d", which);
+  if (P < 0 || (P > 0 && (!x || !raw))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp: null argument");
+  if (stop_layer >= kLayers) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp: stop_layer=%d", stop_layer);
+  if (!h->net[which].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_stage_mlp: weights not set");
+  if (P == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dims& d = h->d;
+  const int64_t chunk = std::min<int64_t>(P, h->cfg.max_chunk_points);
+  int r;
+  if ((r = ensure_workspace(h, 1, chunk)) != NMR_OK) return r;
+  for (int64_t p0 = 0; p0 < P; p0 += chunk) {
+    const int64_t np = std::min<int64_t>(chunk, P - p0);
+    launch_repack_input(d, x + p0 * d.in_dim, np, (float*)h->X.p, s);
+    NMR_LAUNCHED(h, "repack_input");
+    const float* tap = nullptr;
+    if (h->cfg.precision == NMR_PREC_BF16) {
+      std::string terr; int nl = 0;
+      if (tc_run_rows(d, h->tc[which], (const float*)h->X.p, np, stop_layer, raw + p0 * 4, feat ? feat + p0 * kHid : nullptr,
+                      &h->tcws.p, &h->tcws.cap, &nl, s, &terr) != 0)
+        NMR_FAIL(h, NMR_ERR_CUDA, "tc_run_rows: %s", terr.c_str());
+      NMR_LAUNCHED(h, "tcgen05 mlp rows", nl);
+    } else {
+      if ((r = mlp_fp32(h, which, (const float*)h->X.p, np, stop_layer, (float*)h->raw.p, &tap, s)) != NMR_OK) return r;
+      NMR_CUDA(h, cudaMemcpyAsync(raw + p0 * 4, h->raw.p, (size_t)np * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      if (feat) NMR_CUDA(h, cudaMemcpyAsync(feat + p0 * kHid, tap, (size_t)np * kHid * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  return NMR_OK;
+}
+
+extern "C" int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z, const float* rays_d, int64_t n,
+                                   int32_t S, uint32_t flags, const float* feats, const float* pts, float* rgb,
+                                   float* depth, float* acc, float* disp, float* weights, float* feat_out,
+                                   float* pts_out, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!raw || !z || !rays_d))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_composite: null argument");
+  if (S < 2 || S > kMaxSamples) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_composite: S=%d (2..%d)", S, kMaxSamples);
+  if (pts_out && !pts) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_composite: pts_out needs pts");
+  if (n == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  CompositeParams cp{};
+  cp.raw = raw; cp.z = z; cp.rays = nullptr; cp.rays_d = rays_d; cp.n = n; cp.S = S; cp.mip = h->d.mip; cp.flags = flags;
+  cp.feats = feats; cp.feats_bf16 = 0; cp.pts_in = pts;
+  cp.rgb = rgb; cp.depth = depth; cp.acc = acc; cp.disp = disp; cp.weights = weights;
+  cp.feat_out = feats ? feat_out : nullptr; cp.pts_out = pts_out;
+  launch_composite(cp, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "composite");
+  return NMR_OK;
+}

@@ -1,0 +1,357 @@
+// Kernel (c): warp-per-ray volume rendering, feature / depth / point compositing and the fused
+// hierarchical re-sampling (CDF inversion) for the next pass.  Compiled with -fmad=false.
+//
+// Reference behaviour restated here:
+//   nerfmatch/nerf/render_utils.py:176-230   volume_render_radiance_field
+//   nerfmatch/nerf/renderer.py:250-281       feature / point compositing ("lin" | "max")
+//   nerfmatch/nerf/render_utils.py:453-552, 555-615  mip resampling (blur, pdf, cdf, find_interval)
+//   nerfmatch/nerf/render_utils.py:132-148, 233-264  classic sample_pdf + sort
+//   nerfmatch/utils/geometry.py:76-85        unnormaliz_pts
+//
+// One warp owns one ray.  The S samples of the ray live in shared memory; the feature rows
+// ([S,256] fp32 or bf16, the only large read) are streamed with 16-byte loads, 8 channels per
+// lane, several rows in flight.  Scans that feed the CDF are done the way torch's CPU kernels do
+// them (sequential, float64 accumulator, each prefix rounded to fp32) so that interval indices are
+// bit-identical to the oracle; the 0.1 us this costs per ray is invisible next to the MLP.
+#include "nmr_internal.cuh"
+
+namespace nmr {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kSmemPerWarp = 4 * (kMaxSamples + 8);   // floats: w, z, cdf/aux, tmp
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void frustum_tmean(float t0, float t1, float* t_mean) {
+  float mu = (t0 + t1) / 2.0f, hw = (t1 - t0) / 2.0f;
+  float mu2 = mu * mu, hw2 = hw * hw;
+  float denom = fmaxf(kEps32, 3.0f * mu2 + hw2);
+  *t_mean = mu + (2.0f * mu * hw2) / denom;
+}
+
+// number of entries of the non-decreasing table a[0..n) that are <= u  (searchsorted right=True)
+__device__ __forceinline__ int upper_bound(const float* a, int n, float u) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] <= u) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ void accum8_bf16(float acc[8], uint4 v, float w) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
+    acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+  }
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(CompositeParams p) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (ray >= p.n) return;
+  float* sw = smem + warp * kSmemPerWarp;        // weights
+  float* sz = sw + (kMaxSamples + 8);            // z / t fence posts
+  float* sa = sz + (kMaxSamples + 8);            // alpha, then pdf / cdf
+  float* st = sa + (kMaxSamples + 8);            // transmittance terms, then scratch
+  const int S = p.S;
+  const int nz = p.mip ? S + 1 : S;
+
+  const float* r = p.rays ? p.rays + ray * p.ncols : nullptr;
+  float o[3] = {0.f, 0.f, 0.f}, d[3];
+  if (r) {
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+    d[0] = r[3]; d[1] = r[4]; d[2] = r[5];
+  } else {
+    d[0] = p.rays_d[ray * 3]; d[1] = p.rays_d[ray * 3 + 1]; d[2] = p.rays_d[ray * 3 + 2];
+  }
+  for (int j = lane; j < nz; j += 32) sz[j] = p.z[ray * nz + j];
+  __syncwarp();
+
+  if (p.weights_in == nullptr) {
+    // ---- alpha and the exclusive transmittance product ------------------------------------
+    const float dnorm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    for (int s = lane; s < S; s += 32) {
+      float sigma = fmaxf(p.raw[(ray * S + s) * 4 + 3], 0.0f);
+      float dist = (p.mip || s < S - 1) ? (sz[s + 1] - sz[s]) : 1e10f;
+      dist = dist * dnorm;
+      float alpha = 1.0f - expf(-sigma * dist);
+      sa[s] = alpha;
+      st[s] = 1.0f - alpha + 1e-10f;
+    }
+    __syncwarp();
+    // cumprod as torch's CPU kernel: float64 running product, each prefix rounded to fp32.
+    const int seg = (S + 31) / 32;
+    const int s0 = min(S, lane * seg), s1 = min(S, s0 + seg);
+    double prod = 1.0;
+    for (int s = s0; s < s1; ++s) prod *= (double)st[s];
+    double incl = prod;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      double up = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl *= up;
+    }
+    double run = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) run = 1.0;
+    for (int s = s0; s < s1; ++s) {
+      sw[s] = sa[s] * (float)run;
+      run *= (double)st[s];
+    }
+    __syncwarp();
+  } else {
+    for (int s = lane; s < S; s += 32) sw[s] = p.weights_in[ray * S + s];
+    __syncwarp();
+  }
+
+  const bool render = (p.weights_in == nullptr);
+  if (render) {
+    // ---- rgb / depth / acc / points ----------------------------------------------------------
+    float acc = 0.f, dep = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    float best = -1.0f; int besti = 0x7fffffff;
+    for (int s = lane; s < S; s += 32) {
+      float w = sw[s];
+      const float* rw = p.raw + (ray * S + s) * 4;
+      float zmid = p.mip ? 0.5f * (sz[s] + sz[s + 1]) : sz[s];
+      acc += w; dep += w * zmid;
+      c0 += w * rw[0]; c1 += w * rw[1]; c2 += w * rw[2];
+      if (p.pts_out || p.pt3d) {
+        float q[3];
+        if (p.pts_in) {
+          const float* pi = p.pts_in + (ray * S + s) * 3;
+          q[0] = pi[0]; q[1] = pi[1]; q[2] = pi[2];
+        } else {
+          float t;
+          if (p.mip) frustum_tmean(sz[s], sz[s + 1], &t); else t = sz[s];
+          q[0] = p.mip ? d[0] * t + o[0] : o[0] + d[0] * t;
+          q[1] = p.mip ? d[1] * t + o[1] : o[1] + d[1] * t;
+          q[2] = p.mip ? d[2] * t + o[2] : o[2] + d[2] * t;
+        }
+        p0 += w * q[0]; p1 += w * q[1]; p2 += w * q[2];
+      }
+      if (w > best) { best = w; besti = s; }
+    }
+    acc = warp_sum(acc); dep = warp_sum(dep);
+    c0 = warp_sum(c0); c1 = warp_sum(c1); c2 = warp_sum(c2);
+    p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
+    const bool fmax = (p.flags & NMR_FLAG_FEAT_MAX) != 0;
+    if (fmax) {
+      // first index of the maximum weight (torch.max(dim) on CPU returns the first occurrence)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, off);
+        int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+        if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+      }
+      if (besti >= S) besti = 0;
+      if (p.pts_out || p.pt3d) {
+        if (p.pts_in) {
+          const float* pi = p.pts_in + (ray * S + besti) * 3;
+          p0 = pi[0]; p1 = pi[1]; p2 = pi[2];
+        } else {
+          float t;
+          if (p.mip) frustum_tmean(sz[besti], sz[besti + 1], &t); else t = sz[besti];
+          p0 = p.mip ? d[0] * t + o[0] : o[0] + d[0] * t;
+          p1 = p.mip ? d[1] * t + o[1] : o[1] + d[1] * t;
+          p2 = p.mip ? d[2] * t + o[2] : o[2] + d[2] * t;
+        }
+      }
+    }
+    if (lane == 0) {
+      if (p.flags & NMR_FLAG_WHITE_BG) { float bg = 1.0f - acc; c0 += bg; c1 += bg; c2 += bg; }
+      if (p.rgb) { p.rgb[ray * 3] = c0; p.rgb[ray * 3 + 1] = c1; p.rgb[ray * 3 + 2] = c2; }
+      if (p.depth) p.depth[ray] = dep;
+      if (p.acc) p.acc[ray] = acc;
+      if (p.disp) { float q = dep / acc; p.disp[ray] = (q != q) ? q : 1.0f / fmaxf(1e-10f, q); }
+      if (p.pts_out) { p.pts_out[ray * 3] = p0; p.pts_out[ray * 3 + 1] = p1; p.pts_out[ray * 3 + 2] = p2; }
+      if (p.pt3d && p.has_unnorm) {
+        const float* u = p.unnorm;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          p.pt3d[ray * 3 + i] = fmaf(u[4 * i], p0, fmaf(u[4 * i + 1], p1, fmaf(u[4 * i + 2], p2, u[4 * i + 3])));
+      }
+    }
+    if (p.weights) for (int s = lane; s < S; s += 32) p.weights[ray * S + s] = sw[s];
+
+    // ---- feature compositing: the HBM-heavy read ---------------------------------------------
+    if (p.feats && p.feat_out) {
+      float a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = 0.f;
+      if (p.feats_bf16) {
+        const uint4* base = reinterpret_cast<const uint4*>(p.feats) + (ray * S) * 32 + lane;
+        if (fmax) {
+          accum8_bf16(a, __ldg(base + (int64_t)besti * 32), 1.0f);
+        } else {
+          int s = 0;
+          for (; s + 8 <= S; s += 8) {
+            uint4 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldcs(base + (int64_t)(s + k) * 32);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) accum8_bf16(a, v[k], sw[s + k]);
+          }
+          for (; s < S; ++s) accum8_bf16(a, __ldcs(base + (int64_t)s * 32), sw[s]);
+        }
+      } else {
+        // lane owns channels [4*lane, +4) and [128 + 4*lane, +4): every load instruction is a
+        // fully used, contiguous 512-byte warp request.
+        const float4* base = reinterpret_cast<const float4*>(p.feats) + (ray * S) * 64 + lane;
+        if (fmax) {
+          float4 x = __ldg(base + (int64_t)besti * 64), y = __ldg(base + (int64_t)besti * 64 + 32);
+          a[0] = x.x; a[1] = x.y; a[2] = x.z; a[3] = x.w; a[4] = y.x; a[5] = y.y; a[6] = y.z; a[7] = y.w;
+        } else {
+          int s = 0;
+          for (; s + 4 <= S; s += 4) {
+            float4 x[4], y[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              x[k] = __ldcs(base + (int64_t)(s + k) * 64);
+              y[k] = __ldcs(base + (int64_t)(s + k) * 64 + 32);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float w = sw[s + k];
+              a[0] = fmaf(w, x[k].x, a[0]); a[1] = fmaf(w, x[k].y, a[1]);
+              a[2] = fmaf(w, x[k].z, a[2]); a[3] = fmaf(w, x[k].w, a[3]);
+              a[4] = fmaf(w, y[k].x, a[4]); a[5] = fmaf(w, y[k].y, a[5]);
+              a[6] = fmaf(w, y[k].z, a[6]); a[7] = fmaf(w, y[k].w, a[7]);
+            }
+          }
+          for (; s < S; ++s) {
+            float w = sw[s];
+            float4 x = __ldcs(base + (int64_t)s * 64), y = __ldcs(base + (int64_t)s * 64 + 32);
+            a[0] = fmaf(w, x.x, a[0]); a[1] = fmaf(w, x.y, a[1]); a[2] = fmaf(w, x.z, a[2]); a[3] = fmaf(w, x.w, a[3]);
+            a[4] = fmaf(w, y.x, a[4]); a[5] = fmaf(w, y.y, a[5]); a[6] = fmaf(w, y.z, a[6]); a[7] = fmaf(w, y.w, a[7]);
+          }
+        }
+      }
+      if (p.feats_bf16) {   // lane owns channels [8*lane, +8)
+        float4* out = reinterpret_cast<float4*>(p.feat_out + ray * kHid) + lane * 2;
+        out[0] = make_float4(a[0], a[1], a[2], a[3]);
+        out[1] = make_float4(a[4], a[5], a[6], a[7]);
+      } else {
+        float4* out = reinterpret_cast<float4*>(p.feat_out + ray * kHid) + lane;
+        out[0] = make_float4(a[0], a[1], a[2], a[3]);
+        out[32] = make_float4(a[4], a[5], a[6], a[7]);
+      }
+    }
+  }
+
+  if (p.z_next == nullptr) return;
+  __syncwarp();
+
+  // ---- fused hierarchical re-sampling ---------------------------------------------------------
+  if (p.mip) {
+    // blur: edge pad, max of neighbours, mean of neighbours, + resample_padding (:583-590)
+    for (int s = lane; s < S; s += 32) {
+      float wm = sw[max(s - 1, 0)], w0 = sw[s], wp = sw[min(s + 1, S - 1)];
+      st[s] = 0.5f * (fmaxf(wm, w0) + fmaxf(w0, wp)) + p.resample_padding;
+    }
+    __syncwarp();
+    float wsum = 0.f;
+    if (lane == 0) {
+      double acc = 0.0;
+      for (int s = 0; s < S; ++s) acc += (double)st[s];
+      wsum = (float)acc;
+    }
+    wsum = __shfl_sync(0xffffffffu, wsum, 0);
+    float padding = fmaxf(0.0f, 1e-5f - wsum);
+    float wtot = wsum + padding;
+    float padw = padding / (float)S;
+    for (int s = lane; s < S; s += 32) st[s] = (st[s] + padw) / wtot;     // pdf
+    __syncwarp();
+    if (lane == 0) {
+      double run = 0.0;
+      sa[0] = 0.0f;
+      for (int s = 0; s < S - 1; ++s) { run += (double)st[s]; sa[s + 1] = fminf(1.0f, (float)run); }
+      sa[S] = 1.0f;
+    }
+    __syncwarp();
+    const int S1 = S + 1;
+    const float sstep = (float)(1.0 / (double)S1);
+    for (int j = lane; j < S1; j += 32) {
+      float u;
+      if (p.u_jitter != nullptr || p.rng_mode == NMR_RNG_PHILOX) {
+        float jit = p.u_jitter ? p.u_jitter[ray * S1 + j]
+                               : philox_uniform(p.seed, (uint64_t)(p.ray0 + ray) * 1024u + j, 1u) *
+                                     ((float)(1.0 / (double)S1 - (double)kEps32));
+        float uu = (float)j * sstep;
+        u = fminf((uu + uu) + jit, 1.0f - kEps32);                       // u + u + jitter (:480-490)
+      } else {
+        u = torch_linspace(1.0f - kEps32, S1, j);                         // randomized=False (:493-496)
+      }
+      int idx = upper_bound(sa, S1, u) - 1;
+      idx = min(max(idx, 0), S - 1);
+      float x0 = sz[idx], x1 = sz[idx + 1], y0 = sa[idx], y1 = sa[idx + 1];
+      float t = (u - y0) / (y1 - y0);
+      if (t != t) t = 0.0f;                                               // nan_to_num(.., 0)
+      t = fminf(fmaxf(t, 0.0f), 1.0f);
+      p.z_next[ray * S1 + j] = x0 + t * (x1 - x0);
+      if (p.idx_out) p.idx_out[ray * S1 + j] = idx;
+    }
+  } else {
+    // sample_pdf(bins = z mid-points [S-1], weights[1:-1] + 1e-5 [S-2], N = nf, det=True)
+    const int nb = S - 1, nw = S - 2, N = p.nf;
+    for (int i = lane; i < nw; i += 32) st[i] = sw[i + 1] + 1e-5f;
+    __syncwarp();
+    float wsum = 0.f;
+    if (lane == 0) {
+      double acc = 0.0;
+      for (int i = 0; i < nw; ++i) acc += (double)st[i];
+      wsum = (float)acc;
+    }
+    wsum = __shfl_sync(0xffffffffu, wsum, 0);
+    for (int i = lane; i < nw; i += 32) st[i] = st[i] / wsum;            // pdf
+    __syncwarp();
+    if (lane == 0) {
+      double run = 0.0;
+      sa[0] = 0.0f;
+      for (int i = 0; i < nw; ++i) { run += (double)st[i]; sa[i + 1] = (float)run; }
+    }
+    __syncwarp();
+    // st is free again: hold the combined [z | samples] list there (S + N <= 2 * kMaxSamples)
+    float* comb = st;   // S + N <= kMaxSamples floats (checked in nmr_create)
+    for (int j = lane; j < S; j += 32) comb[j] = sz[j];
+    for (int j = lane; j < N; j += 32) {
+      float u = torch_linspace(1.0f, N, j);
+      int inds = upper_bound(sa, nb, u);
+      int below = max(0, inds - 1), above = min(nb - 1, inds);
+      float cb = sa[below], ca = sa[above];
+      float bb = 0.5f * (sz[below + 1] + sz[below]), ba = 0.5f * (sz[above + 1] + sz[above]);
+      float denom = ca - cb;
+      if (denom < 1e-5f) denom = 1.0f;
+      float t = (u - cb) / denom;
+      comb[S + j] = bb + t * (ba - bb);
+      if (p.idx_out) p.idx_out[ray * N + j] = inds;
+    }
+    __syncwarp();
+    // sort(cat(z, samples)): stable rank by counting (robust even if a list is not monotone)
+    const int T = S + N;
+    for (int e = lane; e < T; e += 32) {
+      float v = comb[e];
+      int rank = 0;
+      for (int f = 0; f < T; ++f) {
+        float q = comb[f];
+        rank += (q < v) || (q == v && f < e);
+      }
+      p.z_next[ray * T + rank] = v;
+    }
+  }
+}
+
+void launch_composite(const CompositeParams& p, cudaStream_t s) {
+  if (p.n == 0) return;
+  size_t smem = kWarpsPerBlock * kSmemPerWarp * sizeof(float);
+  unsigned blocks = (unsigned)((p.n + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  composite_kernel<<<blocks, kWarpsPerBlock * 32, smem, s>>>(p);
+}
+
+}  // namespace nmr

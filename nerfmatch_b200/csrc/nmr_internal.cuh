@@ -1,0 +1,142 @@
+// Internal declarations shared by the libnmr.so translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/nmr.h"
+
+namespace nmr {
+
+constexpr int kHid = 256;        // NeRF trunk width (models/nerf.py:18)
+constexpr int kHalf = 128;       // views layer width
+constexpr int kLayers = 8;
+constexpr int kMaxSamples = 256; // per-ray MLP evaluations a warp handles in the compositor
+constexpr float kHalfPi = 1.57079637050628662109375f;  // fp32(0.5*pi), embedding.py:69
+constexpr float kEps32 = 1.1920928955078125e-07f;      // torch.finfo(float32).eps
+
+inline __host__ __device__ int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Derived dimensions of one configuration.
+struct Dims {
+  int mip;        // 1: IPE + conical frustums, 0: classic NeRF
+  int xyz;        // encoded xyz width (90 mip, 93 normal)
+  int xyzp;       // padded to 16 (96)
+  int dirs;       // encoded dirs width (27)
+  int app;        // appearance width (0 | 16)
+  int dap;        // dirs+app padded to 16 (32 | 48)
+  int kx;         // xyzp + dap: row stride of the padded MLP input
+  int in_dim;     // xyz + dirs + app: reference input width
+  int fx, fd;     // number of frequencies
+  int sc;         // coarse evaluations per ray
+  int sf;         // fine evaluations per ray (mip: sc, normal: sc + num_pts_fine)
+  int nf;         // normal mode: extra fine samples
+  int zc, zf;     // z entries per ray (mip: S+1 fence posts)
+};
+
+// fp32 panels of one net, K padded with zero columns so every GEMM has K % 16 == 0.
+struct NetF32 {
+  float* W[kLayers];   // [256, Kp]; layer 0: Kp = xyzp; layer skip+1: the h-part [256,256]
+  float* Wskip_x;      // [256, xyzp]  xyz-part of layer skip+1 (reference cat order is [xyz, h])
+  float* b[kLayers];
+  float* Wfeat; float* bfeat;       // [256,256]
+  float* Walpha; float* balpha;     // [1,256]
+  float* Wview_f;                   // [128,256] feature part of views_linears.0
+  float* Wview_d;                   // [128,dap] dirs+app part
+  float* bview;
+  float* Wrgb; float* brgb;         // [3,128]
+  bool set;
+};
+
+// ---- kernels' launch wrappers (defined in the .cu files) ---------------------------------
+struct RayGenParams {
+  float kinv[9]; float rot[9]; float org[3];
+  int H, W, ds, h, w, mip;
+  float* rays; int* miss_flag;
+};
+void launch_raygen(const RayGenParams& p, cudaStream_t s);
+void launch_far_fallback(float* rays, int64_t n, int ncols, const int* miss_flag, cudaStream_t s);
+
+struct SampleParams {
+  const float* rays; int64_t n; int ncols; int64_t ray0;  // ray0: global index of first ray (Philox)
+  int S; int mip; int use_disp;
+  const float* t_rand;   // [n, S+1] or null
+  int rng_mode; uint64_t seed;
+  float* z;              // mip [n,S+1] | normal [n,S]
+};
+void launch_sample_coarse(const SampleParams& p, cudaStream_t s);
+
+struct PointsParams {    // z -> pts (+var): sample_smth_along_rays outputs for the stage API
+  const float* rays; int64_t n; int ncols; int S; int mip; float var_scale;
+  const float* z; float* pts; float* var;
+};
+void launch_points(const PointsParams& p, cudaStream_t s);
+
+struct EncodeParams {    // z -> padded fp32 MLP input rows X[P, kx]
+  const float* rays; int64_t n; int ncols; int S; Dims d; float var_scale;
+  const float* z;
+  const int64_t* ray_id; const float* app_table; int num_frames;
+  float* X;
+};
+void launch_encode(const EncodeParams& p, cudaStream_t s);
+void launch_encode_stage(int kind, const Dims& d, const float* x, const float* var, int64_t P, float* out,
+                         cudaStream_t s);
+// reference-layout rows [P,in_dim] -> padded rows [P,kx]
+void launch_repack_input(const Dims& d, const float* x, int64_t P, float* X, cudaStream_t s);
+
+struct CompositeParams {
+  const float* raw;        // [n,S,4]
+  const float* z;          // mip [n,S+1] | normal [n,S]
+  const float* rays; int ncols;   // when rays == null: rays_d given separately, no point recompute
+  const float* rays_d;     // [n,3] (stage API)
+  int64_t n; int S; int mip; uint32_t flags;
+  const void* feats; int feats_bf16;   // [n,S,256] fp32 | bf16, or null
+  const float* pts_in;     // [n,S,3] explicit points (stage API) or null -> recomputed from rays/z
+  float* rgb; float* depth; float* acc; float* disp; float* weights;
+  float* feat_out; float* pts_out; float* pt3d;
+  float unnorm[12]; int has_unnorm;
+  // fused hierarchical resampling for the next pass (null z_next: off)
+  float* z_next; int32_t* idx_out; int nf;
+  const float* u_jitter; int rng_mode; uint64_t seed; int64_t ray0; float resample_padding;
+  const float* weights_in; // stage API: resample from given weights instead of computing them
+};
+void launch_composite(const CompositeParams& p, cudaStream_t s);
+
+struct GemmParams {        // C = act(A1*W1^T + A2*W2^T + bias)
+  const float* A1; int lda1; const float* W1; int K1;
+  const float* A2; int lda2; const float* W2; int K2;   // optional second segment
+  const float* bias; float* C; int ldc; int64_t M; int N; int act;  // 0 none, 1 relu, 2 sigmoid
+};
+void launch_sgemm(const GemmParams& p, cudaStream_t s);
+
+// Philox4x32-10 -> uniform [0,1) with 24 random bits (same granularity as torch.rand fp32)
+__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
+  uint64_t p = (uint64_t)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+__device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t index, uint32_t stream) {
+  uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = stream, c3 = 0x6e6d7221u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    uint32_t lo0 = mulhilo32(0xD2511F53u, c0, &hi0);
+    uint32_t lo1 = mulhilo32(0xCD9E8D57u, c2, &hi1);
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return (float)(c0 >> 8) * (1.0f / 16777216.0f);
+}
+
+// torch.linspace(0, end, steps)[i] as the CPU kernel computes it (probed: lower half i*step,
+// upper half fma(-step, steps-1-i, end)); used for tau (render_utils.py:110, 434) and u (:244, 493).
+__device__ __forceinline__ float torch_linspace(float end, int steps, int i) {
+  if (steps <= 1) return 0.0f;
+  float step = __fdiv_rn(end, (float)(steps - 1));
+  return (i < steps / 2) ? __fmul_rn((float)i, step) : __fmaf_rn(-step, (float)(steps - 1 - i), end);
+}
+
+}  // namespace nmr

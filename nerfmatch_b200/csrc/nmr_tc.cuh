@@ -1,0 +1,44 @@
+// Interface of the bf16 tcgen05 / TMEM MLP path (nmr_mlp_tc.cu), used by nmr_api.cu.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "nmr_internal.cuh"
+
+namespace nmr {
+
+// Unpadded fp32 copies of one net's nn.Linear parameters (host), input of the bf16 packer.
+struct HostNet {
+  std::vector<float> pts_w[kLayers], pts_b[kLayers];
+  std::vector<float> feature_w, feature_b, alpha_w, alpha_b, views_w, views_b, rgb_w, rgb_b;
+};
+
+// Device-resident bf16 weight tiles + fp32 epilogue vectors of one net.
+struct TcNet {
+  void* pool = nullptr;
+  size_t bytes = 0;
+  bool set = false;
+};
+
+struct TcRun {
+  const float* rays; int64_t n; int ncols; int S;
+  const float* z;               // mip [n,S+1] | normal [n,S]
+  const int64_t* ray_id; const float* app_table; int num_frames;
+  float var_scale;
+  int stop_layer; bool want_feat;
+  void* ws;
+};
+
+int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err);
+void tc_free_net(TcNet* n);
+int64_t tc_round_chunk_rays(const Dims& d, int64_t chunk_rays, int64_t n);
+int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err);
+// Sample rows of one pass (encode + MLP fused): writes raw [n*S,4] fp32 and bf16 features [n*S,256]
+// into the workspace and returns their addresses.
+int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, const void** feat_out, int* launches,
+           cudaStream_t s, std::string* err);
+// Explicit padded fp32 rows X[P,kx] -> raw [P,4], feat fp32 [P,256] (stage API).
+int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int stop_layer, float* raw, float* feat,
+                void** ws, size_t* cap, int* launches, cudaStream_t s, std::string* err);
+
+}  // namespace nmr

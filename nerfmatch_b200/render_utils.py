@@ -1,0 +1,96 @@
+"""Free functions other reference modules import from ``nerfmatch.nerf.render_utils`` /
+``scene_utils``, re-created on top of the CUDA stage kernels.  Same names,
+argument meaning and return layout; tensors must live on a CUDA device."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import Engine, EngineConfig
+
+_engines = {}
+
+
+def _engine(device, **kw) -> Engine:
+    cfg = EngineConfig(**kw)
+    key = (str(torch.device(device)), tuple(sorted(vars(cfg).items())))
+    if key not in _engines:
+        _engines[key] = Engine(cfg, device)
+    return _engines[key]
+
+
+def _need_cuda(t, what):
+    if not isinstance(t, torch.Tensor) or t.device.type != "cuda":
+        raise RuntimeError(f"{what}: nerfmatch_b200 works on CUDA tensors only (no CPU fallback)")
+
+
+def sample_nerf_rays(H, W, K, c2w, ds=8, embed_type="mip", device=None):
+    """render_utils.py:56-78.  K [3,3] and c2w [4,4] may be host tensors / arrays: only the pose is
+    uploaded and the rays [n, 12|11] are generated on ``device`` (default: current CUDA device)."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    eng = _engine(device, embed_type=embed_type)
+    rays, _, missed = eng.raygen(torch.as_tensor(K).cpu(), torch.as_tensor(c2w).cpu(), H, W, ds, check_far=True)
+    if missed:
+        print("Fail to find far plane: camera outside the unit sphere! Set far to 1.")
+    return rays
+
+
+def rays_intersect_sphere(rays_o, rays_d, r=1):
+    """scene_utils.py:101-120 - tiny and only used as a host-side helper by the reference datasets;
+    kept as a torch expression on whatever device the inputs live on."""
+    odotd = torch.sum(rays_o * rays_d, 1)
+    d2 = torch.sum(rays_d**2, 1)
+    o2 = torch.sum(rays_o**2, 1)
+    det = odotd**2 + (r**2 - o2) * d2
+    assert torch.all(det >= 0), "Not all your cameras are bounded by the unit sphere; please make sure the cameras are normalized properly!"
+    return (torch.sqrt(det) - odotd) / d2
+
+
+def sample_smth_along_rays(rays, num_pts=64, z_vals=None, weights=None, use_disp=True, perturb=False,
+                           embed_type="normal", model_type="coarse", randomized=True, resample_padding=0.01,
+                           scale_var=-1, num_pts_coarse=None):
+    """render_utils.py:267-323.  Returns ((mean, var), t_vals) in mip mode and (pts, z_vals) otherwise.
+    Random draws are made with torch exactly as the reference does, then injected into the kernel."""
+    _need_cuda(rays, "sample_smth_along_rays")
+    if perturb and embed_type != "mip":
+        raise NotImplementedError("perturb=True (training) is outside the built hot path")
+    rays = rays.detach().float().contiguous()
+    n = rays.shape[0]
+    mip = embed_type == "mip"
+    if model_type == "coarse" or z_vals is None:
+        eng = _engine(rays.device, embed_type=embed_type, num_pts_coarse=num_pts, use_disp=bool(use_disp) and not mip,
+                      mip_var_scale=float(scale_var), resample_padding=resample_padding)
+        t_rand = torch.rand(n, num_pts + 1, device=rays.device) if (mip and randomized) else None
+        z, pts, var = eng.stage_sample_coarse(rays, t_rand)
+        return ((pts, var), z) if mip else (pts, z)
+    sc = z_vals.shape[-1] - 1 if mip else z_vals.shape[-1]
+    eng = _engine(rays.device, embed_type=embed_type, num_pts_coarse=sc, num_pts_fine=num_pts,
+                  mip_var_scale=float(scale_var), resample_padding=resample_padding)
+    u_jit = None
+    if mip and randomized:
+        S1 = sc + 1
+        u_jit = torch.empty(n, S1, device=rays.device).uniform_(to=(1 / S1 - float(torch.finfo(torch.float32).eps)))
+    z, idx, pts, var = eng.stage_resample(rays, z_vals.detach().float().contiguous(), weights.detach().float().contiguous(), u_jit)
+    return ((pts, var), z) if mip else (pts, z)
+
+
+def volume_render_radiance_field(radiance_field, z_vals, rays_d, noise_std=0.0, white_bg=True, embed_type=False,
+                                 out_last=False, input_dim=4):
+    """render_utils.py:176-230 -> (rgb_map, disp_map, acc_map, weights, depth_map, None)."""
+    _need_cuda(radiance_field, "volume_render_radiance_field")
+    if noise_std > 0.0 or out_last or input_dim != 4:
+        raise NotImplementedError("sigma noise / out_last heads (training) are outside the built hot path")
+    mip = str(embed_type)[:3] == "mip"
+    eng = _engine(radiance_field.device, embed_type="mip" if mip else "normal")
+    raw = radiance_field[..., :4].detach().float().contiguous()
+    out = eng.stage_composite(raw, z_vals.detach().float().contiguous(), rays_d.detach().float().contiguous(),
+                              flags=L.NMR_FLAG_WHITE_BG if white_bg else 0)
+    return out["rgb"], out["disp"], out["acc"], out["weights"], out["depth"], None
+
+
+def unnormaliz_pts(pt3d_normed, unnorm_mat):
+    """utils/geometry.py:76-85 for callers that hold points already; the renderer folds this affine into
+    the compositing kernel's epilogue instead."""
+    R, t = unnorm_mat[..., :3, :3], unnorm_mat[..., :3, 3]
+    return pt3d_normed @ R.transpose(-1, -2) + t[..., None, :]

@@ -1,0 +1,244 @@
+"""Drop-in replacement for ``nerfmatch.nerf.renderer.NerfRenderer`` (reference renderer.py:26-333).
+
+Same constructor, attributes, ``state_dict`` keys and return dictionaries; the work is done by
+libnmr.so (hand-written sm_100a CUDA) through the C ABI in include/nmr.h.  PyTorch is used for
+device memory, the current stream, random draws and ``torch.distributed`` only.
+
+What is built is the inference path the evaluators use (``predict`` / ``forward(validation=True)``
+/ ``render_novel_view``).  Training-mode forward (perturb, sigma noise, ``s_fine`` /
+``weights_fine`` outputs; renderer.py:217, 242, 283-286), ``out_scr`` heads, ``single_model`` and
+``pfeat_mask`` are outside the hot-path scope and raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .embedding import FourierEmbedding, PositionalEncodingMIP
+from .engine import Engine, EngineConfig
+from .models import NeRF
+
+_EPS32 = float(torch.finfo(torch.float32).eps)
+
+
+class NerfRenderer(nn.Module):
+    def __init__(self, config, num_frames=None, training=True, stop_layer=-1, precision: Optional[str] = None,
+                 max_chunk_points: int = 0):
+        super().__init__()
+        self.training = training
+        r, e, dcfg = config.render, config.embedding, config.data
+        self.chunksize = r.chunksize
+        self.use_disp = r.use_disp
+        self.perturb = r.perturb
+        self.noise_std = r.noise_std
+        self.white_bg = r.white_bg or getattr(dcfg, "white_bg", False)
+        self.use_viewdirs = r.use_viewdirs
+        self.embed_type = getattr(e, "type", "normal")
+        self.bg_color = [1.0, 1.0, 1.0] if self.white_bg else None
+        self.img_wh = dcfg.img_wh
+        self.mip_var_scale = getattr(e, "mip_var_scale", -1)
+        self.out_scr = getattr(dcfg, "out_scr", False)
+        self.single_model = getattr(r, "single_model", False)
+        self.appearance_embedding = getattr(e, "appearance_embed", False)
+        if self.out_scr or self.single_model or not self.use_viewdirs:
+            raise NotImplementedError("out_scr / single_model / use_viewdirs=False are outside the built hot path")
+        if self.embed_type not in ("mip", "normal"):
+            raise NotImplementedError(f"embedding.type={self.embed_type!r}")
+        self.num_out_ch = 0
+
+        mip = self.embed_type == "mip"
+        enc = PositionalEncodingMIP if mip else FourierEmbedding
+        self.xyz_encoder = enc(e.xyz_num_freqs)
+        self.dirs_encoder = enc(e.dirs_num_freqs)
+        xyz_dim = self.xyz_encoder.get_embedding_dim(3) - (3 if mip else 0)
+        dirs_dim = self.dirs_encoder.get_embedding_dim(3)
+        app_dim = 16 if self.appearance_embedding else 0
+
+        def net_conf(base, stop):
+            c = dict(vars(base))
+            c.update(use_viewdirs=True, xyz_dim=xyz_dim, dirs_dim=dirs_dim, app_dim=app_dim, out_3d_pnt=False, out_add_ch=0)
+            if stop is not None:
+                c["stop_layer"] = stop
+            return c
+
+        self.num_pts_coarse = config.coarse_nerf.num_pts
+        self.nerf_coarse = NeRF(net_conf(config.coarse_nerf, None))       # stop_layer only reaches the fine net
+        fine_conf = getattr(config, "fine_nerf", None)
+        if fine_conf is None:
+            raise NotImplementedError("a renderer without fine_nerf is outside the built hot path")
+        self.num_pts_fine = fine_conf.num_pts
+        self.nerf_fine = NeRF(net_conf(fine_conf, stop_layer))            # renderer.py:99
+        self.output_dim = getattr(config.fine_nerf, "output_dim", 4)
+        self.embedding_a = nn.Embedding(num_frames, 16) if self.appearance_embedding else None
+
+        self.ret_pfeat = False
+        self.pfeat_mask = None
+        self.feat_comb = "lin"
+        self.weight_dir = getattr(config.loss, "weight_dir", 1)
+
+        # ---- B200 engine state (not part of the reference surface) ----
+        self.precision = precision or os.environ.get("NMR_PRECISION", "bf16")
+        self.rng = os.environ.get("NMR_RNG", "torch")   # "torch": same draws as the reference; "philox": in-kernel
+        self.max_chunk_points = max_chunk_points
+        self._engines = {}
+
+    # ------------------------------------------------------------------------------------
+    def set_training_mode(self, state):
+        self.training = state
+
+    def _engine_config(self) -> EngineConfig:
+        return EngineConfig(
+            embed_type=self.embed_type, xyz_num_freqs=self.xyz_encoder.num_freqs, dirs_num_freqs=self.dirs_encoder.num_freqs,
+            num_pts_coarse=self.num_pts_coarse, num_pts_fine=self.num_pts_fine,
+            app_dim=16 if self.appearance_embedding else 0,
+            stop_layer_coarse=self.nerf_coarse.stop_layer, stop_layer_fine=self.nerf_fine.stop_layer,
+            use_disp=bool(self.use_disp), precision=self.precision, mip_var_scale=float(self.mip_var_scale),
+            max_chunk_points=self.max_chunk_points,
+        )
+
+    def engine(self, device) -> Engine:
+        """The nmr_handle for ``device``; (re)uploads weights when a parameter changed
+        (load_state_dict, .to(), in-place edits bump the tensors' version counters)."""
+        key = str(torch.device(device))
+        sig = (self.nerf_coarse.weights_signature(), self.nerf_fine.weights_signature(),
+               None if self.embedding_a is None else (self.embedding_a.weight.data_ptr(), self.embedding_a.weight._version),
+               self.embed_type, float(self.mip_var_scale))
+        ent = self._engines.get(key)
+        if ent is None or ent[1] != sig:
+            eng = Engine(self._engine_config(), device) if (ent is None or ent[1][3:] != sig[3:]) else ent[0]
+            eng.set_weights(L.NMR_NET_COARSE, self.nerf_coarse.net_state())
+            eng.set_weights(L.NMR_NET_FINE, self.nerf_fine.net_state())
+            if self.embedding_a is not None:
+                eng.set_appearance(self.embedding_a.weight)
+            ent = (eng, sig)
+            self._engines[key] = ent
+        if ent[0].cfg.precision != self.precision:
+            ent[0].set_precision(self.precision)
+        return ent[0]
+
+    def _flags(self):
+        f = 0
+        if self.ret_pfeat:
+            f |= L.NMR_FLAG_RET_PFEAT
+        if self.feat_comb == "max":
+            f |= L.NMR_FLAG_FEAT_MAX
+        if self.white_bg:
+            f |= L.NMR_FLAG_WHITE_BG
+        return f
+
+    def _draws(self, n, device):
+        """mip mode jitters samples even at inference (``randomized`` is never overridden,
+        renderer.py:211-221).  With rng='torch' the two draws are made with the same calls, shapes
+        and order as the reference (render_utils.py:444, 483-485), so a seeded run sees the same
+        numbers; rng='philox' generates them inside the kernels instead."""
+        if self.embed_type != "mip":
+            return None, None, L.NMR_RNG_NONE, 0
+        if self.rng == "philox":
+            seed = int(torch.randint(0, 2**62, (1,)).item())
+            return None, None, L.NMR_RNG_PHILOX, seed
+        if self.rng == "none":
+            return None, None, L.NMR_RNG_NONE, 0
+        S1 = self.num_pts_coarse + 1
+        t_rand = torch.rand(n, S1, device=device)
+        u_jit = torch.empty(n, S1, device=device).uniform_(to=(1 / S1 - _EPS32))
+        return t_rand, u_jit, L.NMR_RNG_NONE, 0
+
+    # ------------------------------------------------------------------------------------
+    def forward_nerf(self, model, pts, viewdirs=None, ret_pfeat=False, app_emb=None, validation=False):
+        """Reference renderer.py:119-180: encode + evaluate one net on explicit sample points."""
+        if self.embed_type == "mip":
+            mean, var = pts
+            n, m, _ = mean.shape
+            x = self.xyz_encoder(mean.reshape(-1, 3), y=var.reshape(-1, 3))[0]
+        else:
+            n, m, _ = pts.shape
+            x = self.xyz_encoder(pts.reshape(-1, 3))
+        cols = [x]
+        if self.use_viewdirs:
+            cols.append(self.dirs_encoder(viewdirs).repeat_interleave(m, dim=0))
+        if app_emb is not None:
+            cols.append(app_emb.reshape(n, -1).repeat_interleave(m, dim=0))
+        out = model.forward(torch.cat(cols, -1), ret_pfeat=ret_pfeat, val=validation)
+        if ret_pfeat:
+            raw, feats = out
+            return raw.reshape(n, m, -1), feats.reshape(n, m, -1), None
+        return out.reshape(n, m, -1)
+
+    def render_rays(self, rays, ray_id=None, validation=False, _intermediates=False, _unnorm=None):
+        """Hierarchical coarse->fine render of a ray batch (reference renderer.py:182-295)."""
+        if not validation:
+            raise NotImplementedError(
+                "training-mode forward (perturb / sigma noise / s_fine / weights_fine) is outside the built hot path; "
+                "call predict() or forward(validation=True)"
+            )
+        if self.pfeat_mask is not None:
+            raise NotImplementedError("pfeat_mask is a training-validation feature (out of scope)")
+        if rays.device.type != "cuda":
+            raise RuntimeError("NerfRenderer (nerfmatch_b200) renders CUDA ray tensors only: there is no CPU fallback")
+        rays = rays.detach().float().contiguous()
+        n, ncols = rays.shape
+        eng = self.engine(rays.device)
+        if self.appearance_embedding and ray_id is not None:
+            ray_id = ray_id.detach().to(device=rays.device, dtype=torch.int64).contiguous()
+        else:
+            ray_id = None if not self.appearance_embedding else torch.ones(n, dtype=torch.int64, device=rays.device)
+        t_rand, u_jit, rng_mode, seed = self._draws(n, rays.device)
+        outs = eng.alloc_outputs(n, self.ret_pfeat, _unnorm is not None, intermediates=_intermediates)
+        args, keep = eng.make_args(n, ncols, rays=rays, ray_id=ray_id, t_rand=t_rand, u_jitter=u_jit, flags=self._flags(),
+                                   rng_mode=rng_mode, seed=seed, unnorm=_unnorm, outs=outs)
+        eng.render(args)
+        preds = {}
+        for key in ("coarse", "fine"):      # key order of the reference dict
+            if self.ret_pfeat:
+                preds[f"feat_{key}"] = outs[f"feat_{key}"]
+            preds[f"pts_{key}"] = outs[f"pts_{key}"]
+            preds[f"rgb_{key}"] = outs[f"rgb_{key}"]
+            preds[f"depth_{key}"] = outs[f"depth_{key}"]
+        for k, v in outs.items():
+            if k not in preds and (_intermediates or k == "pt3d"):
+                preds[k] = v
+        return preds
+
+    def forward(self, rays, step=0, ray_id=None, validation=False):
+        return self.render_rays(rays, ray_id, validation=validation)
+
+    def predict(self, rays, w, h, out_raw=False, ray_id=None):
+        self.set_training_mode(False)
+        preds = self.forward(rays, validation=True, ray_id=ray_id)
+        if out_raw:
+            return preds
+        for k in ("rgb_coarse", "depth_coarse", "rgb_fine", "depth_fine"):
+            v = preds[k]
+            if h * w == v.shape[0]:
+                preds[k] = v.reshape(h, w, -1)
+        return preds
+
+    def render_novel_view(self, img_hw, K, c2w, unnorm_scene, device, downsample=8):
+        """Reference renderer.py:315-333, with the rays generated on the device instead of on the
+        host: only the pose crosses the bus."""
+        self.ret_pfeat = True
+        self.set_training_mode(False)
+        H, W = img_hw
+        if isinstance(unnorm_scene, np.ndarray):
+            unnorm_scene = torch.from_numpy(unnorm_scene)
+        unnorm_scene = unnorm_scene.detach().float().cpu()
+        c2w_n = unnorm_scene.inverse() @ torch.as_tensor(c2w).detach().float().cpu()
+        device = torch.device(device)
+        eng = self.engine(device)
+        h, w = len(range(downsample // 2, H, downsample)), len(range(downsample // 2, W, downsample))
+        n = h * w
+        t_rand, u_jit, rng_mode, seed = self._draws(n, device)
+        ray_id = torch.ones(n, dtype=torch.int64, device=device) if self.appearance_embedding else None
+        outs = eng.alloc_outputs(n, True, True)
+        args, keep = eng.make_args(n, 12 if self.embed_type == "mip" else 11, ray_id=ray_id, t_rand=t_rand, u_jitter=u_jit,
+                                   flags=self._flags(), rng_mode=rng_mode, seed=seed, unnorm=unnorm_scene, outs=outs)
+        eng.render_view(torch.as_tensor(K).detach().float().cpu(), c2w_n, H, W, downsample, args)
+        im = outs["rgb_fine"]
+        if (W // downsample) * (H // downsample) == n:
+            im = im.reshape(H // downsample, W // downsample, -1)
+        return dict(im_pred=im, pt3d=outs["pt3d"], pt_feat=outs["feat_fine"])

@@ -47,3 +47,10 @@ def cosine_rows(a, b):
     num = (a * b).sum(-1)
     den = np.linalg.norm(a, axis=-1) * np.linalg.norm(b, axis=-1)
     return num / np.maximum(den, 1e-30)
+
+
+from nerfmatch_b200.config import build_renderer as _build, make_config as ref_style_config  # noqa: E402,F401
+
+
+def build_renderer(c, sd, precision="fp32", device="cuda:0", **kw):
+    return _build(c, sd, precision=precision, device=device, **kw)
