@@ -41,6 +41,13 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
+def ray_rel_err(a, b):
+    """per-ray relative L2 error of [n, C] (or [n]) arrays"""
+    a = np.asarray(a, np.float64).reshape(len(a), -1)
+    b = np.asarray(b, np.float64).reshape(len(b), -1)
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)
+
+
 def cosine_rows(a, b):
     a = np.asarray(a, np.float64)
     b = np.asarray(b, np.float64)
