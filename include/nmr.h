@@ -189,6 +189,15 @@ NMR_API int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z,
                         float* depth, float* acc, float* disp, float* weights, float* feat_out,
                         float* pts_out, void* stream);
 
+/* Test hooks for the tcgen05 path (NMR_PREC_BF16 only).  nmr_stage_mlp_probe evaluates the net on
+ * x [P, xyz+dirs+app] and returns the post-activation output of MLP step `step` as fp32 [P,256]:
+ * steps 0..7 = pts_linears.0..7 (+ReLU), 8 = feature_linear, 9 = views_linears.0 (+ReLU, first 128
+ * columns).  nmr_debug_trap_code returns the code a bounded in-kernel barrier wait recorded before
+ * trapping (0 = none); it lives in mapped host memory so it survives a failed launch. */
+NMR_API int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int64_t P, int32_t step, float* out,
+                                void* stream);
+NMR_API int nmr_debug_trap_code(void);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 NMR_API int64_t nmr_launch_count(const nmr_handle* h);
 /* Milliseconds spent in the MLP kernels of the last nmr_render* call on this handle, measured with

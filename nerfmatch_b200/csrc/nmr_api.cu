@@ -47,6 +47,7 @@ struct nmr_handle {
   std::string err;
   int64_t launches = 0;
   bool timing = false;
+  bool auto_chunk = true;
   std::vector<StageEvent> events;
 };
 
@@ -139,7 +140,8 @@ extern "C" int nmr_create(const nmr_config* cfg, nmr_handle** out) {
   nmr_handle* h = new nmr_handle();
   h->cfg = c;
   if (h->cfg.resample_padding <= 0.f) h->cfg.resample_padding = 0.01f;
-  if (h->cfg.max_chunk_points <= 0) h->cfg.max_chunk_points = (int64_t)1 << 20;
+  h->auto_chunk = h->cfg.max_chunk_points <= 0;
+  if (h->auto_chunk) h->cfg.max_chunk_points = (int64_t)1 << 20;
   h->d = d;
   h->device = dev;
   for (int i = 0; i < 2; ++i) { memset(&h->net[i], 0, sizeof(NetF32)); h->tc[i] = TcNet{}; }
@@ -255,7 +257,9 @@ extern "C" int nmr_set_weights(nmr_handle* h, int which, const nmr_weight_ptrs* 
   n.set = true;
   // bf16 UMMA-major tiles for the tcgen05 path
   std::string terr;
-  if (tc_pack_net(h->d, h->cfg.skip_layer, hn, &h->tc[which], &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_pack_net: %s", terr.c_str());
+  int tr = tc_pack_net(h->d, h->cfg.skip_layer, hn, &h->tc[which], &terr);
+  if (tr < 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_pack_net: %s", terr.c_str());
+  if (tr > 0 && h->cfg.precision == NMR_PREC_BF16) NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_set_weights: %s", terr.c_str());
   return NMR_OK;
 }
 
@@ -403,6 +407,8 @@ static int validate_render(nmr_handle* h, const nmr_render_args* a) {
   if (a->ncols < 8) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: rays need at least 8 columns (o, d, near, far), got %d", a->ncols);
   if (h->d.mip && a->ncols < 12) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: mip rays need 12 columns (radius in column 11), got %d", a->ncols);
   if (!h->net[0].set || !h->net[1].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_render: weights of both nets must be set first");
+  if (h->cfg.precision == NMR_PREC_BF16 && (!h->tc[0].set || !h->tc[1].set))
+    NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_render: this configuration is not built for the tcgen05 path; use NMR_PREC_FP32");
   if (h->d.app > 0 && h->num_frames == 0) NMR_FAIL(h, NMR_ERR_STATE, "nmr_render: appearance table not set");
   if (a->pt3d && !a->unnorm) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: pt3d requested without unnorm");
   return NMR_OK;
@@ -417,7 +423,9 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
   const nmr_config& c = h->cfg;
   const bool bf16 = c.precision == NMR_PREC_BF16;
   const int smax = std::max(d.sc, d.sf);
-  int64_t chunk_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, c.max_chunk_points / smax));
+  // fp32 path: ~3.7 KB of workspace per point; bf16 path: 0.5 KB (tiled features) -> larger chunks
+  const int64_t max_points = (bf16 && h->auto_chunk) ? ((int64_t)1 << 22) : c.max_chunk_points;
+  int64_t chunk_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, max_points / smax));
   if (bf16) chunk_rays = tc_round_chunk_rays(d, chunk_rays, a->n);
   if ((r = ensure_workspace(h, chunk_rays, bf16 ? 0 : chunk_rays * smax)) != NMR_OK) return r;
   if (bf16) {
@@ -729,6 +737,30 @@ extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P
   }
   return NMR_OK;
 }
+
+extern "C" int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int64_t P, int32_t step, float* out,
+                                   void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (which != 0 && which != 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: which=%d", which);
+  if (h->cfg.precision != NMR_PREC_BF16) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: bf16 path only");
+  if (step < 0 || step > 9 || P <= 0 || !x || !out) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: bad argument");
+  if (!h->net[which].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_stage_mlp_probe: weights not set");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dims& d = h->d;
+  int r;
+  if ((r = ensure_workspace(h, 1, P)) != NMR_OK) return r;
+  launch_repack_input(d, x, P, (float*)h->X.p, s);
+  NMR_LAUNCHED(h, "repack_input");
+  std::string terr; int nl = 0;
+  if (tc_run_rows(d, h->tc[which], (const float*)h->X.p, P, 3, (float*)h->raw.p, nullptr, &h->tcws.p, &h->tcws.cap, &nl, s,
+                  &terr, step + 1, out) != 0)
+    NMR_FAIL(h, NMR_ERR_CUDA, "tc_run_rows: %s", terr.c_str());
+  NMR_LAUNCHED(h, "tcgen05 mlp probe", nl);
+  return NMR_OK;
+}
+
+extern "C" int nmr_debug_trap_code(void) { return tc_trap_code(); }
 
 extern "C" int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z, const float* rays_d, int64_t n,
                                    int32_t S, uint32_t flags, const float* feats, const float* pts, float* rgb,

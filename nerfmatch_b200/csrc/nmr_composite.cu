@@ -186,19 +186,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = 0.f;
       if (p.feats_bf16) {
-        const uint4* base = reinterpret_cast<const uint4*>(p.feats) + (ray * S) * 32 + lane;
+        // tiled layout written by the tcgen05 kernel's bulk store: 64 KB per 128 points, eight
+        // [128 x 32] blocks, rows of 64 B with the UMMA 64B swizzle.  Lane l reads the 16-byte chunk
+        // holding channels [8l, 8l+8) of the sample's row.
+        const uint8_t* fb = reinterpret_cast<const uint8_t*>(p.feats);
+        const int jb = (lane >> 2) * 8192, cc = lane & 3;
+        auto addr = [&](int s) -> const uint4* {
+          const int64_t pt = ray * S + s;
+          const int rr = (int)(pt & 127);
+          return reinterpret_cast<const uint4*>(fb + (pt >> 7) * 65536 + jb + ((rr >> 3) << 9) + ((rr & 7) << 6) +
+                                                ((cc ^ ((rr & 7) >> 1)) << 4));
+        };
         if (fmax) {
-          accum8_bf16(a, __ldg(base + (int64_t)besti * 32), 1.0f);
+          accum8_bf16(a, __ldg(addr(besti)), 1.0f);
         } else {
           int s = 0;
           for (; s + 8 <= S; s += 8) {
             uint4 v[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldcs(base + (int64_t)(s + k) * 32);
+            for (int k = 0; k < 8; ++k) v[k] = __ldcs(addr(s + k));
 #pragma unroll
             for (int k = 0; k < 8; ++k) accum8_bf16(a, v[k], sw[s + k]);
           }
-          for (; s < S; ++s) accum8_bf16(a, __ldcs(base + (int64_t)s * 32), sw[s]);
+          for (; s < S; ++s) accum8_bf16(a, __ldcs(addr(s)), sw[s]);
         }
       } else {
         // lane owns channels [4*lane, +4) and [128 + 4*lane, +4): every load instruction is a

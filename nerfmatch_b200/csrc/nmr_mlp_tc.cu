@@ -1,11 +1,700 @@
-// bf16 tcgen05 / TMEM MLP path -- placeholder translation unit (filled in next).
+// Kernel (b): the NeRF MLP (models/nerf.py:94-144) as one persistent, warp-specialised sm_100a kernel.
+//
+//   * every Linear layer is a 128 x N x K tile GEMM on the 5th-gen tensor cores: tcgen05.mma
+//     (kind::f16, bf16 operands, fp32 accumulate) issued by ONE thread, accumulators in TMEM;
+//   * positional encoding (kernel (a)'s encode half) is fused in: four encoder warps turn ray /
+//     sample data into the bf16 A-operand tile directly in shared memory - the encoded inputs never
+//     touch HBM;
+//   * activations never leave the SM: the epilogue warps read the accumulator with tcgen05.ld, add
+//     bias, apply ReLU, round to bf16 and write the next layer's A operand in place, in the UMMA
+//     K-major 64B-swizzled layout.  The skip connection is a second K segment into the same
+//     accumulator; sigma (alpha_linear) and rgb (rgb_linear + sigmoid) are fp32 dot products in the
+//     epilogues of the layers that feed them; the [dirs | appearance] part of views_linears is a
+//     per-ray fp32 bias computed once per ray;
+//   * weights stream from L2 through a ring of shared-memory stages filled by the bulk-copy (TMA)
+//     engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the host, so no tensor
+//     map is needed;
+//   * the tapped feature tile (stop_layer) leaves as one 64 KB bulk store shared->global in the same
+//     tiled layout the compositor reads;
+//   * two 128-point tiles are in flight per CTA ("slots"): while the tensor core runs layer l of one
+//     slot, the other slot's epilogue drains layer l from its half of TMEM (2 x 256 columns).
+//
+// Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 idle,
+// 4-7 epilogue of slot 0, 8-11 epilogue of slot 1, 12-15 encoder.
+#include <cstring>
+
+#include "nmr_encode.cuh"
 #include "nmr_tc.cuh"
 
 namespace nmr {
-int tc_pack_net(const Dims&, int, const HostNet&, TcNet* out, std::string*) { out->set = false; return 0; }
-void tc_free_net(TcNet* n) { if (n->pool) cudaFree(n->pool); n->pool = nullptr; n->set = false; }
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64B swizzle
+constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
+constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
+constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
+constexpr int kStages = 3;
+constexpr int kSteps = 10;                 // 8 trunk layers, feature_linear, views_linears.0
+constexpr int kThreads = 512;
+constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128 points
+
+constexpr int OFF_H = 0;
+constexpr int OFF_E = 2 * kHBytes;
+constexpr int OFF_W = OFF_E + 2 * kEBytes;
+constexpr int OFF_BAR = OFF_W + kStages * kStageBytes;
+constexpr int kSmemBytes = OFF_BAR + 256 + 1024;   // + alignment slack
+
+// barrier slots (8 bytes each) inside the OFF_BAR area
+enum { BAR_WFULL = 0, BAR_WEMPTY = 3, BAR_ACCFULL = 6, BAR_AREADY = 8, BAR_EFULL = 10, BAR_EEMPTY = 12, BAR_COUNT = 14 };
+
+struct TcParams {
+  const uint8_t* chunks; const float* bias; const float* walpha; const float* wrgb;
+  float balpha; float brgb0, brgb1, brgb2;
+  const float* vbias; int vb_div;          // view bias row = point / vb_div
+  // input mode 0: rays + z (fused sampling-to-encoding); mode 1: padded fp32 rows X[P,kx]
+  int mode; const float* rays; int ncols; const float* z; int S; int mip; int xyz; int fx; float var_scale;
+  const float* X; int kx;
+  int64_t P; int n_iters;
+  int stop_step; int want_feat;
+  float* raw; uint8_t* feat_tiles;
+  int debug_step; float* debug_out;
+  int* error_flag;
+};
+
+__host__ __device__ constexpr int step_chunks_e(int s) { return (s == 0 || s == 5) ? 3 : 0; }
+__host__ __device__ constexpr int step_chunks_h(int s) { return s == 0 ? 0 : 8; }
+__host__ __device__ constexpr int step_chunk_bytes(int s) { return s == 9 ? 8192 : 16384; }
+__host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the chunk stream
+  int64_t off = 0;
+  for (int i = 0; i < s; ++i) off += (int64_t)(step_chunks_e(i) + step_chunks_h(i)) * step_chunk_bytes(i);
+  return off;
+}
+
+// ---- PTX wrappers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU box - after ~0.2 s record where and trap.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 400000000LL) {
+      atomicExch(error_flag, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;                        // layout type: SWIZZLE_64B
+  return d;
+}
+// instruction descriptor: kind::f16, A = B = bf16 (K-major), D = fp32, M = 128
+__device__ __forceinline__ uint32_t umma_idesc(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// byte offset of 16-byte chunk c (0..3) of row r inside a [128 x 32 bf16] 64B-swizzled block
+__device__ __forceinline__ uint32_t sw64_off(int r, int c) {
+  return (uint32_t)(((r >> 3) << 9) + ((r & 7) << 6) + ((c ^ ((r & 7) >> 1)) << 4));
+}
+
+// ---- the kernel ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bars = base + OFF_BAR;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + BAR_COUNT * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bars + 8 * (BAR_ACCFULL + s), 1);
+      mbar_init(bars + 8 * (BAR_AREADY + s), 128);
+      mbar_init(bars + 8 * (BAR_EFULL + s), 128);
+      mbar_init(bars + 8 * (BAR_EEMPTY + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + BAR_COUNT * 8), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== weight producer: bulk-copy chunks global -> smem ring =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < p.n_iters; ++it) {
+        const uint8_t* src = p.chunks;
+        for (int s = 0; s < kSteps; ++s) {
+          const int nch = step_chunks_e(s) + step_chunks_h(s);
+          const uint32_t bytes = step_chunk_bytes(s);
+          for (int slot = 0; slot < 2; ++slot) {
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
+              mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
+              bulk_g2s(base + OFF_W + stage * kStageBytes, src + (size_t)c * bytes, bytes, bars + 8 * (BAR_WFULL + stage));
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          src += (size_t)nch * bytes;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0; uint32_t wphase = 0;
+      uint32_t ph_aready[2] = {0, 0}, ph_efull[2] = {0, 0};
+      for (int it = 0; it < p.n_iters; ++it) {
+        for (int s = 0; s < kSteps; ++s) {
+          const int ne = step_chunks_e(s), nh = step_chunks_h(s);
+          const int N = (s == 9) ? 128 : 256;
+          const uint32_t idesc = umma_idesc(N);
+          for (int slot = 0; slot < 2; ++slot) {
+            // inputs of this step: previous epilogue of this slot done (TMEM drained, H written)
+            mbar_wait(bars + 8 * (BAR_AREADY + slot), ph_aready[slot], p.error_flag, 200 + slot);
+            ph_aready[slot] ^= 1;
+            if (s == 0) {
+              mbar_wait(bars + 8 * (BAR_EFULL + slot), ph_efull[slot], p.error_flag, 210 + slot);
+              ph_efull[slot] ^= 1;
+            }
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + slot * 256;
+            uint32_t accumulate = 0;
+            for (int c = 0; c < ne + nh; ++c) {
+              const uint32_t a_addr = (c < ne) ? (base + OFF_E + slot * kEBytes + c * kBlk)
+                                               : (base + OFF_H + slot * kHBytes + (c - ne) * kBlk);
+              mbar_wait(bars + 8 * (BAR_WFULL + stage), wphase, p.error_flag, 220 + stage);
+              tc_fence_after();
+              const uint32_t b_addr = base + OFF_W + stage * kStageBytes;
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                umma_bf16(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, accumulate);
+                accumulate = 1;
+              }
+              umma_commit(bars + 8 * (BAR_WEMPTY + stage));      // stage free once these MMAs retire
+              if (++stage == kStages) { stage = 0; wphase ^= 1; }
+            }
+            umma_commit(bars + 8 * (BAR_ACCFULL + slot));        // accumulator complete -> epilogue
+            if (s == 5) umma_commit(bars + 8 * (BAR_EEMPTY + slot));  // encoded tile no longer needed
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===== epilogue warps: TMEM -> bias/activation -> bf16 A operand of the next layer =====
+    const int slot = (warp - 4) >> 2;
+    const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                    // row of the tile
+    const int et = (warp - 4 - slot * 4) * 32 + lane;  // thread index inside the slot's epilogue group
+    const uint32_t h_base = base + OFF_H + slot * kHBytes;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
+    mbar_arrive(bars + 8 * (BAR_AREADY + slot));    // TMEM / H start out free
+    uint32_t ph_acc = 0;
+    bool store_pending = false;
+    for (int it = 0; it < p.n_iters; ++it) {
+      const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
+      const int64_t pt = tile * kTileM + r;
+      const bool valid = pt < p.P;
+      float alpha = 0.f;
+      for (int s = 0; s < kSteps; ++s) {
+        mbar_wait(bars + 8 * (BAR_ACCFULL + slot), ph_acc, p.error_flag, 300 + slot);
+        ph_acc ^= 1;
+        tc_fence_after();
+        const bool writes_h = s < 9;
+        if (writes_h && store_pending) {            // the tap store must have finished reading H
+          if (et == 0) bulk_wait_read0();
+          named_bar_sync(1 + slot, 128);
+          store_pending = false;
+        }
+        const int nj = (s == 9) ? 4 : 8;
+        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+        const float* vb = (s == 9 && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
+        for (int j = 0; j < nj; ++j) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + j * 32, v);
+          float b[32];
+          if (s < 9) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + s * kHid + j * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { float4 t = __ldg(bp + i); b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) b[i] = 0.f;
+            if (vb) {
+              const float4* bp = reinterpret_cast<const float4*>(vb + j * 32);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { float4 t = __ldg(bp + i); b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w; }
+            }
+          }
+          tmem_ld_wait();
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float t = __uint_as_float(v[i]) + b[i];
+            x[i] = (s != 8) ? fmaxf(t, 0.f) : t;     // feature_linear has no activation
+          }
+          if (s == 7) {                              // alpha_linear on the un-rounded fp32 activations
+            const float4* wp = reinterpret_cast<const float4*>(p.walpha + j * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 w = __ldg(wp + i);
+              alpha = fmaf(x[4 * i], w.x, fmaf(x[4 * i + 1], w.y, fmaf(x[4 * i + 2], w.z, fmaf(x[4 * i + 3], w.w, alpha))));
+            }
+          }
+          if (s == 9) {                              // rgb_linear
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              c0 = fmaf(x[i], __ldg(p.wrgb + j * 32 + i), c0);
+              c1 = fmaf(x[i], __ldg(p.wrgb + kHalf + j * 32 + i), c1);
+              c2 = fmaf(x[i], __ldg(p.wrgb + 2 * kHalf + j * 32 + i), c2);
+            }
+          }
+          if (writes_h) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t w0 = pack_bf16(x[8 * c], x[8 * c + 1]), w1 = pack_bf16(x[8 * c + 2], x[8 * c + 3]);
+              uint32_t w2 = pack_bf16(x[8 * c + 4], x[8 * c + 5]), w3 = pack_bf16(x[8 * c + 6], x[8 * c + 7]);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_base + j * kBlk + sw64_off(r, c)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+            }
+          }
+          if (p.debug_out && s == p.debug_step && valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = x[i];
+          }
+        }
+        if (s == 9 && valid) {
+          float4 o;
+          o.x = 1.f / (1.f + __expf(-(c0 + p.brgb0)));
+          o.y = 1.f / (1.f + __expf(-(c1 + p.brgb1)));
+          o.z = 1.f / (1.f + __expf(-(c2 + p.brgb2)));
+          o.w = alpha + p.balpha;
+          *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+        }
+        tc_fence_before();
+        if (writes_h) fence_proxy_async();           // generic-proxy writes -> visible to UMMA / bulk copy
+        if (s == p.stop_step && p.want_feat) {
+          named_bar_sync(1 + slot, 128);
+          if (et == 0 && tile * kTileM < p.P) {
+            bulk_s2g(p.feat_tiles + (size_t)tile * kFeatTileBytes, h_base, kFeatTileBytes);
+            bulk_commit();
+          }
+          store_pending = true;
+        }
+        mbar_arrive(bars + 8 * (BAR_AREADY + slot));
+      }
+    }
+    if (et == 0) bulk_wait0();
+  } else if (warp >= 12) {
+    // ===== encoder warps: sampling data -> positional encoding -> bf16 A tile of layer 0 / skip =====
+    const int r = (warp - 12) * 32 + lane;
+    uint32_t ph_eempty[2] = {0, 0};
+    for (int it = 0; it < p.n_iters; ++it) {
+      for (int slot = 0; slot < 2; ++slot) {
+        const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
+        const int64_t pt = tile * kTileM + r;
+        const bool valid = pt < p.P;
+        float m[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
+        const float* xrow = nullptr;
+        if (valid) {
+          if (p.mode == 0) {
+            const int64_t ray = pt / p.S;
+            const int sidx = (int)(pt - ray * p.S);
+            const float* rr = p.rays + ray * p.ncols;
+            if (p.mip) {
+              const float* z = p.z + ray * (p.S + 1);
+              float rl[12];
+#pragma unroll
+              for (int i = 0; i < 12; ++i) rl[i] = __ldg(rr + i);
+              frustum_gaussian(rl, __ldg(z + sidx), __ldg(z + sidx + 1), p.var_scale, m, vv);
+            } else {
+              const float zz = __ldg(p.z + pt);
+#pragma unroll
+              for (int c = 0; c < 3; ++c) m[c] = __ldg(rr + c) + __ldg(rr + 3 + c) * zz;
+            }
+          } else {
+            xrow = p.X + pt * p.kx;
+          }
+        }
+        mbar_wait(bars + 8 * (BAR_EEMPTY + slot), ph_eempty[slot] ^ 1, p.error_flag, 400 + slot);
+        ph_eempty[slot] ^= 1;
+        const uint32_t e_base = base + OFF_E + slot * kEBytes;
+        for (int kb = 0; kb < 3; ++kb) {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int col = kb * 32 + c * 8 + i;
+              float val = 0.f;
+              if (valid && col < p.xyz) {
+                if (p.mode == 1) val = __ldg(xrow + col);
+                else val = p.mip ? ipe_col(m, vv, p.fx, col) : fourier_col(m, p.fx, col);
+              }
+              f[i] = val;
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e_base + kb * kBlk + sw64_off(r, c)),
+                         "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+          }
+        }
+        fence_proxy_async();
+        mbar_arrive(bars + 8 * (BAR_EFULL + slot));
+      }
+    }
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// per-ray (or per-row) view bias: b_view + W_view[:, 256:] . [dirs encoding | appearance]   (fp32)
+struct VbParams {
+  int mode; const float* rays; int ncols; const int64_t* ray_id; const float* app_table; int num_frames;
+  const float* X; int kx; int xyzp;
+  int mip; int fd; int dirs; int app; int dap;
+  const float* wview_d; const float* bview; int64_t n; float* out;
+};
+__global__ void __launch_bounds__(128) view_bias_kernel(VbParams p) {
+  __shared__ float de[64];
+  const int64_t row = blockIdx.x;
+  const int t = threadIdx.x;
+  if (t < p.dap) {
+    float v = 0.f;
+    if (p.mode == 1) {
+      v = p.X[row * p.kx + p.xyzp + t];
+    } else if (t < p.dirs) {
+      const float* rr = p.rays + row * p.ncols;
+      const float* vd = (p.ncols >= 11) ? rr + 8 : rr + 3;
+      float v3[3] = {vd[0], vd[1], vd[2]};
+      v = p.mip ? pe_col(v3, p.fd, t) : fourier_col(v3, p.fd, t);
+    } else if (t < p.dirs + p.app) {
+      int64_t id = p.ray_id ? p.ray_id[row] : 1;
+      id = id < 0 ? 0 : (id >= p.num_frames ? p.num_frames - 1 : id);
+      v = p.app_table[id * p.app + (t - p.dirs)];
+    }
+    de[t] = v;
+  }
+  __syncthreads();
+  float acc = 0.f;
+  const float* w = p.wview_d + t * p.dap;
+  for (int k = 0; k < p.dirs + p.app; ++k) acc = fmaf(de[k], w[k], acc);
+  p.out[row * kHalf + t] = acc + p.bview[t];
+}
+
+// tiled bf16 features -> fp32 [P,256] rows (stage API only)
+__global__ void detile_kernel(const uint8_t* tiles, int64_t P, float* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte chunk (8 channels) per thread
+  if (i >= P * 32) return;
+  int64_t pt = i >> 5;
+  int l = (int)(i & 31);
+  int j = l >> 2, c = l & 3;
+  int r = (int)(pt & 127);
+  const uint8_t* src = tiles + (pt >> 7) * kFeatTileBytes + j * kBlk + sw64_off(r, c);
+  uint4 v = *reinterpret_cast<const uint4*>(src);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  float* o = out + pt * kHid + j * 32 + c * 8;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); o[2 * k] = f.x; o[2 * k + 1] = f.y; }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+uint16_t f2bf(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// pack W[rows, ldw] columns [k0, k0+32) (zero beyond kmax) as one swizzled chunk
+void pack_chunk(std::vector<uint8_t>& out, const float* W, int rows, int ldw, int k0, int kmax) {
+  size_t off = out.size();
+  out.resize(off + (size_t)rows * 64, 0);
+  for (int n = 0; n < rows; ++n)
+    for (int k = 0; k < 32; ++k) {
+      int kk = k0 + k;
+      float v = (kk < kmax) ? W[(size_t)n * ldw + kk] : 0.f;
+      uint16_t h = f2bf(v);
+      size_t b = off + (size_t)(n >> 3) * 512 + (n & 7) * 64 + (((k >> 3) ^ ((n & 7) >> 1)) << 4) + (k & 7) * 2;
+      memcpy(&out[b], &h, 2);
+    }
+}
+
+struct TcWs {   // carved from one device allocation
+  float* raw; uint8_t* feat; float* vbias; int* error_flag; float* xfeat;
+};
+size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+  int64_t tiles = (points + kTileM - 1) / kTileM + 2;
+  size_t o_raw = take((size_t)tiles * kTileM * 4 * sizeof(float));
+  size_t o_feat = take((size_t)tiles * kFeatTileBytes);
+  size_t o_vb = take((size_t)std::max<int64_t>(vb_rows, 1) * kHalf * sizeof(float));
+  size_t o_err = take(1024);
+  if (w && basep) {
+    w->raw = (float*)(basep + o_raw); w->feat = basep + o_feat; w->vbias = (float*)(basep + o_vb);
+    w->error_flag = (int*)(basep + o_err);
+  }
+  return off;
+}
+
+int* g_trap_host = nullptr;   // mapped pinned int: survives a trapped launch
+int* g_trap_dev = nullptr;
+
+int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std::string* err) {
+  static int num_sms = 0;
+  static bool attr_set = false;
+  if (!g_trap_host) {
+    if (cudaHostAlloc((void**)&g_trap_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&g_trap_dev, g_trap_host, 0) != cudaSuccess) {
+      *err = "cudaHostAlloc(trap flag) failed"; return -1;
+    }
+    *g_trap_host = 0;
+  }
+  p.error_flag = g_trap_dev;
+  if (!attr_set) {
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
+    attr_set = true;
+  }
+  int64_t tiles = (p.P + kTileM - 1) / kTileM;
+  int64_t pairs = (tiles + 1) / 2;
+  int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(pairs, 1));
+  p.n_iters = (int)((pairs + grid - 1) / grid);
+  p.chunks = net.chunks; p.bias = net.bias; p.walpha = net.walpha; p.wrgb = net.wrgb;
+  p.balpha = net.balpha; p.brgb0 = net.brgb[0]; p.brgb1 = net.brgb[1]; p.brgb2 = net.brgb[2];
+  nerf_mlp_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("nerf_mlp_tc_kernel launch: ") + cudaGetErrorString(e); return -1; }
+  *launches += 1;
+  return 0;
+}
+
+}  // namespace
+
+int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err) {
+  const int skipl = skip_layer + 1;
+  out->set = false;
+  if (skipl != 5 || d.xyzp != 96) {   // return 1: configuration valid for the fp32 path only
+    *err = "the tcgen05 path is built for skips=[4] and a 96-wide padded xyz encoding (15 frequencies)";
+    return 1;
+  }
+  std::vector<uint8_t> chunks;
+  for (int s = 0; s < kSteps; ++s) {
+    if (s < kLayers) {
+      const int kin = (s == 0) ? d.xyz : (s == skipl ? d.xyz + kHid : kHid);
+      const float* W = hn.pts_w[s].data();
+      if (s == 0) {
+        for (int c = 0; c < 3; ++c) pack_chunk(chunks, W, kHid, kin, 32 * c, d.xyz);
+      } else if (s == skipl) {
+        for (int c = 0; c < 3; ++c) pack_chunk(chunks, W, kHid, kin, 32 * c, d.xyz);
+        for (int c = 0; c < 8; ++c) pack_chunk(chunks, W + d.xyz, kHid, kin, 32 * c, kHid);
+      } else {
+        for (int c = 0; c < 8; ++c) pack_chunk(chunks, W, kHid, kin, 32 * c, kHid);
+      }
+    } else if (s == 8) {
+      for (int c = 0; c < 8; ++c) pack_chunk(chunks, hn.feature_w.data(), kHid, kHid, 32 * c, kHid);
+    } else {
+      const int vin = kHid + d.dirs + d.app;
+      for (int c = 0; c < 8; ++c) pack_chunk(chunks, hn.views_w.data(), kHalf, vin, 32 * c, kHid);
+    }
+  }
+  if ((int64_t)chunks.size() != step_offset(kSteps)) { *err = "internal: chunk stream size mismatch"; return -1; }
+  std::vector<float> fl;
+  auto put = [&](const float* src, size_t n) { size_t o = fl.size(); fl.insert(fl.end(), src, src + n); fl.resize((fl.size() + 63) / 64 * 64, 0.f); return o; };
+  std::vector<float> bias(9 * kHid);
+  for (int i = 0; i < kLayers; ++i) memcpy(&bias[i * kHid], hn.pts_b[i].data(), kHid * sizeof(float));
+  memcpy(&bias[8 * kHid], hn.feature_b.data(), kHid * sizeof(float));
+  size_t o_bias = put(bias.data(), bias.size());
+  size_t o_wa = put(hn.alpha_w.data(), kHid);
+  size_t o_wr = put(hn.rgb_w.data(), 3 * kHalf);
+  std::vector<float> wvd((size_t)kHalf * d.dap, 0.f);
+  const int vin = kHid + d.dirs + d.app;
+  for (int o = 0; o < kHalf; ++o) memcpy(&wvd[(size_t)o * d.dap], &hn.views_w[(size_t)o * vin + kHid], (d.dirs + d.app) * sizeof(float));
+  size_t o_wvd = put(wvd.data(), wvd.size());
+  size_t o_bv = put(hn.views_b.data(), kHalf);
+
+  size_t cbytes = (chunks.size() + 1023) / 1024 * 1024;
+  size_t total = cbytes + fl.size() * sizeof(float);
+  if (out->pool == nullptr || out->bytes < total) {
+    if (out->pool) cudaFree(out->pool);
+    out->pool = nullptr;
+    cudaError_t e = cudaMalloc(&out->pool, total);
+    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    out->bytes = total;
+  }
+  uint8_t* base = (uint8_t*)out->pool;
+  cudaError_t e = cudaMemcpy(base, chunks.data(), chunks.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(base + cbytes, fl.data(), fl.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+  const float* fb = (const float*)(base + cbytes);
+  out->chunks = base; out->bias = fb + o_bias; out->walpha = fb + o_wa; out->wrgb = fb + o_wr;
+  out->wview_d = fb + o_wvd; out->bview = fb + o_bv;
+  out->balpha = hn.alpha_b[0];
+  for (int i = 0; i < 3; ++i) out->brgb[i] = hn.rgb_b[i];
+  out->set = true;
+  return 0;
+}
+
+int tc_trap_code() { return g_trap_host ? *(volatile int*)g_trap_host : 0; }
+
+void tc_free_net(TcNet* n) {
+  if (n->pool) cudaFree(n->pool);
+  *n = TcNet{};
+}
+
 int64_t tc_round_chunk_rays(const Dims&, int64_t chunk_rays, int64_t) { return chunk_rays; }
-int tc_ensure_workspace(const Dims&, int64_t, void**, size_t*, std::string* err) { *err = "bf16 path not built"; return -1; }
-int tc_run(const Dims&, const TcNet&, const TcRun&, float**, const void**, int*, cudaStream_t, std::string* err) { *err = "bf16 path not built"; return -1; }
-int tc_run_rows(const Dims&, const TcNet&, const float*, int64_t, int, float*, float*, void**, size_t*, int*, cudaStream_t, std::string* err) { *err = "bf16 path not built"; return -1; }
+
+static int reserve(void** ws, size_t* cap, size_t need, std::string* err) {
+  if (*cap >= need && *ws) return 0;
+  if (*ws) cudaFree(*ws);
+  *ws = nullptr; *cap = 0;
+  cudaError_t e = cudaMalloc(ws, need);
+  if (e != cudaSuccess) { *err = std::string("cudaMalloc(") + std::to_string(need) + "): " + cudaGetErrorString(e); return -1; }
+  *cap = need;
+  return cudaMemset(*ws, 0, 1024) == cudaSuccess ? 0 : -1;
+}
+
+int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err) {
+  size_t need = ws_layout(chunk_rays * std::max(d.sc, d.sf), chunk_rays, nullptr, nullptr);
+  return reserve(ws, cap, need, err);
+}
+
+int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, const void** feat_out, int* launches,
+           cudaStream_t s, std::string* err) {
+  if (!net.set) { *err = "weights not packed"; return -1; }
+  if (r.S < 1) { *err = "S < 1"; return -1; }
+  TcWs w{};
+  ws_layout(r.n * std::max(d.sc, d.sf), r.n, &w, (uint8_t*)r.ws);
+  VbParams vp{};
+  vp.mode = 0; vp.rays = r.rays; vp.ncols = r.ncols; vp.ray_id = r.ray_id; vp.app_table = r.app_table; vp.num_frames = r.num_frames;
+  vp.mip = d.mip; vp.fd = d.fd; vp.dirs = d.dirs; vp.app = d.app; vp.dap = d.dap;
+  vp.wview_d = net.wview_d; vp.bview = net.bview; vp.n = r.n; vp.out = w.vbias;
+  view_bias_kernel<<<(unsigned)r.n, 128, 0, s>>>(vp);
+  *launches += 1;
+  TcParams p{};
+  p.vbias = w.vbias; p.vb_div = r.S;
+  p.mode = 0; p.rays = r.rays; p.ncols = r.ncols; p.z = r.z; p.S = r.S; p.mip = d.mip; p.xyz = d.xyz; p.fx = d.fx; p.var_scale = r.var_scale;
+  p.P = r.n * r.S;
+  p.stop_step = r.stop_layer < 0 ? kLayers - 1 : r.stop_layer; p.want_feat = r.want_feat ? 1 : 0;
+  p.raw = w.raw; p.feat_tiles = w.feat; p.debug_step = -1; p.debug_out = nullptr; p.error_flag = w.error_flag;
+  if (launch_tc(net, p, launches, s, err) != 0) return -1;
+  *raw_out = w.raw; *feat_out = w.feat;
+  return 0;
+}
+
+int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int stop_layer, float* raw, float* feat,
+                void** ws, size_t* cap, int* launches, cudaStream_t s, std::string* err, int debug_steps, float* debug_out) {
+  if (!net.set) { *err = "weights not packed"; return -1; }
+  size_t need = ws_layout(P, P, nullptr, nullptr);
+  if (reserve(ws, cap, need, err) != 0) return -1;
+  TcWs w{};
+  ws_layout(P, P, &w, (uint8_t*)*ws);
+  VbParams vp{};
+  vp.mode = 1; vp.X = X; vp.kx = d.kx; vp.xyzp = d.xyzp;
+  vp.mip = d.mip; vp.fd = d.fd; vp.dirs = d.dirs; vp.app = d.app; vp.dap = d.dap;
+  vp.wview_d = net.wview_d; vp.bview = net.bview; vp.n = P; vp.out = w.vbias;
+  view_bias_kernel<<<(unsigned)P, 128, 0, s>>>(vp);
+  *launches += 1;
+  TcParams p{};
+  p.vbias = w.vbias; p.vb_div = 1;
+  p.mode = 1; p.X = X; p.kx = d.kx; p.xyz = d.xyz; p.S = 1;
+  p.P = P;
+  p.stop_step = stop_layer < 0 ? kLayers - 1 : stop_layer; p.want_feat = feat ? 1 : 0;
+  p.raw = w.raw; p.feat_tiles = w.feat; p.error_flag = w.error_flag;
+  p.debug_step = debug_steps > 0 ? debug_steps - 1 : -1; p.debug_out = debug_steps > 0 ? debug_out : nullptr;
+  if (launch_tc(net, p, launches, s, err) != 0) return -1;
+  cudaError_t e = cudaMemcpyAsync(raw, w.raw, (size_t)P * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+  if (feat) {
+    detile_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, s>>>(w.feat, P, feat);
+    *launches += 1;
+  }
+  return 0;
+}
+
 }  // namespace nmr

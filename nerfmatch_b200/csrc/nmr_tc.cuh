@@ -13,11 +13,20 @@ struct HostNet {
   std::vector<float> feature_w, feature_b, alpha_w, alpha_b, views_w, views_b, rgb_w, rgb_b;
 };
 
-// Device-resident bf16 weight tiles + fp32 epilogue vectors of one net.
+// Device-resident bf16 weight chunks (UMMA K-major, 64B-swizzled, in consumption order) and the
+// fp32 vectors the epilogues need.
 struct TcNet {
   void* pool = nullptr;
   size_t bytes = 0;
   bool set = false;
+  const uint8_t* chunks = nullptr;   // weight chunk stream
+  const float* bias = nullptr;       // [9][256]: pts_linears.0..7 bias, feature_linear bias
+  const float* walpha = nullptr;     // [256]
+  const float* wrgb = nullptr;       // [3][128]
+  const float* wview_d = nullptr;    // [128][dap]  dirs+app part of views_linears.0 (fp32)
+  const float* bview = nullptr;      // [128]
+  float balpha = 0.f;
+  float brgb[3] = {0.f, 0.f, 0.f};
 };
 
 struct TcRun {
@@ -33,12 +42,17 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
 void tc_free_net(TcNet* n);
 int64_t tc_round_chunk_rays(const Dims& d, int64_t chunk_rays, int64_t n);
 int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err);
-// Sample rows of one pass (encode + MLP fused): writes raw [n*S,4] fp32 and bf16 features [n*S,256]
+// Sample rows of one pass (encode + MLP fused): writes raw [n*S,4] fp32 and tiled bf16 features
 // into the workspace and returns their addresses.
 int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, const void** feat_out, int* launches,
            cudaStream_t s, std::string* err);
-// Explicit padded fp32 rows X[P,kx] -> raw [P,4], feat fp32 [P,256] (stage API).
+// Explicit padded fp32 rows X[P,kx] -> raw [P,4], feat fp32 [P,256] (stage API).  debug_steps > 0 also
+// dumps the post-activation output of step (debug_steps-1) into debug_out [P,256] (unit tests).
 int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int stop_layer, float* raw, float* feat,
-                void** ws, size_t* cap, int* launches, cudaStream_t s, std::string* err);
+                void** ws, size_t* cap, int* launches, cudaStream_t s, std::string* err, int debug_steps = 0,
+                float* debug_out = nullptr);
+
+// code recorded by a bounded barrier wait before trapping (mapped host memory), 0 = none
+int tc_trap_code();
 
 }  // namespace nmr

@@ -282,6 +282,14 @@ class Engine:
         self.check(st, "nmr_stage_mlp")
         return raw, feat
 
+    def stage_mlp_probe(self, which: int, x, step: int):
+        P = x.shape[0]
+        out = torch.zeros(P, 256, device=self.device)
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_stage_mlp_probe(self.h, which, _ptr(x), P, step, _ptr(out), self.stream())
+        self.check(st, "nmr_stage_mlp_probe")
+        return out
+
     def stage_composite(self, raw, z, rays_d, flags=0, feats=None, pts=None):
         n, S = raw.shape[0], raw.shape[1]
         dev = self.device

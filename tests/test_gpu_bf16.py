@@ -1,0 +1,165 @@
+"""The bf16 tcgen05 / TMEM MLP path: step-by-step against a numpy bf16 emulation, then end to end
+against the reference-generated goldens with the north-star bf16 criterion (cosine >= 0.999)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from nmr_helpers import RENDER_CASES, build_renderer, case_setup, cosine_rows, load_golden, ray_rel_err, rel_l2  # noqa: E402
+from oracle import nerf_oracle as O  # noqa: E402
+from oracle.weights import K_7SCENES, make_pose, make_state_dict, uniform01  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def bf16(x):
+    """round-to-nearest-even to bfloat16, returned as float32"""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def emulate_steps(wts, x, cfg):
+    """Outputs of the 10 MLP steps with bf16 operands / fp32 accumulation, as the kernel computes them."""
+    xd, dd = cfg.xyz_dim, cfg.dirs_dim
+    enc = bf16(x[:, :xd])
+    side = x[:, xd:]
+    W = lambda k: bf16(wts[k])
+    outs = []
+    h = enc
+    for i in range(8):
+        w = W(f"pts_linears.{i}.weight")
+        if i == 5:
+            pre = enc @ w[:, :xd].T + h @ w[:, xd:].T
+        else:
+            pre = h @ w.T
+        act = np.maximum(pre + wts[f"pts_linears.{i}.bias"], 0).astype(np.float32)
+        outs.append(act)
+        h = bf16(act)
+    alpha = outs[7] @ wts["alpha_linear.weight"].T + wts["alpha_linear.bias"]
+    feat = (h @ W("feature_linear.weight").T + wts["feature_linear.bias"]).astype(np.float32)
+    outs.append(feat)
+    wv = wts["views_linears.0.weight"]
+    vb = side @ wv[:, 256:].T + wts["views_linears.0.bias"]
+    hv = np.maximum(bf16(feat) @ bf16(wv[:, :256]).T + vb, 0).astype(np.float32)
+    outs.append(hv)
+    rgb = 1 / (1 + np.exp(-(hv @ wts["rgb_linear.weight"].T + wts["rgb_linear.bias"])))
+    return outs, np.concatenate([rgb, alpha], -1).astype(np.float32)
+
+
+def engine(**kw):
+    from nerfmatch_b200.engine import Engine, EngineConfig
+
+    return Engine(EngineConfig(**kw), torch.device(DEV))
+
+
+@pytest.mark.parametrize("embed,app", [("mip", False), ("normal", True)])
+def test_tc_mlp_step_by_step(embed, app):
+    from nerfmatch_b200 import _lib as L
+
+    cfg = O.RenderConfig(embed_type=embed, app_dim=16 if app else 0)
+    sd = make_state_dict(61, embed_type=embed, app_dim=cfg.app_dim, num_frames=5 if app else 0, sigma_gain=30.0, sigma_bias=1.0)
+    wts = O.split_state_dict(sd, "nerf_fine.")
+    eng = engine(embed_type=embed, app_dim=cfg.app_dim, precision="bf16")
+    eng.set_weights(0, {k: torch.from_numpy(v) for k, v in wts.items()})
+    P = 128 * 5 + 37        # several tiles over few CTAs + a ragged tail
+    in_dim = cfg.xyz_dim + cfg.dirs_dim + cfg.app_dim
+    x = (uniform01(62, 1, P * in_dim).reshape(P, in_dim) * 2 - 1).astype(np.float32)
+    outs, raw_ref = emulate_steps(wts, x, cfg)
+    for step in range(10):
+        got = N(eng.stage_mlp_probe(0, T(x), step))
+        torch.cuda.synchronize()
+        assert L.load().nmr_debug_trap_code() == 0
+        ncol = 128 if step == 9 else 256
+        err = rel_l2(got[:, :ncol], outs[step])
+        assert err < 2e-3, (step, err)
+    raw, feat = eng.stage_mlp(0, T(x), 3)
+    np.testing.assert_allclose(N(raw), raw_ref, rtol=2e-3, atol=2e-3)
+    assert rel_l2(N(feat), bf16(outs[3])) < 2e-3
+    for stop in (-1, 0, 7):
+        _, f = eng.stage_mlp(0, T(x), stop)
+        assert rel_l2(N(f), bf16(outs[7 if stop < 0 else stop])) < 2e-3, stop
+
+
+def test_tc_mlp_many_tiles_matches_fp32_path():
+    """More tiles than CTAs (several persistent iterations, both slots, odd tile count) vs the fp32 SIMT path."""
+    embed = "normal"
+    cfg = O.RenderConfig(embed_type=embed)
+    sd = make_state_dict(63, embed_type=embed, sigma_gain=30.0, sigma_bias=1.0)
+    wts = {k: torch.from_numpy(v) for k, v in O.split_state_dict(sd, "nerf_coarse.").items()}
+    P = 128 * (148 * 2 * 2 + 3) + 5
+    x = (torch.rand(P, cfg.xyz_dim + cfg.dirs_dim, device=DEV, generator=torch.Generator(DEV).manual_seed(1)) * 2 - 1)
+    a = engine(embed_type=embed, precision="bf16"); a.set_weights(0, wts)
+    b = engine(embed_type=embed, precision="fp32"); b.set_weights(0, wts)
+    ra, fa = a.stage_mlp(0, x, 3)
+    rb, fb = b.stage_mlp(0, x, 3)
+    assert torch.isfinite(ra).all() and torch.isfinite(fa).all()
+    cos = torch.nn.functional.cosine_similarity(fa, fb, dim=-1)
+    assert cos.min() > 0.999, cos.min()
+    assert (ra[:, :3] - rb[:, :3]).abs().max() < 2e-2
+    assert rel_l2(N(ra[:, 3]), N(rb[:, 3])) < 2e-2
+
+
+def _render_bf16(name):
+    g = load_golden(f"render_{name}.npz")
+    cfg, sd, c = case_setup(g)
+    ren = build_renderer(c, sd, precision="bf16")
+    rays = T(g["rays"])
+    n = rays.shape[0]
+    eng = ren.engine(rays.device)
+    outs = eng.alloc_outputs(n, True, True, intermediates=True)
+    kw = {}
+    if cfg.embed_type == "mip":
+        kw = dict(t_rand=T(g["t_rand"]), u_jitter=T(g["u_jitter"]))
+    rid = T(g["ray_id"]) if "ray_id" in g else (torch.ones(n, dtype=torch.int64, device=DEV) if c["app"] else None)
+    args, keep = eng.make_args(n, rays.shape[1], rays=rays, ray_id=rid, flags=ren._flags(), unnorm=g["unnorm_scene"], outs=outs, **kw)
+    eng.render(args)
+    torch.cuda.synchronize()
+    return g, cfg, c, {k: N(v) for k, v in outs.items()}
+
+
+@pytest.mark.parametrize("name", RENDER_CASES)
+def test_full_render_bf16_matches_reference(name):
+    """North star for the bf16 MLP: composited features with cosine >= 0.999 per ray against the reference
+    renderer's fp32 output; depth / points within bf16-level error."""
+    g, cfg, c, out = _render_bf16(name)
+    peaky = max(c["sigma_gain"]) > 1000        # sigma gain ~5e3 amplifies bf16 round-off into O(1) density changes
+    for key in ("coarse", "fine"):
+        if cfg.feat_comb == "lin":
+            cos = cosine_rows(out[f"feat_{key}"], g[f"feat_{key}"])
+            if not peaky:
+                assert cos.min() >= 0.999, (key, cos.min())
+                assert rel_l2(out[f"depth_{key}"], g[f"depth_{key}"]) < 2e-2, key
+                assert np.abs(out[f"pts_{key}"] - g[f"pts_{key}"]).max() < 2e-2, key
+            else:
+                assert np.median(cos) >= 0.999 and (cos >= 0.99).mean() > 0.9, (key, np.median(cos), (cos >= 0.99).mean())
+        assert np.isfinite(out[f"feat_{key}"]).all() and np.isfinite(out[f"rgb_{key}"]).all()
+        assert np.abs(out[f"rgb_{key}"] - g[f"rgb_{key}"]).max() < (0.05 if not peaky else 0.5), key
+    # sampling is fp32 in both precisions: coarse fence posts are identical to the fp32 path
+    np.testing.assert_allclose(out["z_coarse"], g["z_coarse"], rtol=0, atol=1e-6)
+
+
+def test_bf16_vs_fp32_path_same_view():
+    """Same 1200-ray view through both precisions of OUR path: aggregate agreement of every output."""
+    for embed in ("mip", "normal"):
+        c = dict(embed=embed, nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+        sd = make_state_dict(41, embed_type=embed, sigma_gain=60.0, sigma_bias=(4.0, 2.0))
+        rays = T(O.sample_nerf_rays(480, 640, K_7SCENES, make_pose(7), ds=16, embed_type=embed))
+        res = {}
+        for prec in ("fp32", "bf16"):
+            ren = build_renderer(c, sd, precision=prec)
+            ren.rng = "none"
+            res[prec] = {k: N(v) for k, v in ren.predict(rays, 1, 1).items()}
+        cos = cosine_rows(res["bf16"]["feat_fine"], res["fp32"]["feat_fine"])
+        assert cos.min() > 0.999, (embed, cos.min())
+        for k in ("depth_fine", "pts_fine", "rgb_fine", "depth_coarse", "feat_coarse"):
+            assert rel_l2(res["bf16"][k], res["fp32"][k]) < 2e-2, (embed, k)
