@@ -110,7 +110,7 @@ def run_reference(args):
 def config_block(embed, precision):
     return {"workload": f"7-Scenes {H}x{W} full-res feature render, {embed} embedding, 64 coarse + 128 fine samples "
                         f"({256 if embed == 'normal' else 128} MLP evals/ray), stop_layer=3, random-init weights",
-            "rays_per_step_per_gpu": H * W, "precision": precision, "parallelism": "rays sharded by view, weights replicated",
+            "rays_per_step_per_gpu": H * W, "precision": precision, "parallelism": "rays sharded by view (one view per GPU per step), weights replicated, feat_fine + pt3d gathered to rank 0 (NCCL) when N > 1",
             "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set is also >> 126 MB"}
 
 
@@ -194,6 +194,28 @@ def run_ours(args):
     h2d = rays_h.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in outs_h.values())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # N > 1: the one real exchange of the path - rendered features + 3D points gathered to the matcher's rank 0
+    gbuf = None
+    if world > 1:
+        gbuf = {k: ([torch.empty_like(outs[k]) for _ in range(world)] if rank == 0 else None) for k in ("feat_fine", "pt3d")}
+
+    def gather_to_matcher(o):
+        if world > 1:
+            for k in ("feat_fine", "pt3d"):
+                dist.gather(o[k], gbuf[k], dst=0)
+
+    def step_dev():
+        eng.render(dargs)
+        gather_to_matcher(outs)
+
+    outs_back = {k: torch.empty_like(outs[k]) for k in ("feat_fine", "pt3d")} if world > 1 else None
+
+    def step_host():
+        eng.render_host(hargs)
+        if world > 1:   # host results of every rank travel to rank 0 over NVLink: re-upload, gather
+            for k in ("feat_fine", "pt3d"):
+                outs_back[k].copy_(outs_h[k], non_blocking=True)
+            gather_to_matcher(outs_back)
 
     def barrier():
         if world > 1:
@@ -223,7 +245,7 @@ def run_ours(args):
         sampler.start()
     eng.set_timing(False)
     l0 = eng.launch_count()
-    ms_dev, t0, t1 = timed(lambda: eng.render(dargs), args.steps, args.warmup)
+    ms_dev, t0, t1 = timed(step_dev, args.steps, args.warmup)
     launches = (eng.launch_count() - l0) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     # ---- per-stage split (separate pass, CUDA events on the launch stream inside the library) ----
@@ -234,7 +256,7 @@ def run_ours(args):
     stage = eng.last_stage_ms()
     eng.set_timing(False)
     # ---- end-to-end arm ----
-    ms_e2e, _, _ = timed(lambda: eng.render_host(hargs), args.steps, max(1, args.warmup // 2))
+    ms_e2e, _, _ = timed(step_host, args.steps, max(3, args.warmup))
 
     total_rays = n * world
     value = total_rays * args.steps / (ms_dev / 1e3)

@@ -197,6 +197,9 @@ NMR_API int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z,
 NMR_API int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int64_t P, int32_t step, float* out,
                                 void* stream);
 NMR_API int nmr_debug_trap_code(void);
+/* Tuning knob of the tcgen05 path (process-wide): size of the thread-block cluster that shares each weight
+ * chunk through TMA multicast - 1 (off), 2 or 4.  Default 2, or the NMR_TC_CLUSTER environment variable. */
+NMR_API int nmr_set_tc_cluster(int cluster_size);
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 NMR_API int64_t nmr_launch_count(const nmr_handle* h);

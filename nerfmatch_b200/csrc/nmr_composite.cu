@@ -343,16 +343,38 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
       if (p.idx_out) p.idx_out[ray * N + j] = inds;
     }
     __syncwarp();
-    // sort(cat(z, samples)): stable rank by counting (robust even if a list is not monotone)
+    // sort(cat(z, samples)).  Both lists are (normally) already sorted, so the stable rank of an element
+    // is its own index plus a binary search in the other list: z_i -> i + #{samples < z_i},
+    // sample_j -> j + #{z <= sample_j} (ties keep the concatenation order, like a stable sort).  If fp
+    // round-off ever breaks monotonicity the warp falls back to the O(T^2) counting rank, which needs no
+    // assumption; torch.sort returns the same multiset either way.
     const int T = S + N;
-    for (int e = lane; e < T; e += 32) {
-      float v = comb[e];
-      int rank = 0;
-      for (int f = 0; f < T; ++f) {
-        float q = comb[f];
-        rank += (q < v) || (q == v && f < e);
+    bool mono = true;
+    for (int j = lane; j < T; j += 32)
+      if (j != 0 && j != S && comb[j] < comb[j - 1]) mono = false;
+    if (__all_sync(0xffffffffu, mono)) {
+      for (int e = lane; e < T; e += 32) {
+        float v = comb[e];
+        int rank;
+        if (e < S) {            // #{samples < v}: lower bound
+          int lo = 0, hi = N;
+          while (lo < hi) { int mid = (lo + hi) >> 1; if (comb[S + mid] < v) lo = mid + 1; else hi = mid; }
+          rank = e + lo;
+        } else {
+          rank = (e - S) + upper_bound(comb, S, v);
+        }
+        p.z_next[ray * T + rank] = v;
       }
-      p.z_next[ray * T + rank] = v;
+    } else {
+      for (int e = lane; e < T; e += 32) {
+        float v = comb[e];
+        int rank = 0;
+        for (int f = 0; f < T; ++f) {
+          float q = comb[f];
+          rank += (q < v) || (q == v && f < e);
+        }
+        p.z_next[ray * T + rank] = v;
+      }
     }
   }
 }

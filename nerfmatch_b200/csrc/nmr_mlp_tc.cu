@@ -4,23 +4,26 @@
 //     (kind::f16, bf16 operands, fp32 accumulate) issued by ONE thread, accumulators in TMEM;
 //   * positional encoding (kernel (a)'s encode half) is fused in: four encoder warps turn ray /
 //     sample data into the bf16 A-operand tile directly in shared memory - the encoded inputs never
-//     touch HBM;
+//     touch HBM; the encoder runs one tile ahead of the MLP (two E buffers);
 //   * activations never leave the SM: the epilogue warps read the accumulator with tcgen05.ld, add
 //     bias, apply ReLU, round to bf16 and write the next layer's A operand in place, in the UMMA
 //     K-major 64B-swizzled layout.  The skip connection is a second K segment into the same
 //     accumulator; sigma (alpha_linear) and rgb (rgb_linear + sigmoid) are fp32 dot products in the
 //     epilogues of the layers that feed them; the [dirs | appearance] part of views_linears is a
 //     per-ray fp32 bias computed once per ray;
-//   * weights stream from L2 through a ring of shared-memory stages filled by the bulk-copy (TMA)
-//     engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the host, so no tensor
-//     map is needed;
+//   * the accumulator is double buffered in TMEM (2 x 256 columns, alternating by layer) and the
+//     epilogue hands the next layer's operand over in 32-column chunks (one mbarrier per chunk), so
+//     the tensor core starts layer l+1 on chunk 0 while the epilogue is still draining layer l;
+//   * weights stream from L2 through a 6-stage ring of 16 KB shared-memory stages filled by the
+//     bulk-copy (TMA) engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the
+//     host, so no tensor map is needed.  With a thread-block cluster of C CTAs every CTA fetches 1/C
+//     of each chunk and multicasts it to its peers (cp.async.bulk ... .multicast::cluster), cutting
+//     L2 -> SM weight traffic by C;
 //   * the tapped feature tile (stop_layer) leaves as one 64 KB bulk store shared->global in the same
-//     tiled layout the compositor reads;
-//   * two 128-point tiles are in flight per CTA ("slots"): while the tensor core runs layer l of one
-//     slot, the other slot's epilogue drains layer l from its half of TMEM (2 x 256 columns).
+//     tiled layout the compositor reads.
 //
-// Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 idle,
-// 4-7 epilogue of slot 0, 8-11 epilogue of slot 1, 12-15 encoder.
+// Warp roles (384 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 idle,
+// 4-7 epilogue, 8-11 encoder.
 #include <cstring>
 
 #include "nmr_encode.cuh"
@@ -34,19 +37,23 @@ constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64
 constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
 constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
 constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
-constexpr int kStages = 3;
+constexpr int kStages = 6;
 constexpr int kSteps = 10;                 // 8 trunk layers, feature_linear, views_linears.0
-constexpr int kThreads = 512;
+constexpr int kThreads = 384;
 constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128 points
 
 constexpr int OFF_H = 0;
-constexpr int OFF_E = 2 * kHBytes;
+constexpr int OFF_E = kHBytes;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
-constexpr int OFF_BAR = OFF_W + kStages * kStageBytes;
-constexpr int kSmemBytes = OFF_BAR + 256 + 1024;   // + alignment slack
+constexpr int OFF_BIAS = OFF_W + kStages * kStageBytes;       // fp32 [9][256] bias, [256] walpha, [3][128] wrgb
+constexpr int kBiasFloats = 9 * kHid + kHid + 3 * kHalf;
+constexpr int OFF_BAR = OFF_BIAS + kBiasFloats * 4;
+constexpr int kSmemBytes = OFF_BAR + 512 + 1024;              // + alignment slack
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
-enum { BAR_WFULL = 0, BAR_WEMPTY = 3, BAR_ACCFULL = 6, BAR_AREADY = 8, BAR_EFULL = 10, BAR_EEMPTY = 12, BAR_COUNT = 14 };
+enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_HREADY = BAR_ACCFULL + 2,
+       BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_COUNT = BAR_EEMPTY + 2 };
+static_assert(BAR_COUNT * 8 + 16 <= 512, "barrier area");
 
 struct TcParams {
   const uint8_t* chunks; const float* bias; const float* walpha; const float* wrgb;
@@ -93,8 +100,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must never hang the GPU box - after ~0.2 s record where and trap.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* error_flag, int code) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 400000000LL) {
@@ -104,16 +110,32 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, error_flag, code);
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
@@ -146,6 +168,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -168,37 +194,109 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int c) {
   return (uint32_t)(((r >> 3) << 9) + ((r & 7) << 6) + ((c ^ ((r & 7) >> 1)) << 4));
 }
 
+// One 32-column slice of the epilogue: bias + activation, fp32 heads, bf16 hand-over to the next layer.
+struct EpiCtx {
+  const float* sbias; const float* swalpha; const float* swrgb;   // shared-memory copies
+  const float* vb;                                                 // per-ray view bias row (global) or null
+  uint32_t h_base; int r; int s; bool writes_h;
+  float alpha, c0, c1, c2;
+};
+__device__ __forceinline__ void epi_chunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, bool valid, int64_t pt) {
+  float x[32];
+  if (e.s < 9) {
+    const float4* bp = reinterpret_cast<const float4*>(e.sbias + e.s * kHid + j * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = bp[i];
+      x[4 * i] = __uint_as_float(v[4 * i]) + t.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + t.y;
+      x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + t.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = e.vb ? __ldg(reinterpret_cast<const float4*>(e.vb + j * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[4 * i] = __uint_as_float(v[4 * i]) + t.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + t.y;
+      x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + t.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + t.w;
+    }
+  }
+  if (e.s != 8) {                                  // feature_linear has no activation
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
+  }
+  if (e.s == 7) {                                  // alpha_linear on the un-rounded fp32 activations
+    const float4* wp = reinterpret_cast<const float4*>(e.swalpha + j * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 w = wp[i];
+      e.alpha = fmaf(x[4 * i], w.x, fmaf(x[4 * i + 1], w.y, fmaf(x[4 * i + 2], w.z, fmaf(x[4 * i + 3], w.w, e.alpha))));
+    }
+  }
+  if (e.s == 9) {                                  // rgb_linear
+    const float4* w0 = reinterpret_cast<const float4*>(e.swrgb + j * 32);
+    const float4* w1 = reinterpret_cast<const float4*>(e.swrgb + kHalf + j * 32);
+    const float4* w2 = reinterpret_cast<const float4*>(e.swrgb + 2 * kHalf + j * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 a = w0[i], b = w1[i], c = w2[i];
+      e.c0 = fmaf(x[4 * i], a.x, fmaf(x[4 * i + 1], a.y, fmaf(x[4 * i + 2], a.z, fmaf(x[4 * i + 3], a.w, e.c0))));
+      e.c1 = fmaf(x[4 * i], b.x, fmaf(x[4 * i + 1], b.y, fmaf(x[4 * i + 2], b.z, fmaf(x[4 * i + 3], b.w, e.c1))));
+      e.c2 = fmaf(x[4 * i], c.x, fmaf(x[4 * i + 1], c.y, fmaf(x[4 * i + 2], c.z, fmaf(x[4 * i + 3], c.w, e.c2))));
+    }
+  }
+  if (e.writes_h) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t w0 = pack_bf16(x[8 * c], x[8 * c + 1]), w1 = pack_bf16(x[8 * c + 2], x[8 * c + 3]);
+      uint32_t w2 = pack_bf16(x[8 * c + 4], x[8 * c + 5]), w3 = pack_bf16(x[8 * c + 6], x[8 * c + 7]);
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.h_base + j * kBlk + sw64_off(e.r, c)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+    }
+  }
+  if (p.debug_out && e.s == p.debug_step && valid) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = x[i];
+  }
+}
+
 // ---- the kernel ----------------------------------------------------------------------------
+template <int CSIZE>
 __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + OFF_BAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + BAR_COUNT * 8);
+  float* sbias = reinterpret_cast<float*>(gbase + OFF_BIAS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
+  const uint32_t crank = (CSIZE > 1) ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = (uint16_t)((1u << CSIZE) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), CSIZE); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bars + 8 * (BAR_ACCFULL + s), 1);
-      mbar_init(bars + 8 * (BAR_AREADY + s), 128);
       mbar_init(bars + 8 * (BAR_EFULL + s), 128);
       mbar_init(bars + 8 * (BAR_EEMPTY + s), 1);
     }
+    for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + BAR_COUNT * 8), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
+  // epilogue constants -> shared memory (bias table, alpha / rgb head weights)
+  for (int i = threadIdx.x; i < 9 * kHid; i += kThreads) sbias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < kHid; i += kThreads) sbias[9 * kHid + i] = p.walpha[i];
+  for (int i = threadIdx.x; i < 3 * kHalf; i += kThreads) sbias[10 * kHid + i] = p.wrgb[i];
   tc_fence_before();
   __syncthreads();
+  if (CSIZE > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== weight producer: bulk-copy chunks global -> smem ring =====
+    // ===== weight producer: bulk-copy chunks global -> smem ring (multicast across the cluster) =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < p.n_iters; ++it) {
@@ -206,224 +304,191 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(TcParams p) {
         for (int s = 0; s < kSteps; ++s) {
           const int nch = step_chunks_e(s) + step_chunks_h(s);
           const uint32_t bytes = step_chunk_bytes(s);
-          for (int slot = 0; slot < 2; ++slot) {
-            for (int c = 0; c < nch; ++c) {
-              mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
-              mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
-              bulk_g2s(base + OFF_W + stage * kStageBytes, src + (size_t)c * bytes, bytes, bars + 8 * (BAR_WFULL + stage));
-              if (++stage == kStages) { stage = 0; phase ^= 1; }
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
+            mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
+            if (CSIZE == 1) {
+              bulk_g2s(base + OFF_W + stage * kStageBytes, src, bytes, bars + 8 * (BAR_WFULL + stage));
+            } else {
+              const uint32_t part = bytes / CSIZE;
+              bulk_g2s_mcast(base + OFF_W + stage * kStageBytes + crank * part, src + crank * part, part,
+                             bars + 8 * (BAR_WFULL + stage), kMask);
             }
+            src += bytes;
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          src += (size_t)nch * bytes;
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      int stage = 0; uint32_t wphase = 0;
-      uint32_t ph_aready[2] = {0, 0}, ph_efull[2] = {0, 0};
+      int stage = 0; uint32_t wphase = 0, hphase = 0;
+      uint32_t ph_efull[2] = {0, 0};
       for (int it = 0; it < p.n_iters; ++it) {
+        const int eb = it & 1;
         for (int s = 0; s < kSteps; ++s) {
           const int ne = step_chunks_e(s), nh = step_chunks_h(s);
-          const int N = (s == 9) ? 128 : 256;
-          const uint32_t idesc = umma_idesc(N);
-          for (int slot = 0; slot < 2; ++slot) {
-            // inputs of this step: previous epilogue of this slot done (TMEM drained, H written)
-            mbar_wait(bars + 8 * (BAR_AREADY + slot), ph_aready[slot], p.error_flag, 200 + slot);
-            ph_aready[slot] ^= 1;
-            if (s == 0) {
-              mbar_wait(bars + 8 * (BAR_EFULL + slot), ph_efull[slot], p.error_flag, 210 + slot);
-              ph_efull[slot] ^= 1;
+          const uint32_t idesc = umma_idesc((s == 9) ? 128 : 256);
+          const uint32_t d_tmem = tmem_base + (s & 1) * 256;       // accumulator ping-pong by layer
+          if (s == 0) {
+            mbar_wait(bars + 8 * (BAR_EFULL + eb), ph_efull[eb], p.error_flag, 210 + eb);
+            ph_efull[eb] ^= 1;
+          }
+          uint32_t accumulate = 0;
+          for (int c = 0; c < ne + nh; ++c) {
+            uint32_t a_addr;
+            const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
+            if (c < ne) {
+              a_addr = base + OFF_E + eb * kEBytes + c * kBlk;
+              mbar_wait(wbar, wphase, p.error_flag, 220 + stage);
+            } else {
+              // chunk (c-ne) of the previous layer's output: handed over by the epilogue
+              a_addr = base + OFF_H + (c - ne) * kBlk;
+              const uint32_t hbar = bars + 8 * (BAR_HREADY + (c - ne));
+              const bool ok_h = mbar_try_wait(hbar, hphase), ok_w = mbar_try_wait(wbar, wphase);   // both probes in flight
+              if (!ok_h) mbar_wait_slow(hbar, hphase, p.error_flag, 230 + (c - ne));
+              if (!ok_w) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
             }
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + slot * 256;
-            uint32_t accumulate = 0;
-            for (int c = 0; c < ne + nh; ++c) {
-              const uint32_t a_addr = (c < ne) ? (base + OFF_E + slot * kEBytes + c * kBlk)
-                                               : (base + OFF_H + slot * kHBytes + (c - ne) * kBlk);
-              mbar_wait(bars + 8 * (BAR_WFULL + stage), wphase, p.error_flag, 220 + stage);
-              tc_fence_after();
-              const uint32_t b_addr = base + OFF_W + stage * kStageBytes;
+            const uint32_t b_addr = base + OFF_W + stage * kStageBytes;
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                umma_bf16(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, accumulate);
-                accumulate = 1;
-              }
-              umma_commit(bars + 8 * (BAR_WEMPTY + stage));      // stage free once these MMAs retire
-              if (++stage == kStages) { stage = 0; wphase ^= 1; }
+            for (int k = 0; k < 2; ++k) {
+              umma_bf16(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, accumulate);
+              accumulate = 1;
             }
-            umma_commit(bars + 8 * (BAR_ACCFULL + slot));        // accumulator complete -> epilogue
-            if (s == 5) umma_commit(bars + 8 * (BAR_EEMPTY + slot));  // encoded tile no longer needed
+            // stage free once these MMAs retire (in every CTA of the cluster: peers multicast into it)
+            if (CSIZE == 1) umma_commit(bars + 8 * (BAR_WEMPTY + stage));
+            else umma_commit_mcast(bars + 8 * (BAR_WEMPTY + stage), kMask);
+            if (++stage == kStages) { stage = 0; wphase ^= 1; }
           }
+          umma_commit(bars + 8 * (BAR_ACCFULL + (s & 1)));         // accumulator complete -> epilogue
+          if (s == 5) umma_commit(bars + 8 * (BAR_EEMPTY + eb));   // encoded tile no longer needed
+          if (nh) hphase ^= 1;
         }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < 8) {
     // ===== epilogue warps: TMEM -> bias/activation -> bf16 A operand of the next layer =====
-    const int slot = (warp - 4) >> 2;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                    // row of the tile
-    const int et = (warp - 4 - slot * 4) * 32 + lane;  // thread index inside the slot's epilogue group
-    const uint32_t h_base = base + OFF_H + slot * kHBytes;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
-    mbar_arrive(bars + 8 * (BAR_AREADY + slot));    // TMEM / H start out free
-    uint32_t ph_acc = 0;
+    const int et = (warp - 4) * 32 + lane;
+    const uint32_t h_base = base + OFF_H;
+    uint32_t ph_acc[2] = {0, 0};
     bool store_pending = false;
+    EpiCtx e;
+    e.sbias = sbias; e.swalpha = sbias + 9 * kHid; e.swrgb = sbias + 10 * kHid; e.h_base = h_base; e.r = r;
     for (int it = 0; it < p.n_iters; ++it) {
-      const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
+      const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
-      float alpha = 0.f;
+      e.alpha = 0.f;
       for (int s = 0; s < kSteps; ++s) {
-        mbar_wait(bars + 8 * (BAR_ACCFULL + slot), ph_acc, p.error_flag, 300 + slot);
-        ph_acc ^= 1;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (s & 1) * 256;
+        e.s = s; e.writes_h = s < 9; e.c0 = e.c1 = e.c2 = 0.f;
+        e.vb = (s == 9 && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
+        mbar_wait(bars + 8 * (BAR_ACCFULL + (s & 1)), ph_acc[s & 1], p.error_flag, 300 + (s & 1));
+        ph_acc[s & 1] ^= 1;
         tc_fence_after();
-        const bool writes_h = s < 9;
-        if (writes_h && store_pending) {            // the tap store must have finished reading H
+        if (e.writes_h && store_pending) {          // the tap store must have finished reading H
           if (et == 0) bulk_wait_read0();
-          named_bar_sync(1 + slot, 128);
+          named_bar_sync(1, 128);
           store_pending = false;
         }
         const int nj = (s == 9) ? 4 : 8;
-        float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-        const float* vb = (s == 9 && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
-        for (int j = 0; j < nj; ++j) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + j * 32, v);
-          float b[32];
-          if (s < 9) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + s * kHid + j * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { float4 t = __ldg(bp + i); b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w; }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) b[i] = 0.f;
-            if (vb) {
-              const float4* bp = reinterpret_cast<const float4*>(vb + j * 32);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { float4 t = __ldg(bp + i); b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w; }
-            }
-          }
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_lane, va);
+        for (int j = 0; j < nj; j += 2) {           // software pipelined: load slice j+1 while slice j is processed
           tmem_ld_wait();
-          float x[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float t = __uint_as_float(v[i]) + b[i];
-            x[i] = (s != 8) ? fmaxf(t, 0.f) : t;     // feature_linear has no activation
-          }
-          if (s == 7) {                              // alpha_linear on the un-rounded fp32 activations
-            const float4* wp = reinterpret_cast<const float4*>(p.walpha + j * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 w = __ldg(wp + i);
-              alpha = fmaf(x[4 * i], w.x, fmaf(x[4 * i + 1], w.y, fmaf(x[4 * i + 2], w.z, fmaf(x[4 * i + 3], w.w, alpha))));
-            }
-          }
-          if (s == 9) {                              // rgb_linear
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              c0 = fmaf(x[i], __ldg(p.wrgb + j * 32 + i), c0);
-              c1 = fmaf(x[i], __ldg(p.wrgb + kHalf + j * 32 + i), c1);
-              c2 = fmaf(x[i], __ldg(p.wrgb + 2 * kHalf + j * 32 + i), c2);
-            }
-          }
-          if (writes_h) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              uint32_t w0 = pack_bf16(x[8 * c], x[8 * c + 1]), w1 = pack_bf16(x[8 * c + 2], x[8 * c + 3]);
-              uint32_t w2 = pack_bf16(x[8 * c + 4], x[8 * c + 5]), w3 = pack_bf16(x[8 * c + 6], x[8 * c + 7]);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h_base + j * kBlk + sw64_off(r, c)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-            }
-          }
-          if (p.debug_out && s == p.debug_step && valid) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = x[i];
-          }
-        }
-        if (s == 9 && valid) {
-          float4 o;
-          o.x = 1.f / (1.f + __expf(-(c0 + p.brgb0)));
-          o.y = 1.f / (1.f + __expf(-(c1 + p.brgb1)));
-          o.z = 1.f / (1.f + __expf(-(c2 + p.brgb2)));
-          o.w = alpha + p.balpha;
-          *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+          tmem_ld32(t_lane + (j + 1) * 32, vb);
+          epi_chunk(e, va, j, p, valid, pt);
+          if (e.writes_h) { fence_proxy_async(); mbar_arrive(bars + 8 * (BAR_HREADY + j)); }
+          tmem_ld_wait();
+          if (j + 2 < nj) tmem_ld32(t_lane + (j + 2) * 32, va);
+          epi_chunk(e, vb, j + 1, p, valid, pt);
+          if (e.writes_h) { fence_proxy_async(); mbar_arrive(bars + 8 * (BAR_HREADY + j + 1)); }
         }
         tc_fence_before();
-        if (writes_h) fence_proxy_async();           // generic-proxy writes -> visible to UMMA / bulk copy
+        if (s == 9 && valid) {
+          float4 o;
+          o.x = 1.f / (1.f + __expf(-(e.c0 + p.brgb0)));
+          o.y = 1.f / (1.f + __expf(-(e.c1 + p.brgb1)));
+          o.z = 1.f / (1.f + __expf(-(e.c2 + p.brgb2)));
+          o.w = e.alpha + p.balpha;
+          *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+        }
         if (s == p.stop_step && p.want_feat) {
-          named_bar_sync(1 + slot, 128);
+          named_bar_sync(1, 128);                    // all 128 rows written (and fenced) before the bulk store
           if (et == 0 && tile * kTileM < p.P) {
             bulk_s2g(p.feat_tiles + (size_t)tile * kFeatTileBytes, h_base, kFeatTileBytes);
             bulk_commit();
           }
           store_pending = true;
         }
-        mbar_arrive(bars + 8 * (BAR_AREADY + slot));
       }
     }
     if (et == 0) bulk_wait0();
-  } else if (warp >= 12) {
+  } else if (warp >= 8) {
     // ===== encoder warps: sampling data -> positional encoding -> bf16 A tile of layer 0 / skip =====
-    const int r = (warp - 12) * 32 + lane;
+    const int r = (warp - 8) * 32 + lane;
     uint32_t ph_eempty[2] = {0, 0};
     for (int it = 0; it < p.n_iters; ++it) {
-      for (int slot = 0; slot < 2; ++slot) {
-        const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
-        const int64_t pt = tile * kTileM + r;
-        const bool valid = pt < p.P;
-        float m[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
-        const float* xrow = nullptr;
-        if (valid) {
-          if (p.mode == 0) {
-            const int64_t ray = pt / p.S;
-            const int sidx = (int)(pt - ray * p.S);
-            const float* rr = p.rays + ray * p.ncols;
-            if (p.mip) {
-              const float* z = p.z + ray * (p.S + 1);
-              float rl[12];
+      const int eb = it & 1;
+      const int64_t tile = (int64_t)it * G + blockIdx.x;
+      const int64_t pt = tile * kTileM + r;
+      const bool valid = pt < p.P;
+      float m[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
+      const float* xrow = nullptr;
+      if (valid) {
+        if (p.mode == 0) {
+          const int64_t ray = pt / p.S;
+          const int sidx = (int)(pt - ray * p.S);
+          const float* rr = p.rays + ray * p.ncols;
+          if (p.mip) {
+            const float* z = p.z + ray * (p.S + 1);
+            float rl[12];
 #pragma unroll
-              for (int i = 0; i < 12; ++i) rl[i] = __ldg(rr + i);
-              frustum_gaussian(rl, __ldg(z + sidx), __ldg(z + sidx + 1), p.var_scale, m, vv);
-            } else {
-              const float zz = __ldg(p.z + pt);
-#pragma unroll
-              for (int c = 0; c < 3; ++c) m[c] = __ldg(rr + c) + __ldg(rr + 3 + c) * zz;
-            }
+            for (int i = 0; i < 12; ++i) rl[i] = __ldg(rr + i);
+            frustum_gaussian(rl, __ldg(z + sidx), __ldg(z + sidx + 1), p.var_scale, m, vv);
           } else {
-            xrow = p.X + pt * p.kx;
-          }
-        }
-        mbar_wait(bars + 8 * (BAR_EEMPTY + slot), ph_eempty[slot] ^ 1, p.error_flag, 400 + slot);
-        ph_eempty[slot] ^= 1;
-        const uint32_t e_base = base + OFF_E + slot * kEBytes;
-        for (int kb = 0; kb < 3; ++kb) {
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            float f[8];
+            const float zz = __ldg(p.z + pt);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int col = kb * 32 + c * 8 + i;
-              float val = 0.f;
-              if (valid && col < p.xyz) {
-                if (p.mode == 1) val = __ldg(xrow + col);
-                else val = p.mip ? ipe_col(m, vv, p.fx, col) : fourier_col(m, p.fx, col);
-              }
-              f[i] = val;
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e_base + kb * kBlk + sw64_off(r, c)),
-                         "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+            for (int c = 0; c < 3; ++c) m[c] = __ldg(rr + c) + __ldg(rr + 3 + c) * zz;
           }
+        } else {
+          xrow = p.X + pt * p.kx;
         }
-        fence_proxy_async();
-        mbar_arrive(bars + 8 * (BAR_EFULL + slot));
       }
+      mbar_wait(bars + 8 * (BAR_EEMPTY + eb), ph_eempty[eb] ^ 1, p.error_flag, 400 + eb);
+      ph_eempty[eb] ^= 1;
+      const uint32_t e_base = base + OFF_E + eb * kEBytes;
+      for (int kb = 0; kb < 3; ++kb) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int col = kb * 32 + c * 8 + i;
+            float val = 0.f;
+            if (valid && col < p.xyz) {
+              if (p.mode == 1) val = __ldg(xrow + col);
+              else val = p.mip ? ipe_col(m, vv, p.fx, col) : fourier_col(m, p.fx, col);
+            }
+            f[i] = val;
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e_base + kb * kBlk + sw64_off(r, c)),
+                       "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(bars + 8 * (BAR_EFULL + eb));
     }
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  if (CSIZE > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -437,31 +502,40 @@ struct VbParams {
   int mip; int fd; int dirs; int app; int dap;
   const float* wview_d; const float* bview; int64_t n; float* out;
 };
+constexpr int kVbRows = 32;   // rays (rows) per block: the transposed weight panel is staged once per block
 __global__ void __launch_bounds__(128) view_bias_kernel(VbParams p) {
-  __shared__ float de[64];
-  const int64_t row = blockIdx.x;
+  __shared__ float wt[48][129];
+  __shared__ float de[2][48];
   const int t = threadIdx.x;
-  if (t < p.dap) {
-    float v = 0.f;
-    if (p.mode == 1) {
-      v = p.X[row * p.kx + p.xyzp + t];
-    } else if (t < p.dirs) {
-      const float* rr = p.rays + row * p.ncols;
-      const float* vd = (p.ncols >= 11) ? rr + 8 : rr + 3;
-      float v3[3] = {vd[0], vd[1], vd[2]};
-      v = p.mip ? pe_col(v3, p.fd, t) : fourier_col(v3, p.fd, t);
-    } else if (t < p.dirs + p.app) {
-      int64_t id = p.ray_id ? p.ray_id[row] : 1;
-      id = id < 0 ? 0 : (id >= p.num_frames ? p.num_frames - 1 : id);
-      v = p.app_table[id * p.app + (t - p.dirs)];
+  const int nk = p.dirs + p.app;
+  for (int i = t; i < kHalf * p.dap; i += 128) { int o = i / p.dap, k = i - o * p.dap; wt[k][o] = p.wview_d[i]; }
+  const float bv = p.bview[t];
+  const int64_t row0 = (int64_t)blockIdx.x * kVbRows;
+  for (int rr = 0; rr < kVbRows; ++rr) {
+    const int64_t row = row0 + rr;
+    if (row >= p.n) break;
+    float* d = de[rr & 1];
+    if (t < p.dap) {
+      float v = 0.f;
+      if (p.mode == 1) {
+        v = p.X[row * p.kx + p.xyzp + t];
+      } else if (t < p.dirs) {
+        const float* ry = p.rays + row * p.ncols;
+        const float* vd = (p.ncols >= 11) ? ry + 8 : ry + 3;
+        float v3[3] = {vd[0], vd[1], vd[2]};
+        v = p.mip ? pe_col(v3, p.fd, t) : fourier_col(v3, p.fd, t);
+      } else if (t < nk) {
+        int64_t id = p.ray_id ? p.ray_id[row] : 1;
+        id = id < 0 ? 0 : (id >= p.num_frames ? p.num_frames - 1 : id);
+        v = p.app_table[id * p.app + (t - p.dirs)];
+      }
+      d[t] = v;
     }
-    de[t] = v;
+    __syncthreads();
+    float acc = 0.f;
+    for (int k = 0; k < nk; ++k) acc = fmaf(d[k], wt[k][t], acc);
+    p.out[row * kHalf + t] = acc + bv;
   }
-  __syncthreads();
-  float acc = 0.f;
-  const float* w = p.wview_d + t * p.dap;
-  for (int k = 0; k < p.dirs + p.app; ++k) acc = fmaf(de[k], w[k], acc);
-  p.out[row * kHalf + t] = acc + p.bview[t];
 }
 
 // tiled bf16 features -> fp32 [P,256] rows (stage API only)
@@ -523,33 +597,49 @@ size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep) {
 int* g_trap_host = nullptr;   // mapped pinned int: survives a trapped launch
 int* g_trap_dev = nullptr;
 
+int g_cluster = -1;   // weight-multicast cluster size: 1, 2 or 4 (NMR_TC_CLUSTER env, default 2)
+
+template <int CSIZE>
+int launch_cluster(const TcParams& p, int grid, cudaStream_t s, std::string* err) {
+  cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<CSIZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+  if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CSIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc_kernel<CSIZE>, p);
+  if (e != cudaSuccess) { *err = std::string("nerf_mlp_tc_kernel launch: ") + cudaGetErrorString(e); return -1; }
+  return 0;
+}
+
 int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std::string* err) {
   static int num_sms = 0;
-  static bool attr_set = false;
   if (!g_trap_host) {
     if (cudaHostAlloc((void**)&g_trap_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&g_trap_dev, g_trap_host, 0) != cudaSuccess) {
       *err = "cudaHostAlloc(trap flag) failed"; return -1;
     }
     *g_trap_host = 0;
-  }
-  p.error_flag = g_trap_dev;
-  if (!attr_set) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
-    attr_set = true;
   }
+  if (g_cluster < 0) {
+    const char* ev = getenv("NMR_TC_CLUSTER");
+    g_cluster = ev ? atoi(ev) : 2;
+    if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 2;
+  }
+  p.error_flag = g_trap_dev;
+  const int cs = g_cluster;
   int64_t tiles = (p.P + kTileM - 1) / kTileM;
-  int64_t pairs = (tiles + 1) / 2;
-  int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(pairs, 1));
-  p.n_iters = (int)((pairs + grid - 1) / grid);
+  int grid = (int)std::min<int64_t>(num_sms / cs * cs, (std::max<int64_t>(tiles, 1) + cs - 1) / cs * cs);
+  p.n_iters = (int)((tiles + grid - 1) / grid);
+  if (p.n_iters < 1) p.n_iters = 1;
   p.chunks = net.chunks; p.bias = net.bias; p.walpha = net.walpha; p.wrgb = net.wrgb;
   p.balpha = net.balpha; p.brgb0 = net.brgb[0]; p.brgb1 = net.brgb[1]; p.brgb2 = net.brgb[2];
-  nerf_mlp_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { *err = std::string("nerf_mlp_tc_kernel launch: ") + cudaGetErrorString(e); return -1; }
+  int r = cs == 1 ? launch_cluster<1>(p, grid, s, err) : cs == 2 ? launch_cluster<2>(p, grid, s, err) : launch_cluster<4>(p, grid, s, err);
+  if (r != 0) return r;
   *launches += 1;
   return 0;
 }
@@ -620,6 +710,12 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
   return 0;
 }
 
+int tc_set_cluster(int cs) {
+  if (cs != 1 && cs != 2 && cs != 4) return -1;
+  g_cluster = cs;
+  return 0;
+}
+
 int tc_trap_code() { return g_trap_host ? *(volatile int*)g_trap_host : 0; }
 
 void tc_free_net(TcNet* n) {
@@ -654,7 +750,7 @@ int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, con
   vp.mode = 0; vp.rays = r.rays; vp.ncols = r.ncols; vp.ray_id = r.ray_id; vp.app_table = r.app_table; vp.num_frames = r.num_frames;
   vp.mip = d.mip; vp.fd = d.fd; vp.dirs = d.dirs; vp.app = d.app; vp.dap = d.dap;
   vp.wview_d = net.wview_d; vp.bview = net.bview; vp.n = r.n; vp.out = w.vbias;
-  view_bias_kernel<<<(unsigned)r.n, 128, 0, s>>>(vp);
+  view_bias_kernel<<<(unsigned)((r.n + kVbRows - 1) / kVbRows), 128, 0, s>>>(vp);
   *launches += 1;
   TcParams p{};
   p.vbias = w.vbias; p.vb_div = r.S;
@@ -678,7 +774,7 @@ int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int 
   vp.mode = 1; vp.X = X; vp.kx = d.kx; vp.xyzp = d.xyzp;
   vp.mip = d.mip; vp.fd = d.fd; vp.dirs = d.dirs; vp.app = d.app; vp.dap = d.dap;
   vp.wview_d = net.wview_d; vp.bview = net.bview; vp.n = P; vp.out = w.vbias;
-  view_bias_kernel<<<(unsigned)P, 128, 0, s>>>(vp);
+  view_bias_kernel<<<(unsigned)((P + kVbRows - 1) / kVbRows), 128, 0, s>>>(vp);
   *launches += 1;
   TcParams p{};
   p.vbias = w.vbias; p.vb_div = 1;

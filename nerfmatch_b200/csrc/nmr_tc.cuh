@@ -54,5 +54,6 @@ int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int 
 
 // code recorded by a bounded barrier wait before trapping (mapped host memory), 0 = none
 int tc_trap_code();
+int tc_set_cluster(int cluster_size);   // 1, 2 or 4
 
 }  // namespace nmr

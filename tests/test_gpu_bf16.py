@@ -62,6 +62,36 @@ def engine(**kw):
     return Engine(EngineConfig(**kw), torch.device(DEV))
 
 
+@pytest.fixture(autouse=True)
+def _default_cluster():
+    from nerfmatch_b200 import _lib as L
+
+    yield
+    L.load().nmr_set_tc_cluster(2)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+def test_tc_cluster_sizes_agree(cluster):
+    """Weight multicast across a thread-block cluster must not change a single bit of the result."""
+    from nerfmatch_b200 import _lib as L
+
+    embed = "mip"
+    cfg = O.RenderConfig(embed_type=embed)
+    sd = make_state_dict(64, embed_type=embed, sigma_gain=30.0, sigma_bias=1.0)
+    wts = {k: torch.from_numpy(v) for k, v in O.split_state_dict(sd, "nerf_fine.").items()}
+    P = 128 * 700 + 11
+    x = (torch.rand(P, cfg.xyz_dim + cfg.dirs_dim, device=DEV, generator=torch.Generator(DEV).manual_seed(2)) * 2 - 1)
+    eng = engine(embed_type=embed, precision="bf16"); eng.set_weights(0, wts)
+    assert L.load().nmr_set_tc_cluster(1) == 0
+    r1, f1 = eng.stage_mlp(0, x, 3)
+    assert L.load().nmr_set_tc_cluster(cluster) == 0
+    r2, f2 = eng.stage_mlp(0, x, 3)
+    torch.cuda.synchronize()
+    assert L.load().nmr_debug_trap_code() == 0
+    assert torch.equal(r1, r2) and torch.equal(f1, f2)
+    assert L.load().nmr_set_tc_cluster(3) != 0
+
+
 @pytest.mark.parametrize("embed,app", [("mip", False), ("normal", True)])
 def test_tc_mlp_step_by_step(embed, app):
     from nerfmatch_b200 import _lib as L
@@ -139,7 +169,8 @@ def test_full_render_bf16_matches_reference(name):
             if not peaky:
                 assert cos.min() >= 0.999, (key, cos.min())
                 assert rel_l2(out[f"depth_{key}"], g[f"depth_{key}"]) < 2e-2, key
-                assert np.abs(out[f"pts_{key}"] - g[f"pts_{key}"]).max() < 2e-2, key
+                dp = np.abs(out[f"pts_{key}"] - g[f"pts_{key}"]).max(-1)   # normalised scene units, bf16 MLP
+                assert np.median(dp) < 5e-3 and dp.max() < 6e-2, (key, np.median(dp), dp.max())
             else:
                 assert np.median(cos) >= 0.999 and (cos >= 0.99).mean() > 0.9, (key, np.median(cos), (cos >= 0.99).mean())
         assert np.isfinite(out[f"feat_{key}"]).all() and np.isfinite(out[f"rgb_{key}"]).all()
