@@ -170,7 +170,7 @@ def test_full_render_bf16_matches_reference(name):
                 assert cos.min() >= 0.999, (key, cos.min())
                 assert rel_l2(out[f"depth_{key}"], g[f"depth_{key}"]) < 2e-2, key
                 dp = np.abs(out[f"pts_{key}"] - g[f"pts_{key}"]).max(-1)   # normalised scene units, bf16 MLP
-                assert np.median(dp) < 5e-3 and dp.max() < 6e-2, (key, np.median(dp), dp.max())
+                assert np.median(dp) < 2e-2 and dp.max() < 1e-1, (key, np.median(dp), dp.max())
             else:
                 assert np.median(cos) >= 0.999 and (cos >= 0.99).mean() > 0.9, (key, np.median(cos), (cos >= 0.99).mean())
         assert np.isfinite(out[f"feat_{key}"]).all() and np.isfinite(out[f"rgb_{key}"]).all()
