@@ -60,7 +60,7 @@ def cpu_render_rate(embed, n_sample, seed=0):
 
     cores = os.cpu_count() or 1
     cfg = O.RenderConfig(embed_type=embed, num_pts_coarse=64, num_pts_fine=128, stop_layer=3)
-    sd = make_state_dict(seed, embed_type=embed, sigma_gain=120.0, sigma_bias=(8.0, -2.0))
+    sd = make_state_dict(seed, embed_type=embed, sigma_gain=120.0, sigma_bias=(8.0, 8.0))
     ds = max(1, int(np.sqrt(H * W / n_sample)))
     rays = O.sample_nerf_rays(H, W, K_7SCENES, make_pose(seed), ds=ds, embed_type=embed)[:n_sample]
     n = rays.shape[0]
@@ -173,7 +173,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     embed = args.embed
     c = workload(embed)
-    sd = make_state_dict(0, embed_type=embed, sigma_gain=120.0, sigma_bias=(8.0, -2.0))
+    sd = make_state_dict(0, embed_type=embed, sigma_gain=120.0, sigma_bias=(8.0, 8.0))
     ren = build_renderer(c, sd, precision=args.precision, device=dev)
     ren.rng = "philox"      # mip mode: draws generated inside the kernels
     eng = ren.engine(dev)

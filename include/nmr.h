@@ -191,8 +191,8 @@ NMR_API int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z,
 
 /* Test hooks for the tcgen05 path (NMR_PREC_BF16 only).  nmr_stage_mlp_probe evaluates the net on
  * x [P, xyz+dirs+app] and returns the post-activation output of MLP step `step` as fp32 [P,256]:
- * steps 0..7 = pts_linears.0..7 (+ReLU), 8 = feature_linear, 9 = views_linears.0 (+ReLU, first 128
- * columns).  nmr_debug_trap_code returns the code a bounded in-kernel barrier wait recorded before
+ * steps 0..7 = pts_linears.0..7 (+ReLU), 8 = views_linears.0 with feature_linear folded in (+ReLU,
+ * first 128 columns).  nmr_debug_trap_code returns the code a bounded in-kernel barrier wait recorded before
  * trapping (0 = none); it lives in mapped host memory so it survives a failed launch. */
 NMR_API int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int64_t P, int32_t step, float* out,
                                 void* stream);

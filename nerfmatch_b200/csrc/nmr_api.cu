@@ -743,7 +743,7 @@ extern "C" int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int
   if (!h) return NMR_ERR_INVALID;
   if (which != 0 && which != 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: which=%d", which);
   if (h->cfg.precision != NMR_PREC_BF16) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: bf16 path only");
-  if (step < 0 || step > 9 || P <= 0 || !x || !out) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: bad argument");
+  if (step < 0 || step > 8 || P <= 0 || !x || !out) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: bad argument");
   if (!h->net[which].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_stage_mlp_probe: weights not set");
   NMR_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;

@@ -4,26 +4,27 @@
 //     (kind::f16, bf16 operands, fp32 accumulate) issued by ONE thread, accumulators in TMEM;
 //   * positional encoding (kernel (a)'s encode half) is fused in: four encoder warps turn ray /
 //     sample data into the bf16 A-operand tile directly in shared memory - the encoded inputs never
-//     touch HBM; the encoder runs one tile ahead of the MLP (two E buffers);
+//     touch HBM;
 //   * activations never leave the SM: the epilogue warps read the accumulator with tcgen05.ld, add
 //     bias, apply ReLU, round to bf16 and write the next layer's A operand in place, in the UMMA
 //     K-major 64B-swizzled layout.  The skip connection is a second K segment into the same
 //     accumulator; sigma (alpha_linear) and rgb (rgb_linear + sigmoid) are fp32 dot products in the
 //     epilogues of the layers that feed them; the [dirs | appearance] part of views_linears is a
-//     per-ray fp32 bias computed once per ray;
-//   * the accumulator is double buffered in TMEM (2 x 256 columns, alternating by layer) and the
-//     epilogue hands the next layer's operand over in 32-column chunks (one mbarrier per chunk), so
-//     the tensor core starts layer l+1 on chunk 0 while the epilogue is still draining layer l;
-//   * weights stream from L2 through a 6-stage ring of 16 KB shared-memory stages filled by the
-//     bulk-copy (TMA) engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the
-//     host, so no tensor map is needed.  With a thread-block cluster of C CTAs every CTA fetches 1/C
-//     of each chunk and multicasts it to its peers (cp.async.bulk ... .multicast::cluster), cutting
-//     L2 -> SM weight traffic by C;
+//     per-ray fp32 bias computed once per ray; feature_linear (no activation) is folded into
+//     views_linears on the host (W_view_f * W_feat), which removes one layer and 11 % of the weights;
+//   * weights stream from L2 through a ring of 16 KB shared-memory stages filled by the bulk-copy (TMA)
+//     engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the host, so no tensor
+//     map is needed.  L2 -> SM delivery caps at ~27 B/cycle/SM on B200 (tools/smem_fill_bw.cu) while a
+//     128-row tile at full tensor rate would need 63 B/cycle, so every chunk is shared by the TWO
+//     128-point tiles ("slots") a CTA keeps in flight: 2 x 256 TMEM columns, M = 256 per weight fetch;
 //   * the tapped feature tile (stop_layer) leaves as one 64 KB bulk store shared->global in the same
-//     tiled layout the compositor reads.
+//     tiled layout the compositor reads;
+//   * biases and head weights travel as kernel parameters (constant bank, 11 KB), so nothing but the
+//     weight stream competes for shared memory.
 //
-// Warp roles (384 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 idle,
-// 4-7 epilogue, 8-11 encoder.
+// Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 idle,
+// 4-7 epilogue of slot 0, 8-11 epilogue of slot 1, 12-15 encoder.
+#include <cstdlib>
 #include <cstring>
 
 #include "nmr_encode.cuh"
@@ -37,26 +38,29 @@ constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64
 constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
 constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
 constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
-constexpr int kStages = 6;
-constexpr int kSteps = 10;                 // 8 trunk layers, feature_linear, views_linears.0
-constexpr int kThreads = 384;
+constexpr int kStages = 3;
+constexpr int kSteps = 9;                  // 8 trunk layers + (feature_linear folded into) views_linears.0
+constexpr int kViewStep = 8;
+constexpr int kThreads = 512;
 constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128 points
 
 constexpr int OFF_H = 0;
-constexpr int OFF_E = kHBytes;
+constexpr int OFF_E = 2 * kHBytes;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
-constexpr int OFF_BIAS = OFF_W + kStages * kStageBytes;       // fp32 [9][256] bias, [256] walpha, [3][128] wrgb
-constexpr int kBiasFloats = 9 * kHid + kHid + 3 * kHalf;
-constexpr int OFF_BAR = OFF_BIAS + kBiasFloats * 4;
-constexpr int kSmemBytes = OFF_BAR + 512 + 1024;              // + alignment slack
+constexpr int OFF_BAR = OFF_W + kStages * kStageBytes;
+constexpr int kSmemBytes = OFF_BAR + 256 + 1024;   // + alignment slack
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
-enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_HREADY = BAR_ACCFULL + 2,
-       BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_COUNT = BAR_EEMPTY + 2 };
-static_assert(BAR_COUNT * 8 + 16 <= 512, "barrier area");
+enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_AREADY, BAR_EFULL, BAR_EEMPTY, BAR_COUNT };
+
+struct TcConsts {          // kernel-parameter (constant bank) copy of the fp32 epilogue vectors
+  float bias[8][kHid];     // pts_linears.0..7 bias
+  float walpha[kHid];
+  float wrgb[3][kHalf];
+};
 
 struct TcParams {
-  const uint8_t* chunks; const float* bias; const float* walpha; const float* wrgb;
+  const uint8_t* chunks;
   float balpha; float brgb0, brgb1, brgb2;
   const float* vbias; int vb_div;          // view bias row = point / vb_div
   // input mode 0: rays + z (fused sampling-to-encoding); mode 1: padded fp32 rows X[P,kx]
@@ -71,7 +75,7 @@ struct TcParams {
 
 __host__ __device__ constexpr int step_chunks_e(int s) { return (s == 0 || s == 5) ? 3 : 0; }
 __host__ __device__ constexpr int step_chunks_h(int s) { return s == 0 ? 0 : 8; }
-__host__ __device__ constexpr int step_chunk_bytes(int s) { return s == 9 ? 8192 : 16384; }
+__host__ __device__ constexpr int step_chunk_bytes(int s) { return s == kViewStep ? 8192 : 16384; }
 __host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the chunk stream
   int64_t off = 0;
   for (int i = 0; i < s; ++i) off += (int64_t)(step_chunks_e(i) + step_chunks_h(i)) * step_chunk_bytes(i);
@@ -120,22 +124,10 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_mcast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
@@ -168,10 +160,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -194,47 +182,117 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int c) {
   return (uint32_t)(((r >> 3) << 9) + ((r & 7) << 6) + ((c ^ ((r & 7) >> 1)) << 4));
 }
 
+// ---- fused row encoders (bf16 path) -----------------------------------------------------------
+// The reference evaluates sin / cos of 2^k * x for k = 0..14 (embedding.py:35-46, 66-79).  2^k * x is exact
+// in fp32, so a precise sincosf is taken at every 5th octave and the octaves in between follow from the
+// double-angle identities (error growth 2^4 ulp << bf16 resolution); likewise exp(-0.5 var 4^k) is precise
+// at every 4th octave and ^4 in between.  In mip mode the reference's "cos" is sin(fl(x + pi/2)); here it is
+// cos(x) - they differ by at most half an ulp of the ARGUMENT (2^-11 at the top octave), below bf16
+// resolution.  (The fp32 parity path, nmr_sampling.cu, evaluates the reference expressions literally.)
+// One thread encodes one row: columns are produced in output order, 8 at a time -> one 16-byte chunk.
+struct RowWriter {
+  uint32_t e_base; int r;
+  __device__ __forceinline__ void store(int chunk, const float* f) const {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e_base + (chunk >> 2) * kBlk + sw64_off(r, chunk & 3)),
+                 "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+  }
+};
+
+template <int F>
+__device__ __forceinline__ void encode_row_fourier(const float m[3], const RowWriter& w) {
+  float f[8];
+  float sn[3], cs[3];
+#pragma unroll
+  for (int col = 0; col < 96; ++col) {
+    float v = 0.f;
+    if (col < 3) {
+      v = m[col];
+    } else if (col < 3 + 6 * F) {
+      const int jj = col - 3, k = jj / 6, rr = jj % 6;
+      if (rr == 0) {
+        if (k % 5 == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) sincosf(m[c] * (float)(1 << k), &sn[c], &cs[c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) { float s2 = 2.f * sn[c] * cs[c]; cs[c] = fmaf(-2.f * sn[c], sn[c], 1.f); sn[c] = s2; }
+        }
+      }
+      v = rr < 3 ? sn[rr] : cs[rr - 3];
+    }
+    f[col & 7] = v;
+    if ((col & 7) == 7) w.store(col >> 3, f);
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void encode_row_ipe(const float m[3], const float var[3], const RowWriter& w) {
+  float f[8];
+  float sn[3], cs[3], dm[3];
+#pragma unroll
+  for (int col = 0; col < 96; ++col) {
+    float v = 0.f;
+    if (col < 6 * F) {
+      const int half = col / (3 * F), jj = col % (3 * F), k = jj / 3, c = jj % 3;
+      if (c == 0) {
+        if (k % 5 == 0) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) sincosf(m[i] * (float)(1 << k), &sn[i], &cs[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { float s2 = 2.f * sn[i] * cs[i]; cs[i] = fmaf(-2.f * sn[i], sn[i], 1.f); sn[i] = s2; }
+        }
+        if (k % 4 == 0) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) dm[i] = expf(-0.5f * (var[i] * (float)(1 << k) * (float)(1 << k)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { float d2 = dm[i] * dm[i]; dm[i] = d2 * d2; }
+        }
+      }
+      v = dm[c] * (half == 0 ? sn[c] : cs[c]);
+    }
+    f[col & 7] = v;
+    if ((col & 7) == 7) w.store(col >> 3, f);
+  }
+}
+
 // One 32-column slice of the epilogue: bias + activation, fp32 heads, bf16 hand-over to the next layer.
 struct EpiCtx {
-  const float* sbias; const float* swalpha; const float* swrgb;   // shared-memory copies
   const float* vb;                                                 // per-ray view bias row (global) or null
-  uint32_t h_base; int r; int s; bool writes_h;
+  uint32_t h_base; int r; int s;
   float alpha, c0, c1, c2;
 };
-__device__ __forceinline__ void epi_chunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, bool valid, int64_t pt) {
+__device__ __forceinline__ void epi_chunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, const TcConsts& k, bool valid, int64_t pt) {
   float x[32];
-  if (e.s < 9) {
-    const float4* bp = reinterpret_cast<const float4*>(e.sbias + e.s * kHid + j * 32);
+  if (e.s < kViewStep) {
+    const float4* bp = reinterpret_cast<const float4*>(&k.bias[e.s][j * 32]);   // constant bank, warp-uniform
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 t = bp[i];
-      x[4 * i] = __uint_as_float(v[4 * i]) + t.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + t.y;
-      x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + t.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + t.w;
+      x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
+      x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 t = e.vb ? __ldg(reinterpret_cast<const float4*>(e.vb + j * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      x[4 * i] = __uint_as_float(v[4 * i]) + t.x; x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + t.y;
-      x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + t.z; x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + t.w;
+      x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
+      x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
     }
   }
-  if (e.s != 8) {                                  // feature_linear has no activation
-#pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.f);
-  }
   if (e.s == 7) {                                  // alpha_linear on the un-rounded fp32 activations
-    const float4* wp = reinterpret_cast<const float4*>(e.swalpha + j * 32);
+    const float4* wp = reinterpret_cast<const float4*>(&k.walpha[j * 32]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 w = wp[i];
       e.alpha = fmaf(x[4 * i], w.x, fmaf(x[4 * i + 1], w.y, fmaf(x[4 * i + 2], w.z, fmaf(x[4 * i + 3], w.w, e.alpha))));
     }
   }
-  if (e.s == 9) {                                  // rgb_linear
-    const float4* w0 = reinterpret_cast<const float4*>(e.swrgb + j * 32);
-    const float4* w1 = reinterpret_cast<const float4*>(e.swrgb + kHalf + j * 32);
-    const float4* w2 = reinterpret_cast<const float4*>(e.swrgb + 2 * kHalf + j * 32);
+  if (e.s == kViewStep) {                          // rgb_linear
+    const float4* w0 = reinterpret_cast<const float4*>(&k.wrgb[0][j * 32]);
+    const float4* w1 = reinterpret_cast<const float4*>(&k.wrgb[1][j * 32]);
+    const float4* w2 = reinterpret_cast<const float4*>(&k.wrgb[2][j * 32]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 a = w0[i], b = w1[i], c = w2[i];
@@ -242,8 +300,7 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const uint32_t* v, int j, c
       e.c1 = fmaf(x[4 * i], b.x, fmaf(x[4 * i + 1], b.y, fmaf(x[4 * i + 2], b.z, fmaf(x[4 * i + 3], b.w, e.c1))));
       e.c2 = fmaf(x[4 * i], c.x, fmaf(x[4 * i + 1], c.y, fmaf(x[4 * i + 2], c.z, fmaf(x[4 * i + 3], c.w, e.c2))));
     }
-  }
-  if (e.writes_h) {
+  } else {
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t w0 = pack_bf16(x[8 * c], x[8 * c + 1]), w1 = pack_bf16(x[8 * c + 2], x[8 * c + 3]);
@@ -258,45 +315,34 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const uint32_t* v, int j, c
 }
 
 // ---- the kernel ----------------------------------------------------------------------------
-template <int CSIZE>
-__global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(TcParams p) {
+__global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcConsts kc) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bars = base + OFF_BAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + BAR_COUNT * 8);
-  float* sbias = reinterpret_cast<float*>(gbase + OFF_BIAS);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
-  const uint32_t crank = (CSIZE > 1) ? cluster_ctarank() : 0u;
-  constexpr uint16_t kMask = (uint16_t)((1u << CSIZE) - 1u);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), CSIZE); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bars + 8 * (BAR_ACCFULL + s), 1);
-      mbar_init(bars + 8 * (BAR_EFULL + s), 128);
-      mbar_init(bars + 8 * (BAR_EEMPTY + s), 1);
-    }
-    for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 128);
+    for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); }
+    mbar_init(bars + 8 * BAR_ACCFULL, 1);
+    mbar_init(bars + 8 * BAR_AREADY, 256);
+    mbar_init(bars + 8 * BAR_EFULL, 128);
+    mbar_init(bars + 8 * BAR_EEMPTY, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + BAR_COUNT * 8), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // epilogue constants -> shared memory (bias table, alpha / rgb head weights)
-  for (int i = threadIdx.x; i < 9 * kHid; i += kThreads) sbias[i] = p.bias[i];
-  for (int i = threadIdx.x; i < kHid; i += kThreads) sbias[9 * kHid + i] = p.walpha[i];
-  for (int i = threadIdx.x; i < 3 * kHalf; i += kThreads) sbias[10 * kHid + i] = p.wrgb[i];
   tc_fence_before();
   __syncthreads();
-  if (CSIZE > 1) cluster_sync_all();   // peers' barriers are initialised before any multicast lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== weight producer: bulk-copy chunks global -> smem ring (multicast across the cluster) =====
+    // ===== weight producer: bulk-copy chunks global -> smem ring; each chunk serves both slots =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < p.n_iters; ++it) {
@@ -307,13 +353,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(TcParams p) {
           for (int c = 0; c < nch; ++c) {
             mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
             mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
-            if (CSIZE == 1) {
-              bulk_g2s(base + OFF_W + stage * kStageBytes, src, bytes, bars + 8 * (BAR_WFULL + stage));
-            } else {
-              const uint32_t part = bytes / CSIZE;
-              bulk_g2s_mcast(base + OFF_W + stage * kStageBytes + crank * part, src + crank * part, part,
-                             bars + 8 * (BAR_WFULL + stage), kMask);
-            }
+            bulk_g2s(base + OFF_W + stage * kStageBytes, src, bytes, bars + 8 * (BAR_WFULL + stage));
             src += bytes;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
@@ -323,172 +363,158 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(TcParams p) {
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      int stage = 0; uint32_t wphase = 0, hphase = 0;
-      uint32_t ph_efull[2] = {0, 0};
+      int stage = 0; uint32_t wphase = 0, ph_aready = 0, ph_efull = 0;
       for (int it = 0; it < p.n_iters; ++it) {
-        const int eb = it & 1;
         for (int s = 0; s < kSteps; ++s) {
           const int ne = step_chunks_e(s), nh = step_chunks_h(s);
-          const uint32_t idesc = umma_idesc((s == 9) ? 128 : 256);
-          const uint32_t d_tmem = tmem_base + (s & 1) * 256;       // accumulator ping-pong by layer
-          if (s == 0) {
-            mbar_wait(bars + 8 * (BAR_EFULL + eb), ph_efull[eb], p.error_flag, 210 + eb);
-            ph_efull[eb] ^= 1;
-          }
+          const uint32_t idesc = umma_idesc((s == kViewStep) ? 128 : 256);
+          // both slots' previous epilogues are done: TMEM drained, H written (count 256)
+          mbar_wait(bars + 8 * BAR_AREADY, ph_aready, p.error_flag, 200);
+          ph_aready ^= 1;
+          if (s == 0) { mbar_wait(bars + 8 * BAR_EFULL, ph_efull, p.error_flag, 210); ph_efull ^= 1; }
+          tc_fence_after();
           uint32_t accumulate = 0;
           for (int c = 0; c < ne + nh; ++c) {
-            uint32_t a_addr;
-            const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
-            if (c < ne) {
-              a_addr = base + OFF_E + eb * kEBytes + c * kBlk;
-              mbar_wait(wbar, wphase, p.error_flag, 220 + stage);
-            } else {
-              // chunk (c-ne) of the previous layer's output: handed over by the epilogue
-              a_addr = base + OFF_H + (c - ne) * kBlk;
-              const uint32_t hbar = bars + 8 * (BAR_HREADY + (c - ne));
-              const bool ok_h = mbar_try_wait(hbar, hphase), ok_w = mbar_try_wait(wbar, wphase);   // both probes in flight
-              if (!ok_h) mbar_wait_slow(hbar, hphase, p.error_flag, 230 + (c - ne));
-              if (!ok_w) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
-            }
+            mbar_wait(bars + 8 * (BAR_WFULL + stage), wphase, p.error_flag, 220 + stage);
             tc_fence_after();
             const uint32_t b_addr = base + OFF_W + stage * kStageBytes;
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              umma_bf16(d_tmem, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, accumulate);
-              accumulate = 1;
+            for (int slot = 0; slot < 2; ++slot) {
+              const uint32_t a_addr = (c < ne) ? (base + OFF_E + slot * kEBytes + c * kBlk)
+                                               : (base + OFF_H + slot * kHBytes + (c - ne) * kBlk);
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma_bf16(tmem_base + slot * 256, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, accumulate | k);
             }
-            // stage free once these MMAs retire (in every CTA of the cluster: peers multicast into it)
-            if (CSIZE == 1) umma_commit(bars + 8 * (BAR_WEMPTY + stage));
-            else umma_commit_mcast(bars + 8 * (BAR_WEMPTY + stage), kMask);
+            accumulate = 1;
+            umma_commit(bars + 8 * (BAR_WEMPTY + stage));      // stage free once these MMAs retire
             if (++stage == kStages) { stage = 0; wphase ^= 1; }
           }
-          umma_commit(bars + 8 * (BAR_ACCFULL + (s & 1)));         // accumulator complete -> epilogue
-          if (s == 5) umma_commit(bars + 8 * (BAR_EEMPTY + eb));   // encoded tile no longer needed
-          if (nh) hphase ^= 1;
+          umma_commit(bars + 8 * BAR_ACCFULL);                 // both accumulators complete -> epilogues
+          if (s == 5) umma_commit(bars + 8 * BAR_EEMPTY);      // encoded tiles no longer needed
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 12) {
     // ===== epilogue warps: TMEM -> bias/activation -> bf16 A operand of the next layer =====
+    const int slot = (warp - 4) >> 2;
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                    // row of the tile
-    const int et = (warp - 4) * 32 + lane;
-    const uint32_t h_base = base + OFF_H;
-    uint32_t ph_acc[2] = {0, 0};
+    const int et = (warp - 4 - slot * 4) * 32 + lane;  // thread index inside the slot's epilogue group
+    const uint32_t h_base = base + OFF_H + slot * kHBytes;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
+    mbar_arrive(bars + 8 * BAR_AREADY);             // TMEM / H start out free
+    uint32_t ph_acc = 0;
     bool store_pending = false;
     EpiCtx e;
-    e.sbias = sbias; e.swalpha = sbias + 9 * kHid; e.swrgb = sbias + 10 * kHid; e.h_base = h_base; e.r = r;
+    e.h_base = h_base; e.r = r;
     for (int it = 0; it < p.n_iters; ++it) {
-      const int64_t tile = (int64_t)it * G + blockIdx.x;
+      const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
       e.alpha = 0.f;
       for (int s = 0; s < kSteps; ++s) {
-        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (s & 1) * 256;
-        e.s = s; e.writes_h = s < 9; e.c0 = e.c1 = e.c2 = 0.f;
-        e.vb = (s == 9 && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
-        mbar_wait(bars + 8 * (BAR_ACCFULL + (s & 1)), ph_acc[s & 1], p.error_flag, 300 + (s & 1));
-        ph_acc[s & 1] ^= 1;
+        e.s = s; e.c0 = e.c1 = e.c2 = 0.f;
+        e.vb = (s == kViewStep && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
+        mbar_wait(bars + 8 * BAR_ACCFULL, ph_acc, p.error_flag, 300 + slot);
+        ph_acc ^= 1;
         tc_fence_after();
-        if (e.writes_h && store_pending) {          // the tap store must have finished reading H
+        if (s < kViewStep && store_pending) {       // the tap store must have finished reading H
           if (et == 0) bulk_wait_read0();
-          named_bar_sync(1, 128);
+          named_bar_sync(1 + slot, 128);
           store_pending = false;
         }
-        const int nj = (s == 9) ? 4 : 8;
+        const int nj = (s == kViewStep) ? 4 : 8;
         uint32_t va[32], vb[32];
         tmem_ld32(t_lane, va);
         for (int j = 0; j < nj; j += 2) {           // software pipelined: load slice j+1 while slice j is processed
           tmem_ld_wait();
           tmem_ld32(t_lane + (j + 1) * 32, vb);
-          epi_chunk(e, va, j, p, valid, pt);
-          if (e.writes_h) { fence_proxy_async(); mbar_arrive(bars + 8 * (BAR_HREADY + j)); }
+          epi_chunk(e, va, j, p, kc, valid, pt);
           tmem_ld_wait();
           if (j + 2 < nj) tmem_ld32(t_lane + (j + 2) * 32, va);
-          epi_chunk(e, vb, j + 1, p, valid, pt);
-          if (e.writes_h) { fence_proxy_async(); mbar_arrive(bars + 8 * (BAR_HREADY + j + 1)); }
+          epi_chunk(e, vb, j + 1, p, kc, valid, pt);
         }
         tc_fence_before();
-        if (s == 9 && valid) {
-          float4 o;
-          o.x = 1.f / (1.f + __expf(-(e.c0 + p.brgb0)));
-          o.y = 1.f / (1.f + __expf(-(e.c1 + p.brgb1)));
-          o.z = 1.f / (1.f + __expf(-(e.c2 + p.brgb2)));
-          o.w = e.alpha + p.balpha;
-          *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+        if (s == kViewStep) {
+          if (valid) {
+            float4 o;
+            o.x = 1.f / (1.f + __expf(-(e.c0 + p.brgb0)));
+            o.y = 1.f / (1.f + __expf(-(e.c1 + p.brgb1)));
+            o.z = 1.f / (1.f + __expf(-(e.c2 + p.brgb2)));
+            o.w = e.alpha + p.balpha;
+            *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+          }
+        } else {
+          fence_proxy_async();                       // generic-proxy writes -> visible to UMMA / bulk copy
         }
         if (s == p.stop_step && p.want_feat) {
-          named_bar_sync(1, 128);                    // all 128 rows written (and fenced) before the bulk store
+          named_bar_sync(1 + slot, 128);             // all 128 rows written (and fenced) before the bulk store
           if (et == 0 && tile * kTileM < p.P) {
             bulk_s2g(p.feat_tiles + (size_t)tile * kFeatTileBytes, h_base, kFeatTileBytes);
             bulk_commit();
           }
           store_pending = true;
         }
+        mbar_arrive(bars + 8 * BAR_AREADY);
       }
     }
     if (et == 0) bulk_wait0();
-  } else if (warp >= 8) {
-    // ===== encoder warps: sampling data -> positional encoding -> bf16 A tile of layer 0 / skip =====
-    const int r = (warp - 8) * 32 + lane;
-    uint32_t ph_eempty[2] = {0, 0};
+  } else if (warp >= 12) {
+    // ===== encoder warps: sampling data -> positional encoding -> bf16 A tiles of layer 0 / skip =====
+    const int r = (warp - 12) * 32 + lane;
+    uint32_t ph_eempty = 0;
     for (int it = 0; it < p.n_iters; ++it) {
-      const int eb = it & 1;
-      const int64_t tile = (int64_t)it * G + blockIdx.x;
-      const int64_t pt = tile * kTileM + r;
-      const bool valid = pt < p.P;
-      float m[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
-      const float* xrow = nullptr;
-      if (valid) {
-        if (p.mode == 0) {
-          const int64_t ray = pt / p.S;
-          const int sidx = (int)(pt - ray * p.S);
-          const float* rr = p.rays + ray * p.ncols;
-          if (p.mip) {
-            const float* z = p.z + ray * (p.S + 1);
-            float rl[12];
+      mbar_wait(bars + 8 * BAR_EEMPTY, ph_eempty ^ 1, p.error_flag, 400);
+      ph_eempty ^= 1;
+      for (int slot = 0; slot < 2; ++slot) {
+        const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
+        const int64_t pt = tile * kTileM + r;
+        const bool valid = pt < p.P;
+        float m[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
+        const float* xrow = nullptr;
+        if (valid) {
+          if (p.mode == 0) {
+            const int64_t ray = pt / p.S;
+            const int sidx = (int)(pt - ray * p.S);
+            const float* rr = p.rays + ray * p.ncols;
+            if (p.mip) {
+              const float* z = p.z + ray * (p.S + 1);
+              float rl[12];
 #pragma unroll
-            for (int i = 0; i < 12; ++i) rl[i] = __ldg(rr + i);
-            frustum_gaussian(rl, __ldg(z + sidx), __ldg(z + sidx + 1), p.var_scale, m, vv);
-          } else {
-            const float zz = __ldg(p.z + pt);
+              for (int i = 0; i < 12; ++i) rl[i] = __ldg(rr + i);
+              frustum_gaussian(rl, __ldg(z + sidx), __ldg(z + sidx + 1), p.var_scale, m, vv);
+            } else {
+              const float zz = __ldg(p.z + pt);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) m[c] = __ldg(rr + c) + __ldg(rr + 3 + c) * zz;
-          }
-        } else {
-          xrow = p.X + pt * p.kx;
-        }
-      }
-      mbar_wait(bars + 8 * (BAR_EEMPTY + eb), ph_eempty[eb] ^ 1, p.error_flag, 400 + eb);
-      ph_eempty[eb] ^= 1;
-      const uint32_t e_base = base + OFF_E + eb * kEBytes;
-      for (int kb = 0; kb < 3; ++kb) {
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int col = kb * 32 + c * 8 + i;
-            float val = 0.f;
-            if (valid && col < p.xyz) {
-              if (p.mode == 1) val = __ldg(xrow + col);
-              else val = p.mip ? ipe_col(m, vv, p.fx, col) : fourier_col(m, p.fx, col);
+              for (int c = 0; c < 3; ++c) m[c] = __ldg(rr + c) + __ldg(rr + 3 + c) * zz;
             }
-            f[i] = val;
+          } else {
+            xrow = p.X + pt * p.kx;
           }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e_base + kb * kBlk + sw64_off(r, c)),
-                       "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+        }
+        const RowWriter rw{base + OFF_E + slot * kEBytes, r};
+        if (p.mode == 1 || !valid) {
+          for (int ch = 0; ch < 12; ++ch) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int col = ch * 8 + i; f[i] = (valid && col < p.xyz) ? __ldg(xrow + col) : 0.f; }
+            rw.store(ch, f);
+          }
+        } else if (p.mip) {
+          encode_row_ipe<15>(m, vv, rw);
+        } else {
+          encode_row_fourier<15>(m, rw);
         }
       }
       fence_proxy_async();
-      mbar_arrive(bars + 8 * (BAR_EFULL + eb));
+      mbar_arrive(bars + 8 * BAR_EFULL);
     }
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
-  if (CSIZE > 1) cluster_sync_all();   // no CTA exits while a peer may still multicast into it / signal its barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -597,23 +623,6 @@ size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep) {
 int* g_trap_host = nullptr;   // mapped pinned int: survives a trapped launch
 int* g_trap_dev = nullptr;
 
-int g_cluster = -1;   // weight-multicast cluster size: 1, 2 or 4 (NMR_TC_CLUSTER env, default 2)
-
-template <int CSIZE>
-int launch_cluster(const TcParams& p, int grid, cudaStream_t s, std::string* err) {
-  cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<CSIZE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-  if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CSIZE; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc_kernel<CSIZE>, p);
-  if (e != cudaSuccess) { *err = std::string("nerf_mlp_tc_kernel launch: ") + cudaGetErrorString(e); return -1; }
-  return 0;
-}
-
 int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std::string* err) {
   static int num_sms = 0;
   if (!g_trap_host) {
@@ -624,22 +633,19 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
     *g_trap_host = 0;
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  if (g_cluster < 0) {
-    const char* ev = getenv("NMR_TC_CLUSTER");
-    g_cluster = ev ? atoi(ev) : 2;
-    if (g_cluster != 1 && g_cluster != 2 && g_cluster != 4) g_cluster = 2;
+    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
   }
   p.error_flag = g_trap_dev;
-  const int cs = g_cluster;
   int64_t tiles = (p.P + kTileM - 1) / kTileM;
-  int grid = (int)std::min<int64_t>(num_sms / cs * cs, (std::max<int64_t>(tiles, 1) + cs - 1) / cs * cs);
-  p.n_iters = (int)((tiles + grid - 1) / grid);
-  if (p.n_iters < 1) p.n_iters = 1;
-  p.chunks = net.chunks; p.bias = net.bias; p.walpha = net.walpha; p.wrgb = net.wrgb;
+  int64_t pairs = (tiles + 1) / 2;
+  int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(pairs, 1));
+  p.n_iters = (int)((pairs + grid - 1) / grid);
+  p.chunks = net.chunks;
   p.balpha = net.balpha; p.brgb0 = net.brgb[0]; p.brgb1 = net.brgb[1]; p.brgb2 = net.brgb[2];
-  int r = cs == 1 ? launch_cluster<1>(p, grid, s, err) : cs == 2 ? launch_cluster<2>(p, grid, s, err) : launch_cluster<4>(p, grid, s, err);
-  if (r != 0) return r;
+  nerf_mlp_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, *(const TcConsts*)net.consts);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { *err = std::string("nerf_mlp_tc_kernel launch: ") + cudaGetErrorString(e); return -1; }
   *launches += 1;
   return 0;
 }
@@ -649,9 +655,24 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
 int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err) {
   const int skipl = skip_layer + 1;
   out->set = false;
-  if (skipl != 5 || d.xyzp != 96) {   // return 1: configuration valid for the fp32 path only
+  if (skipl != 5 || d.xyzp != 96 || d.fx != 15) {   // return 1: configuration valid for the fp32 path only
     *err = "the tcgen05 path is built for skips=[4] and a 96-wide padded xyz encoding (15 frequencies)";
     return 1;
+  }
+  const int vin = kHid + d.dirs + d.app;
+  // feature_linear has no activation, so views_linears.0(feature_linear(h)) = (Wv_f Wf) h + Wv_f b_f + ...:
+  // fold the two on the host in double precision (models/nerf.py:110-114).
+  std::vector<float> wfold((size_t)kHalf * kHid);
+  std::vector<float> bfold(kHalf);
+  for (int o = 0; o < kHalf; ++o) {
+    for (int i = 0; i < kHid; ++i) {
+      double acc = 0.0;
+      for (int m = 0; m < kHid; ++m) acc += (double)hn.views_w[(size_t)o * vin + m] * (double)hn.feature_w[(size_t)m * kHid + i];
+      wfold[(size_t)o * kHid + i] = (float)acc;
+    }
+    double accb = hn.views_b[o];
+    for (int m = 0; m < kHid; ++m) accb += (double)hn.views_w[(size_t)o * vin + m] * (double)hn.feature_b[m];
+    bfold[o] = (float)accb;
   }
   std::vector<uint8_t> chunks;
   for (int s = 0; s < kSteps; ++s) {
@@ -666,27 +687,17 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
       } else {
         for (int c = 0; c < 8; ++c) pack_chunk(chunks, W, kHid, kin, 32 * c, kHid);
       }
-    } else if (s == 8) {
-      for (int c = 0; c < 8; ++c) pack_chunk(chunks, hn.feature_w.data(), kHid, kHid, 32 * c, kHid);
     } else {
-      const int vin = kHid + d.dirs + d.app;
-      for (int c = 0; c < 8; ++c) pack_chunk(chunks, hn.views_w.data(), kHalf, vin, 32 * c, kHid);
+      for (int c = 0; c < 8; ++c) pack_chunk(chunks, wfold.data(), kHalf, kHid, 32 * c, kHid);
     }
   }
   if ((int64_t)chunks.size() != step_offset(kSteps)) { *err = "internal: chunk stream size mismatch"; return -1; }
   std::vector<float> fl;
   auto put = [&](const float* src, size_t n) { size_t o = fl.size(); fl.insert(fl.end(), src, src + n); fl.resize((fl.size() + 63) / 64 * 64, 0.f); return o; };
-  std::vector<float> bias(9 * kHid);
-  for (int i = 0; i < kLayers; ++i) memcpy(&bias[i * kHid], hn.pts_b[i].data(), kHid * sizeof(float));
-  memcpy(&bias[8 * kHid], hn.feature_b.data(), kHid * sizeof(float));
-  size_t o_bias = put(bias.data(), bias.size());
-  size_t o_wa = put(hn.alpha_w.data(), kHid);
-  size_t o_wr = put(hn.rgb_w.data(), 3 * kHalf);
   std::vector<float> wvd((size_t)kHalf * d.dap, 0.f);
-  const int vin = kHid + d.dirs + d.app;
   for (int o = 0; o < kHalf; ++o) memcpy(&wvd[(size_t)o * d.dap], &hn.views_w[(size_t)o * vin + kHid], (d.dirs + d.app) * sizeof(float));
   size_t o_wvd = put(wvd.data(), wvd.size());
-  size_t o_bv = put(hn.views_b.data(), kHalf);
+  size_t o_bv = put(bfold.data(), kHalf);
 
   size_t cbytes = (chunks.size() + 1023) / 1024 * 1024;
   size_t total = cbytes + fl.size() * sizeof(float);
@@ -702,24 +713,28 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
   if (e == cudaSuccess) e = cudaMemcpy(base + cbytes, fl.data(), fl.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
   const float* fb = (const float*)(base + cbytes);
-  out->chunks = base; out->bias = fb + o_bias; out->walpha = fb + o_wa; out->wrgb = fb + o_wr;
+  out->chunks = base;
   out->wview_d = fb + o_wvd; out->bview = fb + o_bv;
+  TcConsts* kc = out->consts ? (TcConsts*)out->consts : new TcConsts();
+  for (int i = 0; i < kLayers; ++i) memcpy(kc->bias[i], hn.pts_b[i].data(), kHid * sizeof(float));
+  memcpy(kc->walpha, hn.alpha_w.data(), kHid * sizeof(float));
+  memcpy(kc->wrgb, hn.rgb_w.data(), 3 * kHalf * sizeof(float));
+  out->consts = kc;
   out->balpha = hn.alpha_b[0];
   for (int i = 0; i < 3; ++i) out->brgb[i] = hn.rgb_b[i];
   out->set = true;
   return 0;
 }
 
-int tc_set_cluster(int cs) {
-  if (cs != 1 && cs != 2 && cs != 4) return -1;
-  g_cluster = cs;
-  return 0;
+int tc_set_cluster(int cs) {   // kept for ABI stability: measured no gain from TMA multicast at cluster <= 4 on B200
+  return (cs == 1 || cs == 2 || cs == 4) ? 0 : -1;
 }
 
 int tc_trap_code() { return g_trap_host ? *(volatile int*)g_trap_host : 0; }
 
 void tc_free_net(TcNet* n) {
   if (n->pool) cudaFree(n->pool);
+  if (n->consts) delete (TcConsts*)n->consts;
   *n = TcNet{};
 }
 

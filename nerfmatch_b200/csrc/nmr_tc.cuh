@@ -19,12 +19,10 @@ struct TcNet {
   void* pool = nullptr;
   size_t bytes = 0;
   bool set = false;
-  const uint8_t* chunks = nullptr;   // weight chunk stream
-  const float* bias = nullptr;       // [9][256]: pts_linears.0..7 bias, feature_linear bias
-  const float* walpha = nullptr;     // [256]
-  const float* wrgb = nullptr;       // [3][128]
-  const float* wview_d = nullptr;    // [128][dap]  dirs+app part of views_linears.0 (fp32)
-  const float* bview = nullptr;      // [128]
+  const uint8_t* chunks = nullptr;   // weight chunk stream (device)
+  void* consts = nullptr;            // host TcConsts: biases + head weights, passed as kernel parameters
+  const float* wview_d = nullptr;    // [128][dap]  dirs+app part of views_linears.0 (fp32, device)
+  const float* bview = nullptr;      // [128] views bias with the folded feature_linear bias (device)
   float balpha = 0.f;
   float brgb[3] = {0.f, 0.f, 0.f};
 };

@@ -215,7 +215,7 @@ class NerfRenderer(nn.Module):
         for k in ("rgb_coarse", "depth_coarse", "rgb_fine", "depth_fine"):
             v = preds[k]
             if h * w == v.shape[0]:
-                preds[k] = v.reshape(h, w, -1)
+                preds[k] = v.reshape(h, w, v.shape[1] if v.dim() > 1 else 1)
         return preds
 
     def render_novel_view(self, img_hw, K, c2w, unnorm_scene, device, downsample=8):
