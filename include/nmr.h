@@ -197,6 +197,9 @@ NMR_API int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z,
 NMR_API int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int64_t P, int32_t step, float* out,
                                 void* stream);
 NMR_API int nmr_debug_trap_code(void);
+/* With NMR_TC_TIMELINE=1 in the environment the tcgen05 kernel's CTA 0 records clock64 stamps for its first
+ * 8 iterations: [iteration][step][4] = {MMA issue start, MMA issue end, epilogue start, epilogue end}. */
+NMR_API int nmr_debug_timeline(long long* host, int n);
 /* Tuning knob of the tcgen05 path (process-wide): size of the thread-block cluster that shares each weight
  * chunk through TMA multicast - 1 (off), 2 or 4.  Default 2, or the NMR_TC_CLUSTER environment variable. */
 NMR_API int nmr_set_tc_cluster(int cluster_size);

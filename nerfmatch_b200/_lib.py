@@ -82,6 +82,7 @@ SYMBOLS = {
     "nmr_stage_mlp_probe": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp]),
     "nmr_debug_trap_code": (C.c_int, []),
     "nmr_set_tc_cluster": (C.c_int, [C.c_int]),
+    "nmr_debug_timeline": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "nmr_launch_count": (_i64, [_vp]),
     "nmr_set_timing": (C.c_int, [_vp, C.c_int]),
     "nmr_last_stage_ms": (C.c_int, [_vp, _fp, _fp, _fp]),

@@ -761,6 +761,7 @@ extern "C" int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int
 }
 
 extern "C" int nmr_debug_trap_code(void) { return tc_trap_code(); }
+extern "C" int nmr_debug_timeline(long long* host, int n) { return tc_read_timeline(host, n); }
 extern "C" int nmr_set_tc_cluster(int cluster_size) { return tc_set_cluster(cluster_size) == 0 ? NMR_OK : NMR_ERR_INVALID; }
 
 extern "C" int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z, const float* rays_d, int64_t n,

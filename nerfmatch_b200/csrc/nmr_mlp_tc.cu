@@ -19,7 +19,7 @@
 //     128-point tiles ("slots") a CTA keeps in flight: 2 x 256 TMEM columns, M = 256 per weight fetch;
 //   * the tapped feature tile (stop_layer) leaves as one 64 KB bulk store shared->global in the same
 //     tiled layout the compositor reads;
-//   * biases and head weights travel as kernel parameters (constant bank, 11 KB), so nothing but the
+//   * biases and head weights are read through L1 (LDG.128, warp-uniform); nothing but the
 //     weight stream competes for shared memory.
 //
 // Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 idle,
@@ -37,8 +37,8 @@ constexpr int kTileM = 128;
 constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64B swizzle
 constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
 constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
-constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
-constexpr int kStages = 3;
+constexpr int kStageBytes = 8192;          // one [128 N x 32 K] weight block (half of a layer's N)
+constexpr int kStages = 5;
 constexpr int kSteps = 9;                  // 8 trunk layers + (feature_linear folded into) views_linears.0
 constexpr int kViewStep = 8;
 constexpr int kThreads = 512;
@@ -47,20 +47,20 @@ constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128
 constexpr int OFF_H = 0;
 constexpr int OFF_E = 2 * kHBytes;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
-constexpr int OFF_BAR = OFF_W + kStages * kStageBytes;
-constexpr int kSmemBytes = OFF_BAR + 256 + 1024;   // + alignment slack
+constexpr int OFF_TAB = OFF_W + kStages * kStageBytes;        // fp32 tables: bias [8][256], walpha [256], wrgb [3][128]
+constexpr int kTabFloats = kLayers * kHid + kHid + 3 * kHalf;
+constexpr int OFF_BAR = OFF_TAB + kTabFloats * 4;
+constexpr int kSmemBytes = OFF_BAR + 128;                    // dynamic smem is 1024-aligned (checked at kernel entry)
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
 enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_AREADY, BAR_EFULL, BAR_EEMPTY, BAR_COUNT };
 
-struct TcConsts {          // kernel-parameter (constant bank) copy of the fp32 epilogue vectors
-  float bias[8][kHid];     // pts_linears.0..7 bias
-  float walpha[kHid];
-  float wrgb[3][kHalf];
-};
-
 struct TcParams {
   const uint8_t* chunks;
+  const float* bias;       // [8][256] pts_linears.0..7 bias   (read through L1 with LDG.128: indexed constant-bank
+  const float* walpha;     // [256]                              loads (LDC) cost ~45 serialized cycles each - measured)
+  const float* wrgb;       // [3][128]
   float balpha; float brgb0, brgb1, brgb2;
   const float* vbias; int vb_div;          // view bias row = point / vb_div
   // input mode 0: rays + z (fused sampling-to-encoding); mode 1: padded fp32 rows X[P,kx]
@@ -71,14 +71,16 @@ struct TcParams {
   float* raw; uint8_t* feat_tiles;
   int debug_step; float* debug_out;
   int* error_flag;
+  long long* timeline;   // optional clock64 trace of CTA 0 (NMR_TC_TIMELINE=1): [it][step][4]
 };
 
 __host__ __device__ constexpr int step_chunks_e(int s) { return (s == 0 || s == 5) ? 3 : 0; }
 __host__ __device__ constexpr int step_chunks_h(int s) { return s == 0 ? 0 : 8; }
-__host__ __device__ constexpr int step_chunk_bytes(int s) { return s == kViewStep ? 8192 : 16384; }
-__host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the chunk stream
+__host__ __device__ constexpr int step_nhalves(int s) { return s == kViewStep ? 1 : 2; }   // N = 128 per weight block
+__host__ __device__ constexpr int step_blocks(int s) { return (step_chunks_e(s) + step_chunks_h(s)) * step_nhalves(s); }
+__host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the weight stream
   int64_t off = 0;
-  for (int i = 0; i < s; ++i) off += (int64_t)(step_chunks_e(i) + step_chunks_h(i)) * step_chunk_bytes(i);
+  for (int i = 0; i < s; ++i) off += (int64_t)step_blocks(i) * kStageBytes;
   return off;
 }
 
@@ -136,14 +138,12 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart.
-__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address
-  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(512 >> 4) << 32;               // stride byte offset between 8-row groups
-  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
-  d |= (uint64_t)4 << 61;                        // layout type: SWIZZLE_64B
+// UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart (SBO), version 1.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo) {
+  constexpr uint32_t hi = (512u >> 4) | (1u << 14) | (4u << 29);   // SBO | version | SWIZZLE_64B  (bits 32..63)
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 // instruction descriptor: kind::f16, A = B = bf16 (K-major), D = fp32, M = 128
@@ -257,56 +257,34 @@ __device__ __forceinline__ void encode_row_ipe(const float m[3], const float var
   }
 }
 
-// One 32-column slice of the epilogue: bias + activation, fp32 heads, bf16 hand-over to the next layer.
+// One 32-column slice of a trunk-layer epilogue: bias + ReLU, fp32 sigma head, bf16 hand-over to the next layer.
 struct EpiCtx {
-  const float* vb;                                                 // per-ray view bias row (global) or null
+  const float* tab;                                                // shared-memory tables (bias | walpha | wrgb)
   uint32_t h_base; int r; int s;
-  float alpha, c0, c1, c2;
+  float alpha;
 };
-__device__ __forceinline__ void epi_chunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, const TcConsts& k, bool valid, int64_t pt) {
+__device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, bool valid, int64_t pt) {
   float x[32];
-  if (e.s < kViewStep) {
-    const float4* bp = reinterpret_cast<const float4*>(&k.bias[e.s][j * 32]);   // constant bank, warp-uniform
+  const float4* bp = reinterpret_cast<const float4*>(e.tab + e.s * kHid + j * 32);   // warp-uniform LDS broadcast
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = bp[i];
-      x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
-      x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = e.vb ? __ldg(reinterpret_cast<const float4*>(e.vb + j * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
-      x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
-    }
+  for (int i = 0; i < 8; ++i) {
+    float4 t = bp[i];
+    x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
+    x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
   }
   if (e.s == 7) {                                  // alpha_linear on the un-rounded fp32 activations
-    const float4* wp = reinterpret_cast<const float4*>(&k.walpha[j * 32]);
+    const float4* wp = reinterpret_cast<const float4*>(e.tab + kLayers * kHid + j * 32);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 w = wp[i];
       e.alpha = fmaf(x[4 * i], w.x, fmaf(x[4 * i + 1], w.y, fmaf(x[4 * i + 2], w.z, fmaf(x[4 * i + 3], w.w, e.alpha))));
     }
   }
-  if (e.s == kViewStep) {                          // rgb_linear
-    const float4* w0 = reinterpret_cast<const float4*>(&k.wrgb[0][j * 32]);
-    const float4* w1 = reinterpret_cast<const float4*>(&k.wrgb[1][j * 32]);
-    const float4* w2 = reinterpret_cast<const float4*>(&k.wrgb[2][j * 32]);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 a = w0[i], b = w1[i], c = w2[i];
-      e.c0 = fmaf(x[4 * i], a.x, fmaf(x[4 * i + 1], a.y, fmaf(x[4 * i + 2], a.z, fmaf(x[4 * i + 3], a.w, e.c0))));
-      e.c1 = fmaf(x[4 * i], b.x, fmaf(x[4 * i + 1], b.y, fmaf(x[4 * i + 2], b.z, fmaf(x[4 * i + 3], b.w, e.c1))));
-      e.c2 = fmaf(x[4 * i], c.x, fmaf(x[4 * i + 1], c.y, fmaf(x[4 * i + 2], c.z, fmaf(x[4 * i + 3], c.w, e.c2))));
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t w0 = pack_bf16(x[8 * c], x[8 * c + 1]), w1 = pack_bf16(x[8 * c + 2], x[8 * c + 3]);
-      uint32_t w2 = pack_bf16(x[8 * c + 4], x[8 * c + 5]), w3 = pack_bf16(x[8 * c + 6], x[8 * c + 7]);
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.h_base + j * kBlk + sw64_off(e.r, c)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
-    }
+  for (int c = 0; c < 4; ++c) {
+    uint32_t w0 = pack_bf16(x[8 * c], x[8 * c + 1]), w1 = pack_bf16(x[8 * c + 2], x[8 * c + 3]);
+    uint32_t w2 = pack_bf16(x[8 * c + 4], x[8 * c + 5]), w3 = pack_bf16(x[8 * c + 6], x[8 * c + 7]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.h_base + j * kBlk + sw64_off(e.r, c)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
   }
   if (p.debug_out && e.s == p.debug_step && valid) {
 #pragma unroll
@@ -314,15 +292,71 @@ __device__ __forceinline__ void epi_chunk(EpiCtx& e, const uint32_t* v, int j, c
   }
 }
 
+// views_linears.0 epilogue (4 slices of 32): per-ray view bias + ReLU, rgb_linear + sigmoid, raw [P,4] store.
+__device__ __forceinline__ void epi_view(const float* tab, const float* vbrow, uint32_t t_lane, const TcParams& p, bool valid,
+                                         int64_t pt, float alpha) {
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  float4 vq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) vq[i] = vbrow ? __ldg(reinterpret_cast<const float4*>(vbrow) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    uint32_t v[32];
+    tmem_ld32(t_lane + j * 32, v);
+    tmem_ld_wait();
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 t = vq[i];
+      x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
+      x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
+    }
+    if (j < 3) {                                   // next slice of the view bias: L2 latency hides behind the rgb FMAs
+#pragma unroll
+      for (int i = 0; i < 8; ++i) vq[i] = vbrow ? __ldg(reinterpret_cast<const float4*>(vbrow + (j + 1) * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4* w0 = reinterpret_cast<const float4*>(tab + (kLayers + 1) * kHid + j * 32);
+    const float4* w1 = w0 + kHalf / 4;
+    const float4* w2 = w1 + kHalf / 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float4 a = w0[i], b = w1[i], c = w2[i];
+      c0 = fmaf(x[4 * i], a.x, fmaf(x[4 * i + 1], a.y, fmaf(x[4 * i + 2], a.z, fmaf(x[4 * i + 3], a.w, c0))));
+      c1 = fmaf(x[4 * i], b.x, fmaf(x[4 * i + 1], b.y, fmaf(x[4 * i + 2], b.z, fmaf(x[4 * i + 3], b.w, c1))));
+      c2 = fmaf(x[4 * i], c.x, fmaf(x[4 * i + 1], c.y, fmaf(x[4 * i + 2], c.z, fmaf(x[4 * i + 3], c.w, c2))));
+    }
+    if (p.debug_out && p.debug_step == kViewStep && valid) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = x[i];
+    }
+  }
+  if (valid) {
+    float4 o;
+    o.x = 1.f / (1.f + __expf(-(c0 + p.brgb0)));
+    o.y = 1.f / (1.f + __expf(-(c1 + p.brgb1)));
+    o.z = 1.f / (1.f + __expf(-(c2 + p.brgb2)));
+    o.w = alpha + p.balpha;
+    *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+  }
+}
+
 // ---- the kernel ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ TcConsts kc) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+__global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* gbase = smem_raw;
   const uint32_t bars = base + OFF_BAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + BAR_COUNT * 8);
+  float* tab = reinterpret_cast<float*>(gbase + OFF_TAB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
+  if (base & 1023u) {                              // the swizzled UMMA tiles need a 1024-byte aligned window
+    if (threadIdx.x == 0) { atomicExch(p.error_flag, 900); __threadfence_system(); }
+    __trap();
+  }
+  for (int i = threadIdx.x; i < kLayers * kHid; i += kThreads) tab[i] = p.bias[i];
+  for (int i = threadIdx.x; i < kHid; i += kThreads) tab[kLayers * kHid + i] = p.walpha[i];
+  for (int i = threadIdx.x; i < 3 * kHalf; i += kThreads) tab[(kLayers + 1) * kHid + i] = p.wrgb[i];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); }
@@ -348,13 +382,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       for (int it = 0; it < p.n_iters; ++it) {
         const uint8_t* src = p.chunks;
         for (int s = 0; s < kSteps; ++s) {
-          const int nch = step_chunks_e(s) + step_chunks_h(s);
-          const uint32_t bytes = step_chunk_bytes(s);
-          for (int c = 0; c < nch; ++c) {
+          const int nblk = step_blocks(s);
+          for (int c = 0; c < nblk; ++c) {
             mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
-            mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
-            bulk_g2s(base + OFF_W + stage * kStageBytes, src, bytes, bars + 8 * (BAR_WFULL + stage));
-            src += bytes;
+            mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), kStageBytes);
+            bulk_g2s(base + OFF_W + stage * kStageBytes, src, kStageBytes, bars + 8 * (BAR_WFULL + stage));
+            src += kStageBytes;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -367,29 +400,35 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       for (int it = 0; it < p.n_iters; ++it) {
         for (int s = 0; s < kSteps; ++s) {
           const int ne = step_chunks_e(s), nh = step_chunks_h(s);
-          const uint32_t idesc = umma_idesc((s == kViewStep) ? 128 : 256);
+          const uint32_t idesc = umma_idesc(128);
+          const int nhv = step_nhalves(s);
           // both slots' previous epilogues are done: TMEM drained, H written (count 256)
           mbar_wait(bars + 8 * BAR_AREADY, ph_aready, p.error_flag, 200);
           ph_aready ^= 1;
           if (s == 0) { mbar_wait(bars + 8 * BAR_EFULL, ph_efull, p.error_flag, 210); ph_efull ^= 1; }
           tc_fence_after();
+          if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 0] = clock64();
           uint32_t accumulate = 0;
           for (int c = 0; c < ne + nh; ++c) {
-            mbar_wait(bars + 8 * (BAR_WFULL + stage), wphase, p.error_flag, 220 + stage);
-            tc_fence_after();
-            const uint32_t b_addr = base + OFF_W + stage * kStageBytes;
-#pragma unroll
-            for (int slot = 0; slot < 2; ++slot) {
-              const uint32_t a_addr = (c < ne) ? (base + OFF_E + slot * kEBytes + c * kBlk)
-                                               : (base + OFF_H + slot * kHBytes + (c - ne) * kBlk);
-#pragma unroll
-              for (int k = 0; k < 2; ++k)
-                umma_bf16(tmem_base + slot * 256, umma_desc_sw64(a_addr + k * 32), umma_desc_sw64(b_addr + k * 32), idesc, accumulate | k);
+            // descriptor low words (start address >> 4 | LBO); +2 advances K by 16 elements (32 bytes)
+            const uint32_t a0 = desc_lo((c < ne) ? (base + OFF_E + c * kBlk) : (base + OFF_H + (c - ne) * kBlk));
+            const uint32_t a1 = a0 + (((c < ne) ? kEBytes : kHBytes) >> 4);          // slot 1 tile
+            for (int half = 0; half < nhv; ++half) {           // weight blocks arrive K-chunk major, N-half minor
+              const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
+              if (!mbar_try_wait(wbar, wphase)) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
+              tc_fence_after();
+              const uint32_t b0 = desc_lo(base + OFF_W + stage * kStageBytes);
+              const uint32_t d0 = tmem_base + half * 128;
+              umma_bf16(d0, mk_desc(a0), mk_desc(b0), idesc, accumulate);
+              umma_bf16(d0, mk_desc(a0 + 2), mk_desc(b0 + 2), idesc, 1u);
+              umma_bf16(d0 + 256, mk_desc(a1), mk_desc(b0), idesc, accumulate);
+              umma_bf16(d0 + 256, mk_desc(a1 + 2), mk_desc(b0 + 2), idesc, 1u);
+              umma_commit(bars + 8 * (BAR_WEMPTY + stage));    // stage free once these MMAs retire
+              if (++stage == kStages) { stage = 0; wphase ^= 1; }
             }
             accumulate = 1;
-            umma_commit(bars + 8 * (BAR_WEMPTY + stage));      // stage free once these MMAs retire
-            if (++stage == kStages) { stage = 0; wphase ^= 1; }
           }
+          if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 1] = clock64();
           umma_commit(bars + 8 * BAR_ACCFULL);                 // both accumulators complete -> epilogues
           if (s == 5) umma_commit(bars + 8 * BAR_EEMPTY);      // encoded tiles no longer needed
         }
@@ -407,46 +446,41 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     uint32_t ph_acc = 0;
     bool store_pending = false;
     EpiCtx e;
-    e.h_base = h_base; e.r = r;
+    e.h_base = h_base; e.r = r; e.tab = tab;
     for (int it = 0; it < p.n_iters; ++it) {
       const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
       e.alpha = 0.f;
       for (int s = 0; s < kSteps; ++s) {
-        e.s = s; e.c0 = e.c1 = e.c2 = 0.f;
-        e.vb = (s == kViewStep && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
+        e.s = s;
+        const float* vbrow = (s == kViewStep && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
         mbar_wait(bars + 8 * BAR_ACCFULL, ph_acc, p.error_flag, 300 + slot);
         ph_acc ^= 1;
         tc_fence_after();
-        if (s < kViewStep && store_pending) {       // the tap store must have finished reading H
-          if (et == 0) bulk_wait_read0();
-          named_bar_sync(1 + slot, 128);
-          store_pending = false;
-        }
-        const int nj = (s == kViewStep) ? 4 : 8;
-        uint32_t va[32], vb[32];
-        tmem_ld32(t_lane, va);
-        for (int j = 0; j < nj; j += 2) {           // software pipelined: load slice j+1 while slice j is processed
-          tmem_ld_wait();
-          tmem_ld32(t_lane + (j + 1) * 32, vb);
-          epi_chunk(e, va, j, p, kc, valid, pt);
-          tmem_ld_wait();
-          if (j + 2 < nj) tmem_ld32(t_lane + (j + 2) * 32, va);
-          epi_chunk(e, vb, j + 1, p, kc, valid, pt);
-        }
-        tc_fence_before();
-        if (s == kViewStep) {
-          if (valid) {
-            float4 o;
-            o.x = 1.f / (1.f + __expf(-(e.c0 + p.brgb0)));
-            o.y = 1.f / (1.f + __expf(-(e.c1 + p.brgb1)));
-            o.z = 1.f / (1.f + __expf(-(e.c2 + p.brgb2)));
-            o.w = e.alpha + p.balpha;
-            *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+        if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0 && slot == 0) p.timeline[(it * kSteps + s) * 4 + 2] = clock64();
+        if (s < kViewStep) {
+          if (store_pending) {                      // the tap store must have finished reading H
+            if (et == 0) bulk_wait_read0();
+            named_bar_sync(1 + slot, 128);
+            store_pending = false;
           }
-        } else {
+          uint32_t va[32], vb[32];
+          tmem_ld32(t_lane, va);
+#pragma unroll 1
+          for (int j = 0; j < 8; j += 2) {          // software pipelined: load slice j+1 while slice j is processed
+            tmem_ld_wait();
+            tmem_ld32(t_lane + (j + 1) * 32, vb);
+            epi_trunk(e, va, j, p, valid, pt);
+            tmem_ld_wait();
+            if (j + 2 < 8) tmem_ld32(t_lane + (j + 2) * 32, va);
+            epi_trunk(e, vb, j + 1, p, valid, pt);
+          }
+          tc_fence_before();
           fence_proxy_async();                       // generic-proxy writes -> visible to UMMA / bulk copy
+        } else {
+          epi_view(tab, vbrow, t_lane, p, valid, pt, e.alpha);
+          tc_fence_before();
         }
         if (s == p.stop_step && p.want_feat) {
           named_bar_sync(1 + slot, 128);             // all 128 rows written (and fenced) before the bulk store
@@ -456,6 +490,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           }
           store_pending = true;
         }
+        if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0 && slot == 0) p.timeline[(it * kSteps + s) * 4 + 3] = clock64();
         mbar_arrive(bars + 8 * BAR_AREADY);
       }
     }
@@ -622,6 +657,7 @@ size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep) {
 
 int* g_trap_host = nullptr;   // mapped pinned int: survives a trapped launch
 int* g_trap_dev = nullptr;
+long long* g_timeline = nullptr;
 
 int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std::string* err) {
   static int num_sms = 0;
@@ -637,13 +673,15 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
   }
   p.error_flag = g_trap_dev;
+  if (!g_timeline && getenv("NMR_TC_TIMELINE")) { cudaMalloc((void**)&g_timeline, (8 * kSteps * 4 + 32) * sizeof(long long)); cudaMemset(g_timeline, 0, (8 * kSteps * 4 + 32) * sizeof(long long)); }
+  p.timeline = g_timeline;
   int64_t tiles = (p.P + kTileM - 1) / kTileM;
   int64_t pairs = (tiles + 1) / 2;
   int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(pairs, 1));
   p.n_iters = (int)((pairs + grid - 1) / grid);
-  p.chunks = net.chunks;
+  p.chunks = net.chunks; p.bias = net.bias; p.walpha = net.walpha; p.wrgb = net.wrgb;
   p.balpha = net.balpha; p.brgb0 = net.brgb[0]; p.brgb1 = net.brgb[1]; p.brgb2 = net.brgb[2];
-  nerf_mlp_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, *(const TcConsts*)net.consts);
+  nerf_mlp_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { *err = std::string("nerf_mlp_tc_kernel launch: ") + cudaGetErrorString(e); return -1; }
   *launches += 1;
@@ -679,13 +717,17 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
     if (s < kLayers) {
       const int kin = (s == 0) ? d.xyz : (s == skipl ? d.xyz + kHid : kHid);
       const float* W = hn.pts_w[s].data();
+      auto both = [&](const float* Wp, int k0, int kmax) {   // N-half 0 then N-half 1 of one K chunk
+        pack_chunk(chunks, Wp, kHalf, kin, k0, kmax);
+        pack_chunk(chunks, Wp + (size_t)kHalf * kin, kHalf, kin, k0, kmax);
+      };
       if (s == 0) {
-        for (int c = 0; c < 3; ++c) pack_chunk(chunks, W, kHid, kin, 32 * c, d.xyz);
+        for (int c = 0; c < 3; ++c) both(W, 32 * c, d.xyz);
       } else if (s == skipl) {
-        for (int c = 0; c < 3; ++c) pack_chunk(chunks, W, kHid, kin, 32 * c, d.xyz);
-        for (int c = 0; c < 8; ++c) pack_chunk(chunks, W + d.xyz, kHid, kin, 32 * c, kHid);
+        for (int c = 0; c < 3; ++c) both(W, 32 * c, d.xyz);
+        for (int c = 0; c < 8; ++c) both(W + d.xyz, 32 * c, kHid);
       } else {
-        for (int c = 0; c < 8; ++c) pack_chunk(chunks, W, kHid, kin, 32 * c, kHid);
+        for (int c = 0; c < 8; ++c) both(W, 32 * c, kHid);
       }
     } else {
       for (int c = 0; c < 8; ++c) pack_chunk(chunks, wfold.data(), kHalf, kHid, 32 * c, kHid);
@@ -698,6 +740,11 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
   for (int o = 0; o < kHalf; ++o) memcpy(&wvd[(size_t)o * d.dap], &hn.views_w[(size_t)o * vin + kHid], (d.dirs + d.app) * sizeof(float));
   size_t o_wvd = put(wvd.data(), wvd.size());
   size_t o_bv = put(bfold.data(), kHalf);
+  std::vector<float> bias(kLayers * kHid);
+  for (int i = 0; i < kLayers; ++i) memcpy(&bias[i * kHid], hn.pts_b[i].data(), kHid * sizeof(float));
+  size_t o_bias = put(bias.data(), bias.size());
+  size_t o_wa = put(hn.alpha_w.data(), kHid);
+  size_t o_wr = put(hn.rgb_w.data(), 3 * kHalf);
 
   size_t cbytes = (chunks.size() + 1023) / 1024 * 1024;
   size_t total = cbytes + fl.size() * sizeof(float);
@@ -715,11 +762,7 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
   const float* fb = (const float*)(base + cbytes);
   out->chunks = base;
   out->wview_d = fb + o_wvd; out->bview = fb + o_bv;
-  TcConsts* kc = out->consts ? (TcConsts*)out->consts : new TcConsts();
-  for (int i = 0; i < kLayers; ++i) memcpy(kc->bias[i], hn.pts_b[i].data(), kHid * sizeof(float));
-  memcpy(kc->walpha, hn.alpha_w.data(), kHid * sizeof(float));
-  memcpy(kc->wrgb, hn.rgb_w.data(), 3 * kHalf * sizeof(float));
-  out->consts = kc;
+  out->bias = fb + o_bias; out->walpha = fb + o_wa; out->wrgb = fb + o_wr;
   out->balpha = hn.alpha_b[0];
   for (int i = 0; i < 3; ++i) out->brgb[i] = hn.rgb_b[i];
   out->set = true;
@@ -730,11 +773,17 @@ int tc_set_cluster(int cs) {   // kept for ABI stability: measured no gain from 
   return (cs == 1 || cs == 2 || cs == 4) ? 0 : -1;
 }
 
+int tc_read_timeline(long long* host, int n) {
+  if (!g_timeline) return 0;
+  int m = std::min(n, 8 * kSteps * 4 + 32);
+  cudaMemcpy(host, g_timeline, m * sizeof(long long), cudaMemcpyDeviceToHost);
+  return m;
+}
+
 int tc_trap_code() { return g_trap_host ? *(volatile int*)g_trap_host : 0; }
 
 void tc_free_net(TcNet* n) {
   if (n->pool) cudaFree(n->pool);
-  if (n->consts) delete (TcConsts*)n->consts;
   *n = TcNet{};
 }
 

@@ -20,7 +20,9 @@ struct TcNet {
   size_t bytes = 0;
   bool set = false;
   const uint8_t* chunks = nullptr;   // weight chunk stream (device)
-  void* consts = nullptr;            // host TcConsts: biases + head weights, passed as kernel parameters
+  const float* bias = nullptr;       // [8][256] pts_linears bias (fp32, device)
+  const float* walpha = nullptr;     // [256]
+  const float* wrgb = nullptr;       // [3][128]
   const float* wview_d = nullptr;    // [128][dap]  dirs+app part of views_linears.0 (fp32, device)
   const float* bview = nullptr;      // [128] views bias with the folded feature_linear bias (device)
   float balpha = 0.f;
@@ -52,6 +54,7 @@ int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int 
 
 // code recorded by a bounded barrier wait before trapping (mapped host memory), 0 = none
 int tc_trap_code();
+int tc_read_timeline(long long* host, int n);   // clock64 trace of CTA 0 (NMR_TC_TIMELINE=1)
 int tc_set_cluster(int cluster_size);   // 1, 2 or 4
 
 }  // namespace nmr

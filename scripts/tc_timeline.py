@@ -1,0 +1,37 @@
+"""Print the tcgen05 kernel's per-step timeline (cycles) of CTA 0.  Run with NMR_TC_TIMELINE=1 on the GPU box."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from nerfmatch_b200 import _lib as L
+from nerfmatch_b200.engine import Engine, EngineConfig
+from nerfmatch_b200.synthetic import make_state_dict
+
+embed = sys.argv[1] if len(sys.argv) > 1 else "normal"
+sd = make_state_dict(0, embed_type=embed, sigma_gain=120.0, sigma_bias=(8.0, 8.0))
+wts = {k[len("nerf_fine."):]: torch.from_numpy(v) for k, v in sd.items() if k.startswith("nerf_fine.")}
+eng = Engine(EngineConfig(embed_type=embed, precision="bf16"), torch.device("cuda:0"))
+eng.set_weights(0, wts)
+P = 128 * 148 * 2 * 10
+x = torch.rand(P, eng.cfg.in_dim, device="cuda") * 2 - 1
+for _ in range(2):
+    eng.stage_mlp(0, x, 3)
+torch.cuda.synchronize()
+buf = (C.c_longlong * (8 * 9 * 4 + 32))()
+n = L.load().nmr_debug_timeline(buf, len(buf))
+t = np.array(buf[:8 * 9 * 4], dtype=np.int64).reshape(8, 9, 4)
+t0 = t[1:6]
+print("per step (cycles), iterations 1..5 averaged")
+print("step  mma_issue  mma_end->epi_start  epilogue  epi_end->next_mma_start   total")
+for s in range(9):
+    issue = (t0[:, s, 1] - t0[:, s, 0]).mean()
+    lat1 = (t0[:, s, 2] - t0[:, s, 1]).mean()
+    epi = (t0[:, s, 3] - t0[:, s, 2]).mean()
+    nxt = t[1:6, s + 1, 0] if s < 8 else t[2:7, 0, 0]
+    lat2 = (nxt - t0[:, s, 3]).mean()
+    print(f"{s:4d} {issue:10.0f} {lat1:18.0f} {epi:9.0f} {lat2:22.0f} {issue + lat1 + epi + lat2:8.0f}")
+print("iteration period:", np.diff(t[1:7, 0, 0]).mean())
