@@ -12,18 +12,21 @@
 //     epilogues of the layers that feed them; the [dirs | appearance] part of views_linears is a
 //     per-ray fp32 bias computed once per ray; feature_linear (no activation) is folded into
 //     views_linears on the host (W_view_f * W_feat), which removes one layer and 11 % of the weights;
-//   * weights stream from L2 through a ring of 16 KB shared-memory stages filled by the bulk-copy (TMA)
-//     engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the host, so no tensor
-//     map is needed.  L2 -> SM delivery caps at ~27 B/cycle/SM on B200 (tools/smem_fill_bw.cu) while a
-//     128-row tile at full tensor rate would need 63 B/cycle, so every chunk is shared by the TWO
-//     128-point tiles ("slots") a CTA keeps in flight: 2 x 256 TMEM columns, M = 256 per weight fetch;
-//   * the tapped feature tile (stop_layer) leaves as one 64 KB bulk store shared->global in the same
-//     tiled layout the compositor reads;
-//   * biases and head weights are read through L1 (LDG.128, warp-uniform); nothing but the
-//     weight stream competes for shared memory.
+//   * the accumulator is double buffered in TMEM (2 x 256 columns, alternating by layer) and the epilogue
+//     hands the next layer's operand over in 32-column chunks (one mbarrier per chunk), so the tensor core
+//     starts layer l+1 on chunk 0 while the epilogue is still draining layer l.  Eight epilogue warps
+//     (two per TMEM lane quarter, even / odd chunks) keep the hand-over faster than the MMA consumes it;
+//   * weights stream from L2 through a 6-stage ring of 16 KB shared-memory stages filled by the bulk-copy
+//     (TMA) engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the host, so no tensor
+//     map is needed.  Measured on B200 (tools/smem_fill_bw.cu): L2 -> SM delivery caps at ~27 B/cycle/SM for
+//     every fill mechanism and TMA multicast does not lower it at cluster sizes <= 4, so this kernel's
+//     ceiling is the weight stream: 1.06 MB per 128-point tile;
+//   * bias / head-weight tables live in shared memory (indexed constant-bank or L1-less global loads cost
+//     the epilogue 2-3x, measured); the tapped feature tile (stop_layer) leaves as one 64 KB bulk store
+//     shared->global in the same tiled layout the compositor reads.
 //
 // Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 idle,
-// 4-7 epilogue of slot 0, 8-11 epilogue of slot 1, 12-15 encoder.
+// 4-7 epilogue (even chunks), 8-11 epilogue (odd chunks), 12-15 encoder.
 #include <cstdlib>
 #include <cstring>
 
@@ -37,24 +40,27 @@ constexpr int kTileM = 128;
 constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64B swizzle
 constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
 constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
-constexpr int kStageBytes = 8192;          // one [128 N x 32 K] weight block (half of a layer's N)
-constexpr int kStages = 5;
+constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
+constexpr int kStages = 6;
 constexpr int kSteps = 9;                  // 8 trunk layers + (feature_linear folded into) views_linears.0
 constexpr int kViewStep = 8;
 constexpr int kThreads = 512;
 constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128 points
 
 constexpr int OFF_H = 0;
-constexpr int OFF_E = 2 * kHBytes;
+constexpr int OFF_E = kHBytes;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
 constexpr int OFF_TAB = OFF_W + kStages * kStageBytes;        // fp32 tables: bias [8][256], walpha [256], wrgb [3][128]
 constexpr int kTabFloats = kLayers * kHid + kHid + 3 * kHalf;
-constexpr int OFF_BAR = OFF_TAB + kTabFloats * 4;
-constexpr int kSmemBytes = OFF_BAR + 128;                    // dynamic smem is 1024-aligned (checked at kernel entry)
+constexpr int OFF_PART = OFF_TAB + kTabFloats * 4;            // float4 per row: partial (rgb, alpha) of the odd-chunk warps
+constexpr int OFF_BAR = OFF_PART + kTileM * 16;
+constexpr int kSmemBytes = OFF_BAR + 256;                     // dynamic smem is 1024-aligned (checked at kernel entry)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
-enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_AREADY, BAR_EFULL, BAR_EEMPTY, BAR_COUNT };
+enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_HREADY = BAR_ACCFULL + 2,
+       BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_COUNT = BAR_EEMPTY + 2 };
+static_assert(BAR_COUNT * 8 + 8 <= 256, "barrier area");
 
 struct TcParams {
   const uint8_t* chunks;
@@ -76,11 +82,10 @@ struct TcParams {
 
 __host__ __device__ constexpr int step_chunks_e(int s) { return (s == 0 || s == 5) ? 3 : 0; }
 __host__ __device__ constexpr int step_chunks_h(int s) { return s == 0 ? 0 : 8; }
-__host__ __device__ constexpr int step_nhalves(int s) { return s == kViewStep ? 1 : 2; }   // N = 128 per weight block
-__host__ __device__ constexpr int step_blocks(int s) { return (step_chunks_e(s) + step_chunks_h(s)) * step_nhalves(s); }
+__host__ __device__ constexpr int step_chunk_bytes(int s) { return s == kViewStep ? 8192 : 16384; }
 __host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the weight stream
   int64_t off = 0;
-  for (int i = 0; i < s; ++i) off += (int64_t)step_blocks(i) * kStageBytes;
+  for (int i = 0; i < s; ++i) off += (int64_t)(step_chunks_e(i) + step_chunks_h(i)) * step_chunk_bytes(i);
   return off;
 }
 
@@ -292,15 +297,15 @@ __device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, int j, c
   }
 }
 
-// views_linears.0 epilogue (4 slices of 32): per-ray view bias + ReLU, rgb_linear + sigmoid, raw [P,4] store.
-__device__ __forceinline__ void epi_view(const float* tab, const float* vbrow, uint32_t t_lane, const TcParams& p, bool valid,
-                                         int64_t pt, float alpha) {
-  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+// views_linears.0 epilogue: this warp's two 32-column slices (g, g+2): per-ray view bias + ReLU, rgb_linear partials.
+__device__ __forceinline__ void epi_view(const float* tab, const float* vbrow, uint32_t t_lane, int g, const TcParams& p, bool valid,
+                                         int64_t pt, float& c0, float& c1, float& c2) {
   float4 vq[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) vq[i] = vbrow ? __ldg(reinterpret_cast<const float4*>(vbrow) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 8; ++i) vq[i] = vbrow ? __ldg(reinterpret_cast<const float4*>(vbrow + g * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (int j = 0; j < 4; ++j) {
+  for (int jj = 0; jj < 2; ++jj) {
+    const int j = g + 2 * jj;
     uint32_t v[32];
     tmem_ld32(t_lane + j * 32, v);
     tmem_ld_wait();
@@ -311,9 +316,9 @@ __device__ __forceinline__ void epi_view(const float* tab, const float* vbrow, u
       x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
       x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
     }
-    if (j < 3) {                                   // next slice of the view bias: L2 latency hides behind the rgb FMAs
+    if (jj == 0) {                                 // next slice of the view bias: L2 latency hides behind the rgb FMAs
 #pragma unroll
-      for (int i = 0; i < 8; ++i) vq[i] = vbrow ? __ldg(reinterpret_cast<const float4*>(vbrow + (j + 1) * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) vq[i] = vbrow ? __ldg(reinterpret_cast<const float4*>(vbrow + (g + 2) * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float4* w0 = reinterpret_cast<const float4*>(tab + (kLayers + 1) * kHid + j * 32);
     const float4* w1 = w0 + kHalf / 4;
@@ -330,14 +335,6 @@ __device__ __forceinline__ void epi_view(const float* tab, const float* vbrow, u
       for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = x[i];
     }
   }
-  if (valid) {
-    float4 o;
-    o.x = 1.f / (1.f + __expf(-(c0 + p.brgb0)));
-    o.y = 1.f / (1.f + __expf(-(c1 + p.brgb1)));
-    o.z = 1.f / (1.f + __expf(-(c2 + p.brgb2)));
-    o.w = alpha + p.balpha;
-    *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
-  }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------
@@ -348,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   const uint32_t bars = base + OFF_BAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + BAR_COUNT * 8);
   float* tab = reinterpret_cast<float*>(gbase + OFF_TAB);
+  float4* part = reinterpret_cast<float4*>(gbase + OFF_PART);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
   if (base & 1023u) {                              // the swizzled UMMA tiles need a 1024-byte aligned window
@@ -360,10 +358,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); }
-    mbar_init(bars + 8 * BAR_ACCFULL, 1);
-    mbar_init(bars + 8 * BAR_AREADY, 256);
-    mbar_init(bars + 8 * BAR_EFULL, 128);
-    mbar_init(bars + 8 * BAR_EEMPTY, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bars + 8 * (BAR_ACCFULL + i), 1);
+      mbar_init(bars + 8 * (BAR_EFULL + i), 128);
+      mbar_init(bars + 8 * (BAR_EEMPTY + i), 1);
+    }
+    for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -376,18 +376,19 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== weight producer: bulk-copy chunks global -> smem ring; each chunk serves both slots =====
+    // ===== weight producer: bulk-copy chunks global -> smem ring =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < p.n_iters; ++it) {
         const uint8_t* src = p.chunks;
         for (int s = 0; s < kSteps; ++s) {
-          const int nblk = step_blocks(s);
-          for (int c = 0; c < nblk; ++c) {
+          const int nch = step_chunks_e(s) + step_chunks_h(s);
+          const uint32_t bytes = step_chunk_bytes(s);
+          for (int c = 0; c < nch; ++c) {
             mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
-            mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), kStageBytes);
-            bulk_g2s(base + OFF_W + stage * kStageBytes, src, kStageBytes, bars + 8 * (BAR_WFULL + stage));
-            src += kStageBytes;
+            mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
+            bulk_g2s(base + OFF_W + stage * kStageBytes, src, bytes, bars + 8 * (BAR_WFULL + stage));
+            src += bytes;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -396,154 +397,178 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
-      int stage = 0; uint32_t wphase = 0, ph_aready = 0, ph_efull = 0;
-      for (int it = 0; it < p.n_iters; ++it) {
-        for (int s = 0; s < kSteps; ++s) {
+      int stage = 0; uint32_t wphase = 0, hphase = 0;
+      uint32_t ph_efull[2] = {0, 0};
+      int gstep = 0;                                               // running layer count: 9 steps per tile is odd, so the
+      for (int it = 0; it < p.n_iters; ++it) {                     // accumulator ping-pong must carry across tiles
+        const int eb = it & 1;
+        for (int s = 0; s < kSteps; ++s, ++gstep) {
           const int ne = step_chunks_e(s), nh = step_chunks_h(s);
-          const uint32_t idesc = umma_idesc(128);
-          const int nhv = step_nhalves(s);
-          // both slots' previous epilogues are done: TMEM drained, H written (count 256)
-          mbar_wait(bars + 8 * BAR_AREADY, ph_aready, p.error_flag, 200);
-          ph_aready ^= 1;
-          if (s == 0) { mbar_wait(bars + 8 * BAR_EFULL, ph_efull, p.error_flag, 210); ph_efull ^= 1; }
-          tc_fence_after();
+          const uint32_t idesc = umma_idesc((s == kViewStep) ? 128 : 256);
+          const int ab = gstep & 1;
+          const uint32_t d_tmem = tmem_base + ab * 256;            // accumulator ping-pong by layer
+          if (s == 0) {
+            mbar_wait(bars + 8 * (BAR_EFULL + eb), ph_efull[eb], p.error_flag, 210 + eb);
+            ph_efull[eb] ^= 1;
+          }
           if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 0] = clock64();
           uint32_t accumulate = 0;
           for (int c = 0; c < ne + nh; ++c) {
-            // descriptor low words (start address >> 4 | LBO); +2 advances K by 16 elements (32 bytes)
-            const uint32_t a0 = desc_lo((c < ne) ? (base + OFF_E + c * kBlk) : (base + OFF_H + (c - ne) * kBlk));
-            const uint32_t a1 = a0 + (((c < ne) ? kEBytes : kHBytes) >> 4);          // slot 1 tile
-            for (int half = 0; half < nhv; ++half) {           // weight blocks arrive K-chunk major, N-half minor
-              const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
+            const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
+            uint32_t a0;
+            if (c < ne) {
+              a0 = desc_lo(base + OFF_E + eb * kEBytes + c * kBlk);
               if (!mbar_try_wait(wbar, wphase)) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
-              tc_fence_after();
-              const uint32_t b0 = desc_lo(base + OFF_W + stage * kStageBytes);
-              const uint32_t d0 = tmem_base + half * 128;
-              umma_bf16(d0, mk_desc(a0), mk_desc(b0), idesc, accumulate);
-              umma_bf16(d0, mk_desc(a0 + 2), mk_desc(b0 + 2), idesc, 1u);
-              umma_bf16(d0 + 256, mk_desc(a1), mk_desc(b0), idesc, accumulate);
-              umma_bf16(d0 + 256, mk_desc(a1 + 2), mk_desc(b0 + 2), idesc, 1u);
-              umma_commit(bars + 8 * (BAR_WEMPTY + stage));    // stage free once these MMAs retire
-              if (++stage == kStages) { stage = 0; wphase ^= 1; }
+            } else {
+              // chunk (c-ne) of the previous layer's output: handed over by the epilogue
+              a0 = desc_lo(base + OFF_H + (c - ne) * kBlk);
+              const uint32_t hbar = bars + 8 * (BAR_HREADY + (c - ne));
+              const bool ok_h = mbar_try_wait(hbar, hphase), ok_w = mbar_try_wait(wbar, wphase);   // both probes in flight
+              if (!ok_h) mbar_wait_slow(hbar, hphase, p.error_flag, 230 + (c - ne));
+              if (!ok_w) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
             }
+            tc_fence_after();
+            const uint32_t b0 = desc_lo(base + OFF_W + stage * kStageBytes);
+            umma_bf16(d_tmem, mk_desc(a0), mk_desc(b0), idesc, accumulate);
+            umma_bf16(d_tmem, mk_desc(a0 + 2), mk_desc(b0 + 2), idesc, 1u);
             accumulate = 1;
+            umma_commit(bars + 8 * (BAR_WEMPTY + stage));          // stage free once these MMAs retire
+            if (++stage == kStages) { stage = 0; wphase ^= 1; }
           }
           if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 1] = clock64();
-          umma_commit(bars + 8 * BAR_ACCFULL);                 // both accumulators complete -> epilogues
-          if (s == 5) umma_commit(bars + 8 * BAR_EEMPTY);      // encoded tiles no longer needed
+          umma_commit(bars + 8 * (BAR_ACCFULL + ab));              // accumulator complete -> epilogue
+          if (s == 5) umma_commit(bars + 8 * (BAR_EEMPTY + eb));   // encoded tile no longer needed
+          if (nh) hphase ^= 1;
         }
       }
     }
   } else if (warp >= 4 && warp < 12) {
     // ===== epilogue warps: TMEM -> bias/activation -> bf16 A operand of the next layer =====
-    const int slot = (warp - 4) >> 2;
+    const int g = (warp - 4) >> 2;                  // 0: even 32-column chunks, 1: odd chunks
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                    // row of the tile
-    const int et = (warp - 4 - slot * 4) * 32 + lane;  // thread index inside the slot's epilogue group
-    const uint32_t h_base = base + OFF_H + slot * kHBytes;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + slot * 256;
-    mbar_arrive(bars + 8 * BAR_AREADY);             // TMEM / H start out free
-    uint32_t ph_acc = 0;
+    const int et = (warp - 4) * 32 + lane;          // 0..255
+    const uint32_t h_base = base + OFF_H;
+    uint32_t ph_acc[2] = {0, 0};
     bool store_pending = false;
     EpiCtx e;
     e.h_base = h_base; e.r = r; e.tab = tab;
+    int gstep = 0;
     for (int it = 0; it < p.n_iters; ++it) {
-      const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
+      const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
       e.alpha = 0.f;
-      for (int s = 0; s < kSteps; ++s) {
+      for (int s = 0; s < kSteps; ++s, ++gstep) {
         e.s = s;
+        const int ab = gstep & 1;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
         const float* vbrow = (s == kViewStep && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
-        mbar_wait(bars + 8 * BAR_ACCFULL, ph_acc, p.error_flag, 300 + slot);
-        ph_acc ^= 1;
+        mbar_wait(bars + 8 * (BAR_ACCFULL + ab), ph_acc[ab], p.error_flag, 300 + ab);
+        ph_acc[ab] ^= 1;
         tc_fence_after();
-        if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0 && slot == 0) p.timeline[(it * kSteps + s) * 4 + 2] = clock64();
+        if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 2] = clock64();
         if (s < kViewStep) {
           if (store_pending) {                      // the tap store must have finished reading H
             if (et == 0) bulk_wait_read0();
-            named_bar_sync(1 + slot, 128);
+            named_bar_sync(1, 256);
             store_pending = false;
           }
           uint32_t va[32], vb[32];
-          tmem_ld32(t_lane, va);
+          tmem_ld32(t_lane + g * 32, va);
 #pragma unroll 1
-          for (int j = 0; j < 8; j += 2) {          // software pipelined: load slice j+1 while slice j is processed
+          for (int jj = 0; jj < 4; jj += 2) {       // this warp's chunks j = g, g+2, g+4, g+6; software pipelined
+            const int j = g + 2 * jj;
             tmem_ld_wait();
-            tmem_ld32(t_lane + (j + 1) * 32, vb);
+            tmem_ld32(t_lane + (j + 2) * 32, vb);
             epi_trunk(e, va, j, p, valid, pt);
+            fence_proxy_async();                     // generic-proxy writes -> visible to UMMA / bulk copy
+            mbar_arrive(bars + 8 * (BAR_HREADY + j));
             tmem_ld_wait();
-            if (j + 2 < 8) tmem_ld32(t_lane + (j + 2) * 32, va);
-            epi_trunk(e, vb, j + 1, p, valid, pt);
+            if (jj + 2 < 4) tmem_ld32(t_lane + (j + 4) * 32, va);
+            epi_trunk(e, vb, j + 2, p, valid, pt);
+            fence_proxy_async();
+            mbar_arrive(bars + 8 * (BAR_HREADY + j + 2));
           }
           tc_fence_before();
-          fence_proxy_async();                       // generic-proxy writes -> visible to UMMA / bulk copy
+          if (s == 7 && g == 1) part[r].w = e.alpha;   // odd-chunk warps publish their partial sigma dot product
         } else {
-          epi_view(tab, vbrow, t_lane, p, valid, pt, e.alpha);
+          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+          epi_view(tab, vbrow, t_lane, g, p, valid, pt, c0, c1, c2);
           tc_fence_before();
+          if (g == 1) { part[r].x = c0; part[r].y = c1; part[r].z = c2; }
+          named_bar_sync(2, 256);
+          if (g == 0 && valid) {
+            const float4 o1 = part[r];
+            float4 o;
+            o.x = 1.f / (1.f + __expf(-(c0 + o1.x + p.brgb0)));
+            o.y = 1.f / (1.f + __expf(-(c1 + o1.y + p.brgb1)));
+            o.z = 1.f / (1.f + __expf(-(c2 + o1.z + p.brgb2)));
+            o.w = e.alpha + o1.w + p.balpha;
+            *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+          }
+          named_bar_sync(2, 256);                    // part[] is free again for the next tile
         }
         if (s == p.stop_step && p.want_feat) {
-          named_bar_sync(1 + slot, 128);             // all 128 rows written (and fenced) before the bulk store
+          named_bar_sync(1, 256);                    // all 128 rows x 8 chunks written (and fenced) before the bulk store
           if (et == 0 && tile * kTileM < p.P) {
             bulk_s2g(p.feat_tiles + (size_t)tile * kFeatTileBytes, h_base, kFeatTileBytes);
             bulk_commit();
           }
           store_pending = true;
         }
-        if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0 && slot == 0) p.timeline[(it * kSteps + s) * 4 + 3] = clock64();
-        mbar_arrive(bars + 8 * BAR_AREADY);
+        if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 3] = clock64();
       }
     }
     if (et == 0) bulk_wait0();
   } else if (warp >= 12) {
-    // ===== encoder warps: sampling data -> positional encoding -> bf16 A tiles of layer 0 / skip =====
+    // ===== encoder warps: sampling data -> positional encoding -> bf16 A tile of layer 0 / skip =====
     const int r = (warp - 12) * 32 + lane;
-    uint32_t ph_eempty = 0;
+    uint32_t ph_eempty[2] = {0, 0};
     for (int it = 0; it < p.n_iters; ++it) {
-      mbar_wait(bars + 8 * BAR_EEMPTY, ph_eempty ^ 1, p.error_flag, 400);
-      ph_eempty ^= 1;
-      for (int slot = 0; slot < 2; ++slot) {
-        const int64_t tile = ((int64_t)it * G + blockIdx.x) * 2 + slot;
-        const int64_t pt = tile * kTileM + r;
-        const bool valid = pt < p.P;
-        float m[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
-        const float* xrow = nullptr;
-        if (valid) {
-          if (p.mode == 0) {
-            const int64_t ray = pt / p.S;
-            const int sidx = (int)(pt - ray * p.S);
-            const float* rr = p.rays + ray * p.ncols;
-            if (p.mip) {
-              const float* z = p.z + ray * (p.S + 1);
-              float rl[12];
+      const int eb = it & 1;
+      const int64_t tile = (int64_t)it * G + blockIdx.x;
+      const int64_t pt = tile * kTileM + r;
+      const bool valid = pt < p.P;
+      float m[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
+      const float* xrow = nullptr;
+      if (valid) {
+        if (p.mode == 0) {
+          const int64_t ray = pt / p.S;
+          const int sidx = (int)(pt - ray * p.S);
+          const float* rr = p.rays + ray * p.ncols;
+          if (p.mip) {
+            const float* z = p.z + ray * (p.S + 1);
+            float rl[12];
 #pragma unroll
-              for (int i = 0; i < 12; ++i) rl[i] = __ldg(rr + i);
-              frustum_gaussian(rl, __ldg(z + sidx), __ldg(z + sidx + 1), p.var_scale, m, vv);
-            } else {
-              const float zz = __ldg(p.z + pt);
-#pragma unroll
-              for (int c = 0; c < 3; ++c) m[c] = __ldg(rr + c) + __ldg(rr + 3 + c) * zz;
-            }
+            for (int i = 0; i < 12; ++i) rl[i] = __ldg(rr + i);
+            frustum_gaussian(rl, __ldg(z + sidx), __ldg(z + sidx + 1), p.var_scale, m, vv);
           } else {
-            xrow = p.X + pt * p.kx;
-          }
-        }
-        const RowWriter rw{base + OFF_E + slot * kEBytes, r};
-        if (p.mode == 1 || !valid) {
-          for (int ch = 0; ch < 12; ++ch) {
-            float f[8];
+            const float zz = __ldg(p.z + pt);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const int col = ch * 8 + i; f[i] = (valid && col < p.xyz) ? __ldg(xrow + col) : 0.f; }
-            rw.store(ch, f);
+            for (int c = 0; c < 3; ++c) m[c] = __ldg(rr + c) + __ldg(rr + 3 + c) * zz;
           }
-        } else if (p.mip) {
-          encode_row_ipe<15>(m, vv, rw);
         } else {
-          encode_row_fourier<15>(m, rw);
+          xrow = p.X + pt * p.kx;
         }
       }
+      mbar_wait(bars + 8 * (BAR_EEMPTY + eb), ph_eempty[eb] ^ 1, p.error_flag, 400 + eb);
+      ph_eempty[eb] ^= 1;
+      const RowWriter rw{base + OFF_E + eb * kEBytes, r};
+      if (p.mode == 1 || !valid) {
+        for (int ch = 0; ch < 12; ++ch) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const int col = ch * 8 + i; f[i] = (valid && col < p.xyz) ? __ldg(xrow + col) : 0.f; }
+          rw.store(ch, f);
+        }
+      } else if (p.mip) {
+        encode_row_ipe<15>(m, vv, rw);
+      } else {
+        encode_row_fourier<15>(m, rw);
+      }
       fence_proxy_async();
-      mbar_arrive(bars + 8 * BAR_EFULL);
+      mbar_arrive(bars + 8 * (BAR_EFULL + eb));
     }
   }
 
@@ -676,9 +701,8 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
   if (!g_timeline && getenv("NMR_TC_TIMELINE")) { cudaMalloc((void**)&g_timeline, (8 * kSteps * 4 + 32) * sizeof(long long)); cudaMemset(g_timeline, 0, (8 * kSteps * 4 + 32) * sizeof(long long)); }
   p.timeline = g_timeline;
   int64_t tiles = (p.P + kTileM - 1) / kTileM;
-  int64_t pairs = (tiles + 1) / 2;
-  int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(pairs, 1));
-  p.n_iters = (int)((pairs + grid - 1) / grid);
+  int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(tiles, 1));
+  p.n_iters = (int)((tiles + grid - 1) / grid);
   p.chunks = net.chunks; p.bias = net.bias; p.walpha = net.walpha; p.wrgb = net.wrgb;
   p.balpha = net.balpha; p.brgb0 = net.brgb[0]; p.brgb1 = net.brgb[1]; p.brgb2 = net.brgb[2];
   nerf_mlp_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
@@ -717,10 +741,7 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
     if (s < kLayers) {
       const int kin = (s == 0) ? d.xyz : (s == skipl ? d.xyz + kHid : kHid);
       const float* W = hn.pts_w[s].data();
-      auto both = [&](const float* Wp, int k0, int kmax) {   // N-half 0 then N-half 1 of one K chunk
-        pack_chunk(chunks, Wp, kHalf, kin, k0, kmax);
-        pack_chunk(chunks, Wp + (size_t)kHalf * kin, kHalf, kin, k0, kmax);
-      };
+      auto both = [&](const float* Wp, int k0, int kmax) { pack_chunk(chunks, Wp, kHid, kin, k0, kmax); };
       if (s == 0) {
         for (int c = 0; c < 3; ++c) both(W, 32 * c, d.xyz);
       } else if (s == skipl) {
