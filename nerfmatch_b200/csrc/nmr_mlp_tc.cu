@@ -50,16 +50,18 @@ constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128
 constexpr int OFF_H = 0;
 constexpr int OFF_E = kHBytes;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
-constexpr int OFF_TAB = OFF_W + kStages * kStageBytes;        // fp32 tables: bias [8][256], walpha [256], wrgb [3][128]
-constexpr int kTabFloats = kLayers * kHid + kHid + 3 * kHalf;
+constexpr int OFF_TAB = OFF_W + kStages * kStageBytes;        // fp32 tables: walpha [256], wrgb [3][128]
+constexpr int kTabFloats = kHid + 3 * kHalf;
 constexpr int OFF_PART = OFF_TAB + kTabFloats * 4;            // float4 per row: partial (rgb, alpha) of the odd-chunk warps
-constexpr int OFF_BAR = OFF_PART + kTileM * 16;
+constexpr int kVbRays = 4;                                    // rays a 128-point tile can touch when S >= 43
+constexpr int OFF_VBS = OFF_PART + kTileM * 16;               // 2 x [kVbRays][128] fp32: per-ray view bias of the tile (double buffered)
+constexpr int OFF_BAR = OFF_VBS + 2 * kVbRays * kHalf * 4;
 constexpr int kSmemBytes = OFF_BAR + 256;                     // dynamic smem is 1024-aligned (checked at kernel entry)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
 enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_HREADY = BAR_ACCFULL + 2,
-       BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_COUNT = BAR_EEMPTY + 2 };
+       BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_VEMPTY = BAR_EEMPTY + 2, BAR_COUNT = BAR_VEMPTY + 2 };
 static_assert(BAR_COUNT * 8 + 8 <= 256, "barrier area");
 
 struct TcParams {
@@ -82,10 +84,14 @@ struct TcParams {
 
 __host__ __device__ constexpr int step_chunks_e(int s) { return (s == 0 || s == 5) ? 3 : 0; }
 __host__ __device__ constexpr int step_chunks_h(int s) { return s == 0 ? 0 : 8; }
+// trunk biases ride in the GEMM: columns 94 / 95 of the encoded tile are 1.0 and the matching weight rows hold the
+// bf16 (lo, hi) split of the bias.  Layers fed by the encoded tile (0, 5) get it for free; the H-fed trunk layers
+// append one K=16 MMA on a "bias chunk" (A = encoded columns 80..95, all other weight rows zero).
+__host__ __device__ constexpr int step_bias_chunk(int s) { return (s >= 1 && s <= 7 && s != 5) ? 1 : 0; }
 __host__ __device__ constexpr int step_chunk_bytes(int s) { return s == kViewStep ? 8192 : 16384; }
 __host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the weight stream
   int64_t off = 0;
-  for (int i = 0; i < s; ++i) off += (int64_t)(step_chunks_e(i) + step_chunks_h(i)) * step_chunk_bytes(i);
+  for (int i = 0; i < s; ++i) off += (int64_t)(step_chunks_e(i) + step_chunks_h(i) + step_bias_chunk(i)) * step_chunk_bytes(i);
   return off;
 }
 
@@ -224,6 +230,8 @@ __device__ __forceinline__ void encode_row_fourier(const float m[3], const RowWr
         }
       }
       v = rr < 3 ? sn[rr] : cs[rr - 3];
+    } else if (col >= 94) {
+      v = 1.0f;                                    // bias carrier columns
     }
     f[col & 7] = v;
     if ((col & 7) == 7) w.store(col >> 3, f);
@@ -256,6 +264,8 @@ __device__ __forceinline__ void encode_row_ipe(const float m[3], const float var
         }
       }
       v = dm[c] * (half == 0 ? sn[c] : cs[c]);
+    } else if (col >= 94) {
+      v = 1.0f;                                    // bias carrier columns
     }
     f[col & 7] = v;
     if ((col & 7) == 7) w.store(col >> 3, f);
@@ -268,17 +278,26 @@ struct EpiCtx {
   uint32_t h_base; int r; int s;
   float alpha;
 };
-__device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, bool valid, int64_t pt) {
-  float x[32];
-  const float4* bp = reinterpret_cast<const float4*>(e.tab + e.s * kHid + j * 32);   // warp-uniform LDS broadcast
+// Fast path (every trunk layer but the one feeding sigma): the bias is already in the accumulator, so a slice is
+// 16 ReLU-fused bf16x2 conversions (F2FP.RELU) and four 16-byte stores.
+__device__ __forceinline__ void epi_trunk_fast(const EpiCtx& e, const uint32_t* v, int j) {
+  uint32_t w[16];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 t = bp[i];
-    x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
-    x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
-  }
+  for (int i = 0; i < 16; ++i)
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.h_base + j * kBlk + sw64_off(e.r, c)), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                 "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
+}
+
+__device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, bool valid, int64_t pt) {
+  if (e.s != 7 && p.debug_out == nullptr) { epi_trunk_fast(e, v, j); return; }
+  float x[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = fmaxf(__uint_as_float(v[i]), 0.f);
   if (e.s == 7) {                                  // alpha_linear on the un-rounded fp32 activations
-    const float4* wp = reinterpret_cast<const float4*>(e.tab + kLayers * kHid + j * 32);
+    const float4* wp = reinterpret_cast<const float4*>(e.tab + j * 32);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 w = wp[i];
@@ -302,7 +321,7 @@ __device__ __forceinline__ void epi_view(const float* tab, const float* vbrow, u
                                          int64_t pt, float& c0, float& c1, float& c2) {
   float4 vq[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) vq[i] = vbrow ? __ldg(reinterpret_cast<const float4*>(vbrow + g * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < 8; ++i) vq[i] = vbrow ? reinterpret_cast<const float4*>(vbrow + g * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int jj = 0; jj < 2; ++jj) {
     const int j = g + 2 * jj;
@@ -318,9 +337,9 @@ __device__ __forceinline__ void epi_view(const float* tab, const float* vbrow, u
     }
     if (jj == 0) {                                 // next slice of the view bias: L2 latency hides behind the rgb FMAs
 #pragma unroll
-      for (int i = 0; i < 8; ++i) vq[i] = vbrow ? __ldg(reinterpret_cast<const float4*>(vbrow + (g + 2) * 32) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < 8; ++i) vq[i] = vbrow ? reinterpret_cast<const float4*>(vbrow + (g + 2) * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float4* w0 = reinterpret_cast<const float4*>(tab + (kLayers + 1) * kHid + j * 32);
+    const float4* w0 = reinterpret_cast<const float4*>(tab + kHid + j * 32);
     const float4* w1 = w0 + kHalf / 4;
     const float4* w2 = w1 + kHalf / 4;
 #pragma unroll
@@ -346,15 +365,16 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + BAR_COUNT * 8);
   float* tab = reinterpret_cast<float*>(gbase + OFF_TAB);
   float4* part = reinterpret_cast<float4*>(gbase + OFF_PART);
+  float* vbs = reinterpret_cast<float*>(gbase + OFF_VBS);
+  const bool use_vbs = p.vb_div >= 43;             // a tile then spans at most kVbRays rays
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x;
   if (base & 1023u) {                              // the swizzled UMMA tiles need a 1024-byte aligned window
     if (threadIdx.x == 0) { atomicExch(p.error_flag, 900); __threadfence_system(); }
     __trap();
   }
-  for (int i = threadIdx.x; i < kLayers * kHid; i += kThreads) tab[i] = p.bias[i];
-  for (int i = threadIdx.x; i < kHid; i += kThreads) tab[kLayers * kHid + i] = p.walpha[i];
-  for (int i = threadIdx.x; i < 3 * kHalf; i += kThreads) tab[(kLayers + 1) * kHid + i] = p.wrgb[i];
+  for (int i = threadIdx.x; i < kHid; i += kThreads) tab[i] = p.walpha[i];
+  for (int i = threadIdx.x; i < 3 * kHalf; i += kThreads) tab[kHid + i] = p.wrgb[i];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); }
@@ -362,6 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       mbar_init(bars + 8 * (BAR_ACCFULL + i), 1);
       mbar_init(bars + 8 * (BAR_EFULL + i), 128);
       mbar_init(bars + 8 * (BAR_EEMPTY + i), 1);
+      mbar_init(bars + 8 * (BAR_VEMPTY + i), 256);
     }
     for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -382,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       for (int it = 0; it < p.n_iters; ++it) {
         const uint8_t* src = p.chunks;
         for (int s = 0; s < kSteps; ++s) {
-          const int nch = step_chunks_e(s) + step_chunks_h(s);
+          const int nch = step_chunks_e(s) + step_chunks_h(s) + step_bias_chunk(s);
           const uint32_t bytes = step_chunk_bytes(s);
           for (int c = 0; c < nch; ++c) {
             mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
@@ -398,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     // ===== MMA issuer =====
     if (lane == 0) {
       int stage = 0; uint32_t wphase = 0, hphase = 0;
-      uint32_t ph_efull[2] = {0, 0};
+      uint32_t ph_efull = 0;                                       // bit eb: phase of E buffer eb (bitmask: no local-memory array)
       int gstep = 0;                                               // running layer count: 9 steps per tile is odd, so the
       for (int it = 0; it < p.n_iters; ++it) {                     // accumulator ping-pong must carry across tiles
         const int eb = it & 1;
@@ -408,11 +429,24 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           const int ab = gstep & 1;
           const uint32_t d_tmem = tmem_base + ab * 256;            // accumulator ping-pong by layer
           if (s == 0) {
-            mbar_wait(bars + 8 * (BAR_EFULL + eb), ph_efull[eb], p.error_flag, 210 + eb);
-            ph_efull[eb] ^= 1;
+            mbar_wait(bars + 8 * (BAR_EFULL + eb), (ph_efull >> eb) & 1u, p.error_flag, 210 + eb);
+            ph_efull ^= 1u << eb;
           }
           if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 0] = clock64();
           uint32_t accumulate = 0;
+          if (step_bias_chunk(s)) {                                // + bias: ones columns of the encoded tile x (lo, hi) bias rows
+            // Issued FIRST so the tensor core has work while the epilogue hands over chunk 0.  It overwrites the other
+            // accumulator buffer, last read by the epilogue two layers back: for s >= 2 the previous layer's hand-over
+            // waits already ordered that; for s == 1 it is the previous TILE's view epilogue, which signals VEMPTY.
+            if (s == 1 && it > 0) mbar_wait(bars + 8 * (BAR_VEMPTY + ((it - 1) & 1)), ((it - 1) >> 1) & 1, p.error_flag, 240);
+            const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
+            if (!mbar_try_wait(wbar, wphase)) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
+            tc_fence_after();
+            umma_bf16(d_tmem, mk_desc(desc_lo(base + OFF_E + eb * kEBytes + 2 * kBlk) + 2), mk_desc(desc_lo(base + OFF_W + stage * kStageBytes) + 2), idesc, 0u);
+            umma_commit(bars + 8 * (BAR_WEMPTY + stage));
+            if (++stage == kStages) { stage = 0; wphase ^= 1; }
+            accumulate = 1;                                      // issued first: keeps the tensor core busy while the epilogue hands over chunk 0
+          }
           for (int c = 0; c < ne + nh; ++c) {
             const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
             uint32_t a0;
@@ -437,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           }
           if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 1] = clock64();
           umma_commit(bars + 8 * (BAR_ACCFULL + ab));              // accumulator complete -> epilogue
-          if (s == 5) umma_commit(bars + 8 * (BAR_EEMPTY + eb));   // encoded tile no longer needed
+          if (s == kSteps - 1) umma_commit(bars + 8 * (BAR_EEMPTY + eb));   // encoded tile (incl. its ones columns) no longer needed
           if (nh) hphase ^= 1;
         }
       }
@@ -449,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     const int r = q * 32 + lane;                    // row of the tile
     const int et = (warp - 4) * 32 + lane;          // 0..255
     const uint32_t h_base = base + OFF_H;
-    uint32_t ph_acc[2] = {0, 0};
+    uint32_t ph_acc = 0;                            // bit ab: phase of accumulator buffer ab
     bool store_pending = false;
     EpiCtx e;
     e.h_base = h_base; e.r = r; e.tab = tab;
@@ -463,9 +497,13 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         e.s = s;
         const int ab = gstep & 1;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
-        const float* vbrow = (s == kViewStep && valid) ? p.vbias + (pt / p.vb_div) * kHalf : nullptr;
-        mbar_wait(bars + 8 * (BAR_ACCFULL + ab), ph_acc[ab], p.error_flag, 300 + ab);
-        ph_acc[ab] ^= 1;
+        const float* vbrow = nullptr;
+        if (s == kViewStep && valid) {
+          const int64_t ray = pt / p.vb_div;
+          vbrow = use_vbs ? vbs + ((it & 1) * kVbRays + (int)(ray - (tile * kTileM) / p.vb_div)) * kHalf : p.vbias + ray * kHalf;
+        }
+        mbar_wait(bars + 8 * (BAR_ACCFULL + ab), (ph_acc >> ab) & 1u, p.error_flag, 300 + ab);
+        ph_acc ^= 1u << ab;
         tc_fence_after();
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 2] = clock64();
         if (s < kViewStep) {
@@ -477,13 +515,20 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           uint32_t va[32], vb[32];
           tmem_ld32(t_lane + g * 32, va);
 #pragma unroll 1
+          const bool trc = p.timeline && blockIdx.x == 0 && it == 2 && s == 2 && et == 0;
+          long long* trk = p.timeline + 8 * kSteps * 4 + 8;
           for (int jj = 0; jj < 4; jj += 2) {       // this warp's chunks j = g, g+2, g+4, g+6; software pipelined
             const int j = g + 2 * jj;
+            if (trc && jj == 0) trk[0] = clock64();
             tmem_ld_wait();
             tmem_ld32(t_lane + (j + 2) * 32, vb);
+            if (trc && jj == 0) trk[1] = clock64();
             epi_trunk(e, va, j, p, valid, pt);
+            if (trc && jj == 0) trk[2] = clock64();
             fence_proxy_async();                     // generic-proxy writes -> visible to UMMA / bulk copy
+            if (trc && jj == 0) trk[3] = clock64();
             mbar_arrive(bars + 8 * (BAR_HREADY + j));
+            if (trc && jj == 0) trk[4] = clock64();
             tmem_ld_wait();
             if (jj + 2 < 4) tmem_ld32(t_lane + (j + 4) * 32, va);
             epi_trunk(e, vb, j + 2, p, valid, pt);
@@ -494,10 +539,15 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           if (s == 7 && g == 1) part[r].w = e.alpha;   // odd-chunk warps publish their partial sigma dot product
         } else {
           float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+          const bool trace = p.timeline && blockIdx.x == 0 && it == 2 && et == 0;
+          long long* tr = p.timeline + 8 * kSteps * 4;
+          if (trace) tr[0] = clock64();
           epi_view(tab, vbrow, t_lane, g, p, valid, pt, c0, c1, c2);
+          if (trace) tr[1] = clock64();
           tc_fence_before();
           if (g == 1) { part[r].x = c0; part[r].y = c1; part[r].z = c2; }
           named_bar_sync(2, 256);
+          if (trace) tr[2] = clock64();
           if (g == 0 && valid) {
             const float4 o1 = part[r];
             float4 o;
@@ -507,7 +557,10 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
             o.w = e.alpha + o1.w + p.balpha;
             *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
           }
+          if (trace) tr[3] = clock64();
           named_bar_sync(2, 256);                    // part[] is free again for the next tile
+          if (trace) tr[4] = clock64();
+          mbar_arrive(bars + 8 * (BAR_VEMPTY + (it & 1)));   // this tile's view-bias table may be overwritten
         }
         if (s == p.stop_step && p.want_feat) {
           named_bar_sync(1, 256);                    // all 128 rows x 8 chunks written (and fenced) before the bulk store
@@ -524,7 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   } else if (warp >= 12) {
     // ===== encoder warps: sampling data -> positional encoding -> bf16 A tile of layer 0 / skip =====
     const int r = (warp - 12) * 32 + lane;
-    uint32_t ph_eempty[2] = {0, 0};
+    uint32_t ph_eempty = 0;
     for (int it = 0; it < p.n_iters; ++it) {
       const int eb = it & 1;
       const int64_t tile = (int64_t)it * G + blockIdx.x;
@@ -552,14 +605,21 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           xrow = p.X + pt * p.kx;
         }
       }
-      mbar_wait(bars + 8 * (BAR_EEMPTY + eb), ph_eempty[eb] ^ 1, p.error_flag, 400 + eb);
-      ph_eempty[eb] ^= 1;
+      mbar_wait(bars + 8 * (BAR_EEMPTY + eb), ((ph_eempty >> eb) & 1u) ^ 1u, p.error_flag, 400 + eb);
+      mbar_wait(bars + 8 * (BAR_VEMPTY + eb), ((ph_eempty >> eb) & 1u) ^ 1u, p.error_flag, 410 + eb);
+      ph_eempty ^= 1u << eb;
+      if (use_vbs) {                               // per-ray view bias of this tile's (<= 4) rays -> shared memory
+        const int64_t ray = (tile * kTileM) / p.vb_div + (r >> 5);
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ray * p.vb_div < p.P) t = __ldg(reinterpret_cast<const float4*>(p.vbias + ray * kHalf) + (r & 31));
+        reinterpret_cast<float4*>(vbs + (eb * kVbRays + (r >> 5)) * kHalf)[r & 31] = t;
+      }
       const RowWriter rw{base + OFF_E + eb * kEBytes, r};
       if (p.mode == 1 || !valid) {
         for (int ch = 0; ch < 12; ++ch) {
           float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { const int col = ch * 8 + i; f[i] = (valid && col < p.xyz) ? __ldg(xrow + col) : 0.f; }
+          for (int i = 0; i < 8; ++i) { const int col = ch * 8 + i; f[i] = (valid && col < p.xyz) ? __ldg(xrow + col) : (col >= 94 ? 1.f : 0.f); }
           rw.store(ch, f);
         }
       } else if (p.mip) {
@@ -717,7 +777,7 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
 int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err) {
   const int skipl = skip_layer + 1;
   out->set = false;
-  if (skipl != 5 || d.xyzp != 96 || d.fx != 15) {   // return 1: configuration valid for the fp32 path only
+  if (skipl != 5 || d.xyzp != 96 || d.fx != 15 || d.xyz > 94) {   // return 1: configuration valid for the fp32 path only
     *err = "the tcgen05 path is built for skips=[4] and a 96-wide padded xyz encoding (15 frequencies)";
     return 1;
   }
@@ -741,13 +801,30 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
     if (s < kLayers) {
       const int kin = (s == 0) ? d.xyz : (s == skipl ? d.xyz + kHid : kHid);
       const float* W = hn.pts_w[s].data();
+      const float* bs = hn.pts_b[s].data();
+      auto put_bias = [&](size_t chunk_off) {      // k = 30 (column 94): lo part, k = 31 (column 95): hi part
+        for (int n = 0; n < kHid; ++n) {
+          uint16_t hi = f2bf(bs[n]);
+          uint32_t hu = (uint32_t)hi << 16; float hf; memcpy(&hf, &hu, 4);
+          uint16_t lo = f2bf(bs[n] - hf);
+          for (int k = 30; k < 32; ++k) {
+            size_t b = chunk_off + (size_t)(n >> 3) * 512 + (n & 7) * 64 + (((k >> 3) ^ ((n & 7) >> 1)) << 4) + (k & 7) * 2;
+            uint16_t v = (k == 30) ? lo : hi;
+            memcpy(&chunks[b], &v, 2);
+          }
+        }
+      };
       auto both = [&](const float* Wp, int k0, int kmax) { pack_chunk(chunks, Wp, kHid, kin, k0, kmax); };
       if (s == 0) {
         for (int c = 0; c < 3; ++c) both(W, 32 * c, d.xyz);
+        put_bias(chunks.size() - kStageBytes);
       } else if (s == skipl) {
         for (int c = 0; c < 3; ++c) both(W, 32 * c, d.xyz);
+        put_bias(chunks.size() - kStageBytes);
         for (int c = 0; c < 8; ++c) both(W + d.xyz, 32 * c, kHid);
       } else {
+        chunks.resize(chunks.size() + kStageBytes, 0);     // bias chunk (first): zero but for the two bias rows
+        put_bias(chunks.size() - kStageBytes);
         for (int c = 0; c < 8; ++c) both(W, 32 * c, kHid);
       }
     } else {

@@ -12,18 +12,25 @@ from nerfmatch_b200.engine import Engine, EngineConfig
 from nerfmatch_b200.synthetic import make_state_dict
 
 embed = sys.argv[1] if len(sys.argv) > 1 else "normal"
+from nerfmatch_b200.config import build_renderer
+from nerfmatch_b200.synthetic import K_7SCENES, make_pose
+
 sd = make_state_dict(0, embed_type=embed, sigma_gain=120.0, sigma_bias=(8.0, 8.0))
-wts = {k[len("nerf_fine."):]: torch.from_numpy(v) for k, v in sd.items() if k.startswith("nerf_fine.")}
-eng = Engine(EngineConfig(embed_type=embed, precision="bf16"), torch.device("cuda:0"))
-eng.set_weights(0, wts)
-P = 128 * 148 * 2 * 10
-x = torch.rand(P, eng.cfg.in_dim, device="cuda") * 2 - 1
+case = dict(embed=embed, nc=64, nf=128, app=False, white_bg=False, stop_layer=3, feat_comb="lin")
+ren = build_renderer(case, sd, precision="bf16", device="cuda:0")
+ren.rng = "philox"
+eng = ren.engine(torch.device("cuda:0"))
+rays, _, _ = eng.raygen(K_7SCENES, make_pose(1), 480, 640, 4)     # 19200 rays: one chunk, fine pass = last launch
 for _ in range(2):
-    eng.stage_mlp(0, x, 3)
+    ren.predict(rays, 1, 1)
 torch.cuda.synchronize()
 buf = (C.c_longlong * (8 * 9 * 4 + 32))()
 n = L.load().nmr_debug_timeline(buf, len(buf))
 t = np.array(buf[:8 * 9 * 4], dtype=np.int64).reshape(8, 9, 4)
+tr = np.array(buf[8 * 9 * 4:8 * 9 * 4 + 5], dtype=np.int64)
+print('view-step trace (it 2): epi_view, wait partials, combine+store, barrier =', np.diff(tr))
+tk = np.array(buf[8 * 9 * 4 + 8:8 * 9 * 4 + 13], dtype=np.int64)
+print('trunk chunk trace (it 2, step 2): ld wait+prefetch, math+STS, proxy fence, mbar arrive =', np.diff(tk))
 t0 = t[1:6]
 print("per step (cycles), iterations 1..5 averaged")
 print("step  mma_issue  mma_end->epi_start  epilogue  epi_end->next_mma_start   total")
