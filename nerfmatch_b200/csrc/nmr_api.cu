@@ -48,6 +48,7 @@ struct nmr_handle {
   int64_t launches = 0;
   bool timing = false;
   bool auto_chunk = true;
+  cudaStream_t copy_stream = nullptr;   // nmr_render_host: device->host copies overlap the next chunk's kernels
   std::vector<StageEvent> events;
 };
 
@@ -152,6 +153,7 @@ extern "C" int nmr_create(const nmr_config* cfg, nmr_handle** out) {
 extern "C" void nmr_destroy(nmr_handle* h) {
   if (!h) return;
   for (auto& ev : h->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[i]); }
   h->app.release(); h->X.release(); h->raw.release(); h->zc.release(); h->zf.release(); h->misc.release();
   h->rays_view.release(); h->tcws.release();
@@ -414,7 +416,14 @@ static int validate_render(nmr_handle* h, const nmr_render_args* a) {
   return NMR_OK;
 }
 
-static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s) {
+// per-ray outputs that nmr_render_host streams back chunk by chunk
+struct HostSink {
+  struct Item { char* host; const char* dev; size_t bytes_per_ray; };
+  std::vector<Item> items;
+  std::vector<cudaEvent_t> events;
+};
+
+static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s, HostSink* sink = nullptr) {
   int r = validate_render(h, a);
   if (r != NMR_OK) return r;
   if (a->n == 0) return NMR_OK;
@@ -521,6 +530,16 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
       float* rawo = pass == 0 ? a->raw_coarse : a->raw_fine;
       if (rawo) NMR_CUDA(h, cudaMemcpyAsync(rawo + r0 * S * 4, raw_pass, (size_t)nr * S * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
+    if (sink) {   // this chunk's rows go home while the next chunk renders
+      cudaEvent_t ev;
+      NMR_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      sink->events.push_back(ev);
+      NMR_CUDA(h, cudaEventRecord(ev, s));
+      NMR_CUDA(h, cudaStreamWaitEvent(h->copy_stream, ev, 0));
+      for (auto& it : sink->items)
+        NMR_CUDA(h, cudaMemcpyAsync(it.host + (size_t)r0 * it.bytes_per_ray, it.dev + (size_t)r0 * it.bytes_per_ray,
+                                    (size_t)nr * it.bytes_per_ray, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
   }
   return NMR_OK;
 }
@@ -594,8 +613,8 @@ extern "C" int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void*
   const int64_t n = args->n;
   nmr_render_args a = *args;
   int slot = 0;
-  struct Out { void* host; void* dev; size_t bytes; };
-  std::vector<Out> outs;
+  if (!h->copy_stream) NMR_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  HostSink sink;
   auto in = [&](const void* host, size_t bytes) -> void* {
     DevBuf& b = h->stage[slot++];
     if (!host || bytes == 0) return nullptr;
@@ -605,9 +624,9 @@ extern "C" int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void*
   };
   auto out = [&](void* host, size_t bytes) -> void* {
     DevBuf& b = h->stage[slot++];
-    if (!host || bytes == 0) return nullptr;
+    if (!host || bytes == 0 || n == 0) return nullptr;
     if (b.reserve(bytes) != cudaSuccess) return nullptr;
-    outs.push_back({host, b.p, bytes});
+    sink.items.push_back({(char*)host, (const char*)b.p, bytes / (size_t)n});
     return b.p;
   };
   const size_t f = sizeof(float);
@@ -633,10 +652,12 @@ extern "C" int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void*
   a.idx_fine = (int32_t*)out(args->idx_fine, (size_t)n * (d.mip ? d.sc + 1 : d.nf) * sizeof(int32_t));
   NMR_CUDA(h, cudaGetLastError());
   if (n > 0 && !a.rays) NMR_FAIL(h, NMR_ERR_CUDA, "nmr_render_host: staging allocation failed");
-  int r = render_device(h, &a, s);
+  int r = render_device(h, &a, s, &sink);
+  cudaError_t e1 = cudaStreamSynchronize(s), e2 = cudaStreamSynchronize(h->copy_stream);
+  for (auto ev : sink.events) cudaEventDestroy(ev);
   if (r != NMR_OK) return r;
-  for (auto& o : outs) NMR_CUDA(h, cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, s));
-  NMR_CUDA(h, cudaStreamSynchronize(s));
+  NMR_CUDA(h, e1);
+  NMR_CUDA(h, e2);
   return NMR_OK;
 }
 
