@@ -104,7 +104,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def config_block(embed, precision):
@@ -295,9 +295,27 @@ def run_ours(args):
         rate, cores, ns, dt = cpu_render_rate(embed, args.cpu_rays)
         line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                                 "sample": f"{ns} rays of the same {H}x{W} view, {dt:.1f} s (numpy oracle port, one thread per core)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, ...) print to fd 1; the contract is ONE JSON line on stdout.
+    Everything else goes to stderr, the JSON line to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -311,6 +329,7 @@ def main():
     ap.add_argument("--cpu-rays", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
