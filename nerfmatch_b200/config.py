@@ -6,11 +6,12 @@ from __future__ import annotations
 from argparse import Namespace as NS
 
 
-def make_config(embed="mip", nc=64, nf=128, app=False, white_bg=False, xyz_num_freqs=15, dirs_num_freqs=4):
-    emb = NS(xyz_num_freqs=xyz_num_freqs, dirs_num_freqs=dirs_num_freqs, appearance_embed=app, type=embed)
+def make_config(embed="mip", nc=64, nf=128, app=False, white_bg=False, xyz_num_freqs=15, dirs_num_freqs=4, use_disp=False,
+                mip_var_scale=-1):
+    emb = NS(xyz_num_freqs=xyz_num_freqs, dirs_num_freqs=dirs_num_freqs, appearance_embed=app, type=embed, mip_var_scale=mip_var_scale)
     return NS(
         data=NS(img_wh=[160, 120]),
-        render=NS(chunksize=16384, use_disp=False, perturb=True, noise_std=1.0, white_bg=white_bg, use_viewdirs=True),
+        render=NS(chunksize=16384, use_disp=use_disp, perturb=True, noise_std=1.0, white_bg=white_bg, use_viewdirs=True),
         embedding=emb,
         coarse_nerf=NS(method="NeRF", layer_num=8, hid_dim=256, output_dim=4, skips=[4], num_pts=nc),
         fine_nerf=NS(method="NeRF", layer_num=8, hid_dim=256, output_dim=4, skips=[4], num_pts=nf),
@@ -27,7 +28,8 @@ def build_renderer(case, state_dict, precision="bf16", device="cuda:0", num_fram
 
     from .renderer import NerfRenderer
 
-    ren = NerfRenderer(make_config(case["embed"], case["nc"], case["nf"], case["app"], case["white_bg"]),
+    ren = NerfRenderer(make_config(case["embed"], case["nc"], case["nf"], case["app"], case["white_bg"],
+                                   use_disp=case.get("use_disp", False), mip_var_scale=case.get("mip_var_scale", -1)),
                        num_frames=num_frames if case["app"] else None, training=False, stop_layer=case["stop_layer"],
                        precision=precision, **kw)
     ren.load_state_dict({k: torch.as_tensor(np.asarray(v)) for k, v in state_dict.items()}, strict=True)

@@ -182,3 +182,33 @@ def test_bf16_vs_fp32_path_same_view():
             # zero flips between "opaque at infinity" and "transparent" (observed: 4 of 1200 rays); all others are tight.
             e = ray_rel_err(res["bf16"][k], res["fp32"][k])
             assert np.median(e) < 1e-2 and (e < 5e-2).mean() > 0.98, (embed, k, np.median(e), (e < 5e-2).mean())
+
+
+@pytest.mark.parametrize("embed,nc,nf", [("normal", 48, 40), ("normal", 32, 96), ("mip", 100, 100), ("mip", 32, 32)])
+def test_bf16_unusual_sample_counts(embed, nc, nf):
+    """Sample counts that are not multiples of the 128-point tile (rays straddle tiles; below 43 samples per ray the
+    per-ray view bias is read from global memory instead of the staged shared-memory table)."""
+    c = dict(embed=embed, nc=nc, nf=nf, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+    sd = make_state_dict(45, embed_type=embed, sigma_gain=60.0, sigma_bias=(4.0, 4.0))
+    rays = T(O.sample_nerf_rays(480, 640, K_7SCENES, make_pose(3), ds=20, embed_type=embed))   # 768 rays
+    res = {}
+    for prec in ("fp32", "bf16"):
+        ren = build_renderer(c, sd, precision=prec)
+        ren.rng = "none"
+        res[prec] = {k: N(v) for k, v in ren.predict(rays, 1, 1).items()}
+    cos = cosine_rows(res["bf16"]["feat_fine"], res["fp32"]["feat_fine"])
+    assert cos.min() > 0.999, (embed, nc, nf, cos.min())
+    e = ray_rel_err(res["bf16"]["rgb_fine"], res["fp32"]["rgb_fine"])
+    assert np.median(e) < 1e-2, (embed, np.median(e))
+
+
+def test_bf16_chunking_is_invisible():
+    """Ragged ray chunks (workspace bound) must not change a bit of the bf16 result."""
+    embed = "normal"
+    c = dict(embed=embed, nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+    sd = make_state_dict(46, embed_type=embed, sigma_gain=60.0, sigma_bias=(4.0, 4.0))
+    rays = T(O.sample_nerf_rays(480, 640, K_7SCENES, make_pose(4), ds=10, embed_type=embed))   # 3072 rays
+    a = build_renderer(c, sd, precision="bf16").predict(rays, 1, 1)
+    b = build_renderer(c, sd, precision="bf16", max_chunk_points=192 * 211).predict(rays, 1, 1)   # 211-ray chunks
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
