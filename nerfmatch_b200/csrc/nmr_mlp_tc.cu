@@ -25,8 +25,8 @@
 //     the epilogue 2-3x, measured); the tapped feature tile (stop_layer) leaves as one 64 KB bulk store
 //     shared->global in the same tiled layout the compositor reads.
 //
-// Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 idle,
-// 4-7 epilogue (even chunks), 8-11 epilogue (odd chunks), 12-15 encoder.
+// Warp roles (512 threads): 0 weight producer, 1 MMA issuer (+ feature-tap bulk stores), 2 TMEM allocator, 3 idle,
+// 4-7 trunk epilogue (even chunks), 8-11 trunk epilogue (odd chunks), 12-15 encoder (one tile ahead) + views epilogue.
 #include <cstdlib>
 #include <cstring>
 
@@ -53,15 +53,17 @@ constexpr int OFF_W = OFF_E + 2 * kEBytes;
 constexpr int OFF_TAB = OFF_W + kStages * kStageBytes;        // fp32 tables: walpha [256], wrgb [3][128]
 constexpr int kTabFloats = kHid + 3 * kHalf;
 constexpr int OFF_PART = OFF_TAB + kTabFloats * 4;            // float4 per row: partial (rgb, alpha) of the odd-chunk warps
+constexpr int OFF_PARTV = OFF_PART + kTileM * 16;            // 2 x float4 per row: rgb partial sums of the two trunk-epilogue groups
 constexpr int kVbRays = 4;                                    // rays a 128-point tile can touch when S >= 43
-constexpr int OFF_VBS = OFF_PART + kTileM * 16;               // 2 x [kVbRays][128] fp32: per-ray view bias of the tile (double buffered)
+constexpr int OFF_VBS = OFF_PARTV + 2 * kTileM * 16;               // 2 x [kVbRays][128] fp32: per-ray view bias of the tile (double buffered)
 constexpr int OFF_BAR = OFF_VBS + 2 * kVbRays * kHalf * 4;
 constexpr int kSmemBytes = OFF_BAR + 256;                     // dynamic smem is 1024-aligned (checked at kernel entry)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
 enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_HREADY = BAR_ACCFULL + 2,
-       BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_VEMPTY = BAR_EEMPTY + 2, BAR_COUNT = BAR_VEMPTY + 2 };
+       BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_VEMPTY = BAR_EEMPTY + 2, BAR_VFULL = BAR_VEMPTY + 2, BAR_VPART = BAR_VFULL + 1,
+       BAR_COUNT = BAR_VPART + 1 };
 static_assert(BAR_COUNT * 8 + 8 <= 256, "barrier area");
 
 struct TcParams {
@@ -134,10 +136,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
-
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -316,44 +318,54 @@ __device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, int j, c
   }
 }
 
-// views_linears.0 epilogue: this warp's two 32-column slices (g, g+2): per-ray view bias + ReLU, rgb_linear partials.
-__device__ __forceinline__ void epi_view(const float* tab, const float* vbrow, uint32_t t_lane, int g, const TcParams& p, bool valid,
-                                         int64_t pt, float& c0, float& c1, float& c2) {
-  float4 vq[8];
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ uint64_t pk2u(uint32_t a, uint32_t b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ void upk2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// views_linears.0 epilogue (run by the encoder warps so the trunk epilogue warps can move on to the next tile):
+// four 32-column slices: per-ray view bias + ReLU, rgb_linear + sigmoid, raw [P,4] store.
+// Slices [j0, j0 + NS) of the 128 views columns; returns this warp's partial rgb dot products.
+template <int NS>
+__device__ __forceinline__ float4 epi_view(const float* tab, const float* vbrow, uint32_t t_lane, int j0, const TcParams& p, bool valid,
+                                           int64_t pt) {
+  uint64_t q0 = 0, q1 = 0, q2 = 0;                 // (even, odd) partial sums of the three rgb dot products
+  uint32_t va[32], vb[32];
+  tmem_ld32(t_lane + j0 * 32, va);
+  {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) vq[i] = vbrow ? reinterpret_cast<const float4*>(vbrow + g * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-  for (int jj = 0; jj < 2; ++jj) {
-    const int j = g + 2 * jj;
-    uint32_t v[32];
-    tmem_ld32(t_lane + j * 32, v);
-    tmem_ld_wait();
-    float x[32];
+    for (int h = 0; h < NS; ++h) {
+      uint32_t* v = h == 0 ? va : vb;
+      tmem_ld_wait();
+      if (h + 1 < NS) tmem_ld32(t_lane + (j0 + 1) * 32, vb);
+      const int jj = j0 + h;
+      float x[32];
+      const float4* w0 = reinterpret_cast<const float4*>(tab + kHid + jj * 32);
+      const float4* w1 = w0 + kHalf / 4;
+      const float4* w2 = w1 + kHalf / 4;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 t = vq[i];
-      x[4 * i] = fmaxf(__uint_as_float(v[4 * i]) + t.x, 0.f); x[4 * i + 1] = fmaxf(__uint_as_float(v[4 * i + 1]) + t.y, 0.f);
-      x[4 * i + 2] = fmaxf(__uint_as_float(v[4 * i + 2]) + t.z, 0.f); x[4 * i + 3] = fmaxf(__uint_as_float(v[4 * i + 3]) + t.w, 0.f);
-    }
-    if (jj == 0) {                                 // next slice of the view bias: L2 latency hides behind the rgb FMAs
+      for (int i = 0; i < 8; ++i) {                // packed fp32x2: bias add (FADD2), rgb dot products (FFMA2)
+        float4 t = vbrow ? reinterpret_cast<const float4*>(vbrow + jj * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        upk2(add2(pk2u(v[4 * i], v[4 * i + 1]), pk2(t.x, t.y)), x[4 * i], x[4 * i + 1]);
+        upk2(add2(pk2u(v[4 * i + 2], v[4 * i + 3]), pk2(t.z, t.w)), x[4 * i + 2], x[4 * i + 3]);
+        x[4 * i] = fmaxf(x[4 * i], 0.f); x[4 * i + 1] = fmaxf(x[4 * i + 1], 0.f);
+        x[4 * i + 2] = fmaxf(x[4 * i + 2], 0.f); x[4 * i + 3] = fmaxf(x[4 * i + 3], 0.f);
+        const uint64_t xa = pk2(x[4 * i], x[4 * i + 1]), xb = pk2(x[4 * i + 2], x[4 * i + 3]);
+        float4 a = w0[i], b = w1[i], c = w2[i];
+        q0 = fma2(xb, pk2(a.z, a.w), fma2(xa, pk2(a.x, a.y), q0));
+        q1 = fma2(xb, pk2(b.z, b.w), fma2(xa, pk2(b.x, b.y), q1));
+        q2 = fma2(xb, pk2(c.z, c.w), fma2(xa, pk2(c.x, c.y), q2));
+      }
+      if (p.debug_out && p.debug_step == kViewStep && valid) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) vq[i] = vbrow ? reinterpret_cast<const float4*>(vbrow + (g + 2) * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const float4* w0 = reinterpret_cast<const float4*>(tab + kHid + j * 32);
-    const float4* w1 = w0 + kHalf / 4;
-    const float4* w2 = w1 + kHalf / 4;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 a = w0[i], b = w1[i], c = w2[i];
-      c0 = fmaf(x[4 * i], a.x, fmaf(x[4 * i + 1], a.y, fmaf(x[4 * i + 2], a.z, fmaf(x[4 * i + 3], a.w, c0))));
-      c1 = fmaf(x[4 * i], b.x, fmaf(x[4 * i + 1], b.y, fmaf(x[4 * i + 2], b.z, fmaf(x[4 * i + 3], b.w, c1))));
-      c2 = fmaf(x[4 * i], c.x, fmaf(x[4 * i + 1], c.y, fmaf(x[4 * i + 2], c.z, fmaf(x[4 * i + 3], c.w, c2))));
-    }
-    if (p.debug_out && p.debug_step == kViewStep && valid) {
-#pragma unroll
-      for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = x[i];
+        for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + jj * 32 + i] = x[i];
+      }
     }
   }
+  float c0, c1, c2, d0, d1, d2;
+  upk2(q0, c0, d0); upk2(q1, c1, d1); upk2(q2, c2, d2);
+  return make_float4(c0 + d0, c1 + d1, c2 + d2, 0.f);
 }
 
 // ---- the kernel ----------------------------------------------------------------------------
@@ -365,6 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + BAR_COUNT * 8);
   float* tab = reinterpret_cast<float*>(gbase + OFF_TAB);
   float4* part = reinterpret_cast<float4*>(gbase + OFF_PART);
+  float4* partv = reinterpret_cast<float4*>(gbase + OFF_PARTV);
   float* vbs = reinterpret_cast<float*>(gbase + OFF_VBS);
   const bool use_vbs = p.vb_div >= 43;             // a tile then spans at most kVbRays rays
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -382,8 +395,10 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       mbar_init(bars + 8 * (BAR_ACCFULL + i), 1);
       mbar_init(bars + 8 * (BAR_EFULL + i), 128);
       mbar_init(bars + 8 * (BAR_EEMPTY + i), 1);
-      mbar_init(bars + 8 * (BAR_VEMPTY + i), 256);
+      mbar_init(bars + 8 * (BAR_VEMPTY + i), 384);
     }
+    mbar_init(bars + 8 * BAR_VFULL, 1);
+    mbar_init(bars + 8 * BAR_VPART, 256);
     for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -470,8 +485,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
             if (++stage == kStages) { stage = 0; wphase ^= 1; }
           }
           if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 1] = clock64();
-          umma_commit(bars + 8 * (BAR_ACCFULL + ab));              // accumulator complete -> epilogue
-          if (s == kSteps - 1) umma_commit(bars + 8 * (BAR_EEMPTY + eb));   // encoded tile (incl. its ones columns) no longer needed
+          if (s < kViewStep) {
+            umma_commit(bars + 8 * (BAR_ACCFULL + ab));            // accumulator complete -> trunk epilogue
+          } else {
+            umma_commit(bars + 8 * BAR_VFULL);                     // views accumulator -> view epilogue (encoder warps)
+            umma_commit(bars + 8 * (BAR_EEMPTY + eb));             // encoded tile (incl. its ones columns) no longer needed
+          }
           if (nh) hphase ^= 1;
         }
       }
@@ -484,6 +503,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     const int et = (warp - 4) * 32 + lane;          // 0..255
     const uint32_t h_base = base + OFF_H;
     uint32_t ph_acc = 0;                            // bit ab: phase of accumulator buffer ab
+    uint32_t ph_vfull = 0;
+    const bool leader = (et & 127) == 0;            // first thread of this chunk group: issues the group's feature-tap bulk stores
     bool store_pending = false;
     EpiCtx e;
     e.h_base = h_base; e.r = r; e.tab = tab;
@@ -493,92 +514,77 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
       e.alpha = 0.f;
-      for (int s = 0; s < kSteps; ++s, ++gstep) {
+      for (int s = 0; s < kViewStep; ++s, ++gstep) {
         e.s = s;
         const int ab = gstep & 1;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
-        const float* vbrow = nullptr;
-        if (s == kViewStep && valid) {
-          const int64_t ray = pt / p.vb_div;
-          vbrow = use_vbs ? vbs + ((it & 1) * kVbRays + (int)(ray - (tile * kTileM) / p.vb_div)) * kHalf : p.vbias + ray * kHalf;
-        }
         mbar_wait(bars + 8 * (BAR_ACCFULL + ab), (ph_acc >> ab) & 1u, p.error_flag, 300 + ab);
         ph_acc ^= 1u << ab;
         tc_fence_after();
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 2] = clock64();
-        if (s < kViewStep) {
-          if (store_pending) {                      // the tap store must have finished reading H
-            if (et == 0) bulk_wait_read0();
-            named_bar_sync(1, 256);
-            store_pending = false;
+        if (store_pending) {                        // this group's tap stores (a layer ago) have finished reading H
+          if (leader) bulk_wait_read0();
+          named_bar_sync(1 + g, 128);
+          store_pending = false;
+        }
+        const bool tap = (s == p.stop_step) && p.want_feat;
+        auto hand_over = [&](int j) {
+          fence_proxy_async();                       // generic-proxy writes -> visible to UMMA / bulk copy
+          if (tap) {                                 // tapped layer: the chunk also goes home as tiled bf16 features
+            named_bar_sync(1 + g, 128);
+            if (leader && tile * kTileM < p.P) {
+              bulk_s2g(p.feat_tiles + (size_t)tile * kFeatTileBytes + j * kBlk, h_base + j * kBlk, kBlk);
+              bulk_commit();
+            }
           }
-          uint32_t va[32], vb[32];
-          tmem_ld32(t_lane + g * 32, va);
+          mbar_arrive(bars + 8 * (BAR_HREADY + j));
+        };
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_lane + g * 32, va);
 #pragma unroll 1
-          const bool trc = p.timeline && blockIdx.x == 0 && it == 2 && s == 2 && et == 0;
-          long long* trk = p.timeline + 8 * kSteps * 4 + 8;
-          for (int jj = 0; jj < 4; jj += 2) {       // this warp's chunks j = g, g+2, g+4, g+6; software pipelined
-            const int j = g + 2 * jj;
-            if (trc && jj == 0) trk[0] = clock64();
-            tmem_ld_wait();
-            tmem_ld32(t_lane + (j + 2) * 32, vb);
-            if (trc && jj == 0) trk[1] = clock64();
-            epi_trunk(e, va, j, p, valid, pt);
-            if (trc && jj == 0) trk[2] = clock64();
-            fence_proxy_async();                     // generic-proxy writes -> visible to UMMA / bulk copy
-            if (trc && jj == 0) trk[3] = clock64();
-            mbar_arrive(bars + 8 * (BAR_HREADY + j));
-            if (trc && jj == 0) trk[4] = clock64();
-            tmem_ld_wait();
-            if (jj + 2 < 4) tmem_ld32(t_lane + (j + 4) * 32, va);
-            epi_trunk(e, vb, j + 2, p, valid, pt);
-            fence_proxy_async();
-            mbar_arrive(bars + 8 * (BAR_HREADY + j + 2));
-          }
-          tc_fence_before();
-          if (s == 7 && g == 1) part[r].w = e.alpha;   // odd-chunk warps publish their partial sigma dot product
-        } else {
-          float c0 = 0.f, c1 = 0.f, c2 = 0.f;
-          const bool trace = p.timeline && blockIdx.x == 0 && it == 2 && et == 0;
-          long long* tr = p.timeline + 8 * kSteps * 4;
-          if (trace) tr[0] = clock64();
-          epi_view(tab, vbrow, t_lane, g, p, valid, pt, c0, c1, c2);
-          if (trace) tr[1] = clock64();
-          tc_fence_before();
-          if (g == 1) { part[r].x = c0; part[r].y = c1; part[r].z = c2; }
-          named_bar_sync(2, 256);
-          if (trace) tr[2] = clock64();
-          if (g == 0 && valid) {
-            const float4 o1 = part[r];
-            float4 o;
-            o.x = 1.f / (1.f + __expf(-(c0 + o1.x + p.brgb0)));
-            o.y = 1.f / (1.f + __expf(-(c1 + o1.y + p.brgb1)));
-            o.z = 1.f / (1.f + __expf(-(c2 + o1.z + p.brgb2)));
-            o.w = e.alpha + o1.w + p.balpha;
-            *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
-          }
-          if (trace) tr[3] = clock64();
-          named_bar_sync(2, 256);                    // part[] is free again for the next tile
-          if (trace) tr[4] = clock64();
-          mbar_arrive(bars + 8 * (BAR_VEMPTY + (it & 1)));   // this tile's view-bias table may be overwritten
+        for (int jj = 0; jj < 4; jj += 2) {         // this warp's chunks j = g, g+2, g+4, g+6; software pipelined
+          const int j = g + 2 * jj;
+          tmem_ld_wait();
+          tmem_ld32(t_lane + (j + 2) * 32, vb);
+          epi_trunk(e, va, j, p, valid, pt);
+          hand_over(j);
+          tmem_ld_wait();
+          if (jj + 2 < 4) tmem_ld32(t_lane + (j + 4) * 32, va);
+          epi_trunk(e, vb, j + 2, p, valid, pt);
+          if (s == 7 && jj == 2) reinterpret_cast<float*>(part)[r * 4 + g] = e.alpha;   // this warp's partial sigma dot product
+          hand_over(j + 2);
         }
-        if (s == p.stop_step && p.want_feat) {
-          named_bar_sync(1, 256);                    // all 128 rows x 8 chunks written (and fenced) before the bulk store
-          if (et == 0 && tile * kTileM < p.P) {
-            bulk_s2g(p.feat_tiles + (size_t)tile * kFeatTileBytes, h_base, kFeatTileBytes);
-            bulk_commit();
-          }
-          store_pending = true;
-        }
+        if (tap) store_pending = true;
+        tc_fence_before();
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 3] = clock64();
       }
+      {  // views layer: this warp takes slice g of the 128 columns (the encoder warps take slices 2, 3 and finish the row)
+        const int ab = gstep & 1;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
+        const float* vbrow = nullptr;
+        if (valid) {
+          const int64_t ray = pt / p.vb_div;
+          vbrow = use_vbs ? vbs + ((it & 1) * kVbRays + (int)(ray - (tile * kTileM) / p.vb_div)) * kHalf : p.vbias + ray * kHalf;
+        }
+        mbar_wait(bars + 8 * BAR_VFULL, ph_vfull, p.error_flag, 430);
+        ph_vfull ^= 1;
+        tc_fence_after();
+        const float4 pv = epi_view<1>(tab, vbrow, t_lane, g, p, valid, pt);
+        tc_fence_before();
+        partv[g * kTileM + r] = pv;
+        mbar_arrive(bars + 8 * BAR_VPART);
+        mbar_arrive(bars + 8 * (BAR_VEMPTY + (it & 1)));
+      }
+      ++gstep;
     }
-    if (et == 0) bulk_wait0();
+    if (leader) bulk_wait0();
   } else if (warp >= 12) {
-    // ===== encoder warps: sampling data -> positional encoding -> bf16 A tile of layer 0 / skip =====
-    const int r = (warp - 12) * 32 + lane;
-    uint32_t ph_eempty = 0;
-    for (int it = 0; it < p.n_iters; ++it) {
+    // ===== encoder warps: (1) sampling data -> positional encoding -> bf16 A tile of layer 0 / skip, one tile ahead;
+    //                      (2) the views-layer epilogue of the current tile (rgb + sigma -> raw) =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    uint32_t ph_eempty = 0, ph_vfull = 0, ph_vpart = 0;
+    auto encode_tile = [&](int it) {
       const int eb = it & 1;
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
@@ -606,10 +612,9 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         }
       }
       mbar_wait(bars + 8 * (BAR_EEMPTY + eb), ((ph_eempty >> eb) & 1u) ^ 1u, p.error_flag, 400 + eb);
-      mbar_wait(bars + 8 * (BAR_VEMPTY + eb), ((ph_eempty >> eb) & 1u) ^ 1u, p.error_flag, 410 + eb);
       ph_eempty ^= 1u << eb;
       if (use_vbs) {                               // per-ray view bias of this tile's (<= 4) rays -> shared memory
-        const int64_t ray = (tile * kTileM) / p.vb_div + (r >> 5);
+        const int64_t ray = (tile * kTileM) / p.vb_div + (r >> 5);   // (this buffer's last reader was our own view epilogue)
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ray * p.vb_div < p.P) t = __ldg(reinterpret_cast<const float4*>(p.vbias + ray * kHalf) + (r & 31));
         reinterpret_cast<float4*>(vbs + (eb * kVbRays + (r >> 5)) * kHalf)[r & 31] = t;
@@ -629,6 +634,41 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       }
       fence_proxy_async();
       mbar_arrive(bars + 8 * (BAR_EFULL + eb));
+    };
+    encode_tile(0);
+    for (int it = 0; it < p.n_iters; ++it) {
+      if (it + 1 < p.n_iters) encode_tile(it + 1);
+      // ---- views-layer epilogue of tile `it` ----
+      const int64_t tile = (int64_t)it * G + blockIdx.x;
+      const int64_t pt = tile * kTileM + r;
+      const bool valid = pt < p.P;
+      const int ab = (it * kSteps + kViewStep) & 1;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
+      const float* vbrow = nullptr;
+      if (valid) {
+        const int64_t ray = pt / p.vb_div;
+        vbrow = use_vbs ? vbs + ((it & 1) * kVbRays + (int)(ray - (tile * kTileM) / p.vb_div)) * kHalf : p.vbias + ray * kHalf;
+      }
+      mbar_wait(bars + 8 * BAR_VFULL, ph_vfull, p.error_flag, 420);
+      ph_vfull ^= 1;
+      tc_fence_after();
+      if (p.timeline && blockIdx.x == 0 && it < 8 && r == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 2] = clock64();
+      float4 pv = epi_view<2>(tab, vbrow, t_lane, 2, p, valid, pt);
+      tc_fence_before();
+      mbar_wait(bars + 8 * BAR_VPART, ph_vpart, p.error_flag, 440);      // the trunk warps' partial sums are in shared memory
+      ph_vpart ^= 1;
+      if (valid) {
+        const float4 p0 = partv[r], p1 = partv[kTileM + r];
+        const float2 pa = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(part) + r * 4);
+        float4 o;
+        o.x = 1.f / (1.f + __expf(-(pv.x + p0.x + p1.x + p.brgb0)));
+        o.y = 1.f / (1.f + __expf(-(pv.y + p0.y + p1.y + p.brgb1)));
+        o.z = 1.f / (1.f + __expf(-(pv.z + p0.z + p1.z + p.brgb2)));
+        o.w = pa.x + pa.y + p.balpha;
+        *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+      }
+      if (p.timeline && blockIdx.x == 0 && it < 8 && r == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 3] = clock64();
+      mbar_arrive(bars + 8 * (BAR_VEMPTY + (it & 1)));   // views accumulator drained (MMA of the next tile's layer 1 may overwrite it)
     }
   }
 
