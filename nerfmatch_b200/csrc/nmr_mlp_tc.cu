@@ -8,10 +8,12 @@
 //   * activations never leave the SM: the epilogue warps read the accumulator with tcgen05.ld, add
 //     bias, apply ReLU, round to bf16 and write the next layer's A operand in place, in the UMMA
 //     K-major 64B-swizzled layout.  The skip connection is a second K segment into the same
-//     accumulator; sigma (alpha_linear) and rgb (rgb_linear + sigmoid) are fp32 dot products in the
-//     epilogues of the layers that feed them; the [dirs | appearance] part of views_linears is a
-//     per-ray fp32 bias computed once per ray; feature_linear (no activation) is folded into
-//     views_linears on the host (W_view_f * W_feat), which removes one layer and 11 % of the weights;
+//     accumulator; feature_linear (no activation) is folded into views_linears on the host
+//     (W_view_f * W_feat: one layer and 11 % of the weights disappear); the sigma head (alpha_linear) rides in
+//     that GEMM as two extra output rows (bf16 hi / lo split of its weights, fp32 accumulation); rgb
+//     (rgb_linear + sigmoid) is an fp32 dot product in the views epilogue; the [dirs | appearance] part of
+//     views_linears is a per-ray fp32 bias computed once per ray; trunk biases ride in the GEMM as well
+//     (ones columns of the encoded tile x bf16 hi / lo bias rows);
 //   * the accumulator is double buffered in TMEM (2 x 256 columns, alternating by layer) and the epilogue
 //     hands the next layer's operand over in 32-column chunks (one mbarrier per chunk), so the tensor core
 //     starts layer l+1 on chunk 0 while the epilogue is still draining layer l.  Eight epilogue warps
@@ -50,8 +52,8 @@ constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128
 constexpr int OFF_H = 0;
 constexpr int OFF_E = kHBytes;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
-constexpr int OFF_TAB = OFF_W + kStages * kStageBytes;        // fp32 tables: walpha [256], wrgb [3][128]
-constexpr int kTabFloats = kHid + 3 * kHalf;
+constexpr int OFF_TAB = OFF_W + kStages * kStageBytes;        // fp32 table: wrgb [3][128]
+constexpr int kTabFloats = 3 * kHalf;
 constexpr int OFF_PART = OFF_TAB + kTabFloats * 4;            // float4 per row: partial (rgb, alpha) of the odd-chunk warps
 constexpr int OFF_PARTV = OFF_PART + kTileM * 16;            // 2 x float4 per row: rgb partial sums of the two trunk-epilogue groups
 constexpr int kVbRays = 4;                                    // rays a 128-point tile can touch when S >= 43
@@ -90,7 +92,8 @@ __host__ __device__ constexpr int step_chunks_h(int s) { return s == 0 ? 0 : 8; 
 // bf16 (lo, hi) split of the bias.  Layers fed by the encoded tile (0, 5) get it for free; the H-fed trunk layers
 // append one K=16 MMA on a "bias chunk" (A = encoded columns 80..95, all other weight rows zero).
 __host__ __device__ constexpr int step_bias_chunk(int s) { return (s >= 1 && s <= 7 && s != 5) ? 1 : 0; }
-__host__ __device__ constexpr int step_chunk_bytes(int s) { return s == kViewStep ? 8192 : 16384; }
+constexpr int kViewN = 144;   // 128 views outputs + sigma head (alpha_linear weights as bf16 hi/lo rows) + padding to a multiple of 16
+__host__ __device__ constexpr int step_chunk_bytes(int s) { return s == kViewStep ? kViewN * 64 : 16384; }
 __host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the weight stream
   int64_t off = 0;
   for (int i = 0; i < s; ++i) off += (int64_t)(step_chunks_e(i) + step_chunks_h(i) + step_bias_chunk(i)) * step_chunk_bytes(i);
@@ -294,18 +297,10 @@ __device__ __forceinline__ void epi_trunk_fast(const EpiCtx& e, const uint32_t* 
 }
 
 __device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, bool valid, int64_t pt) {
-  if (e.s != 7 && p.debug_out == nullptr) { epi_trunk_fast(e, v, j); return; }
+  if (p.debug_out == nullptr) { epi_trunk_fast(e, v, j); return; }
   float x[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) x[i] = fmaxf(__uint_as_float(v[i]), 0.f);
-  if (e.s == 7) {                                  // alpha_linear on the un-rounded fp32 activations
-    const float4* wp = reinterpret_cast<const float4*>(e.tab + j * 32);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 w = wp[i];
-      e.alpha = fmaf(x[4 * i], w.x, fmaf(x[4 * i + 1], w.y, fmaf(x[4 * i + 2], w.z, fmaf(x[4 * i + 3], w.w, e.alpha))));
-    }
-  }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t w0 = pack_bf16(x[8 * c], x[8 * c + 1]), w1 = pack_bf16(x[8 * c + 2], x[8 * c + 3]);
@@ -341,7 +336,7 @@ __device__ __forceinline__ float4 epi_view(const float* tab, const float* vbrow,
       if (h + 1 < NS) tmem_ld32(t_lane + (j0 + 1) * 32, vb);
       const int jj = j0 + h;
       float x[32];
-      const float4* w0 = reinterpret_cast<const float4*>(tab + kHid + jj * 32);
+      const float4* w0 = reinterpret_cast<const float4*>(tab + jj * 32);
       const float4* w1 = w0 + kHalf / 4;
       const float4* w2 = w1 + kHalf / 4;
 #pragma unroll
@@ -376,7 +371,6 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   const uint32_t bars = base + OFF_BAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + BAR_COUNT * 8);
   float* tab = reinterpret_cast<float*>(gbase + OFF_TAB);
-  float4* part = reinterpret_cast<float4*>(gbase + OFF_PART);
   float4* partv = reinterpret_cast<float4*>(gbase + OFF_PARTV);
   float* vbs = reinterpret_cast<float*>(gbase + OFF_VBS);
   const bool use_vbs = p.vb_div >= 43;             // a tile then spans at most kVbRays rays
@@ -386,8 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     if (threadIdx.x == 0) { atomicExch(p.error_flag, 900); __threadfence_system(); }
     __trap();
   }
-  for (int i = threadIdx.x; i < kHid; i += kThreads) tab[i] = p.walpha[i];
-  for (int i = threadIdx.x; i < 3 * kHalf; i += kThreads) tab[kHid + i] = p.wrgb[i];
+  for (int i = threadIdx.x; i < 3 * kHalf; i += kThreads) tab[i] = p.wrgb[i];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); }
@@ -440,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         const int eb = it & 1;
         for (int s = 0; s < kSteps; ++s, ++gstep) {
           const int ne = step_chunks_e(s), nh = step_chunks_h(s);
-          const uint32_t idesc = umma_idesc((s == kViewStep) ? 128 : 256);
+          const uint32_t idesc = umma_idesc((s == kViewStep) ? kViewN : 256);
           const int ab = gstep & 1;
           const uint32_t d_tmem = tmem_base + ab * 256;            // accumulator ping-pong by layer
           if (s == 0) {
@@ -551,7 +544,6 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           tmem_ld_wait();
           if (jj + 2 < 4) tmem_ld32(t_lane + (j + 4) * 32, va);
           epi_trunk(e, vb, j + 2, p, valid, pt);
-          if (s == 7 && jj == 2) reinterpret_cast<float*>(part)[r * 4 + g] = e.alpha;   // this warp's partial sigma dot product
           hand_over(j + 2);
         }
         if (tap) store_pending = true;
@@ -654,17 +646,23 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       tc_fence_after();
       if (p.timeline && blockIdx.x == 0 && it < 8 && r == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 2] = clock64();
       float4 pv = epi_view<2>(tab, vbrow, t_lane, 2, p, valid, pt);
+      float sig_hi, sig_lo;
+      {
+        uint32_t a0, a1;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(t_lane + kHalf) : "memory");
+        tmem_ld_wait();
+        sig_hi = __uint_as_float(a0); sig_lo = __uint_as_float(a1);
+      }
       tc_fence_before();
       mbar_wait(bars + 8 * BAR_VPART, ph_vpart, p.error_flag, 440);      // the trunk warps' partial sums are in shared memory
       ph_vpart ^= 1;
       if (valid) {
         const float4 p0 = partv[r], p1 = partv[kTileM + r];
-        const float2 pa = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(part) + r * 4);
         float4 o;
         o.x = 1.f / (1.f + __expf(-(pv.x + p0.x + p1.x + p.brgb0)));
         o.y = 1.f / (1.f + __expf(-(pv.y + p0.y + p1.y + p.brgb1)));
         o.z = 1.f / (1.f + __expf(-(pv.z + p0.z + p1.z + p.brgb2)));
-        o.w = pa.x + pa.y + p.balpha;
+        o.w = sig_hi + sig_lo + p.balpha;          // sigma = h7 . (w_hi + w_lo), accumulated in fp32 by the tensor core
         *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
       }
       if (p.timeline && blockIdx.x == 0 && it < 8 && r == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 3] = clock64();
@@ -868,7 +866,15 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
         for (int c = 0; c < 8; ++c) both(W, 32 * c, kHid);
       }
     } else {
-      for (int c = 0; c < 8; ++c) pack_chunk(chunks, wfold.data(), kHalf, kHid, 32 * c, kHid);
+      // views_linears.0 (folded) rows 0..127, then the sigma head: alpha_linear weights split into bf16 hi / lo rows
+      std::vector<float> wv((size_t)kViewN * kHid, 0.f);
+      memcpy(wv.data(), wfold.data(), wfold.size() * sizeof(float));
+      for (int i = 0; i < kHid; ++i) {
+        uint32_t hu = (uint32_t)f2bf(hn.alpha_w[i]) << 16; float hf; memcpy(&hf, &hu, 4);
+        wv[(size_t)kHalf * kHid + i] = hf;
+        wv[(size_t)(kHalf + 1) * kHid + i] = hn.alpha_w[i] - hf;
+      }
+      for (int c = 0; c < 8; ++c) pack_chunk(chunks, wv.data(), kViewN, kHid, 32 * c, kHid);
     }
   }
   if ((int64_t)chunks.size() != step_offset(kSteps)) { *err = "internal: chunk stream size mismatch"; return -1; }

@@ -45,7 +45,9 @@ def emulate_steps(wts, x, cfg):
         act = np.maximum(pre + wts[f"pts_linears.{i}.bias"], 0).astype(np.float32)
         outs.append(act)
         h = bf16(act)
-    alpha = outs[7] @ wts["alpha_linear.weight"].T + wts["alpha_linear.bias"]
+    wa = wts["alpha_linear.weight"]                      # sigma head rides in the views GEMM: bf16 h7 x (bf16 hi + bf16 lo) weights
+    wa_hi = bf16(wa)
+    alpha = h @ (wa_hi + bf16(wa - wa_hi)).T + wts["alpha_linear.bias"]
     # feature_linear (no activation) is folded into views_linears.0 on the host, in double precision
     wv = wts["views_linears.0.weight"].astype(np.float64)
     wfold = (wv[:, :256] @ wts["feature_linear.weight"].astype(np.float64)).astype(np.float32)
