@@ -189,6 +189,17 @@ NMR_API int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z,
                         float* depth, float* acc, float* disp, float* weights, float* feat_out,
                         float* pts_out, void* stream);
 
+/* ---- next row: NeRFMatch-Mini coarse matching on the rendered features, batch size 1 ------------
+ * NeRFMatcherCoarse.coarse_matching (nerfmatch_coarse_trainer.py:223-234) + extract_mutual_matches
+ * (modules/extract_matches.py:13-40, inference branch).  im_feat [m,d], pt_feat [n,d]: device fp32, d <= 512;
+ * im_mask [m] / pt_mask [n]: optional device uint8 (1 = valid); temp_div: 0 -> sim * temperature ("mul"),
+ * 1 -> sim / temperature ("div").  Outputs (device): conf [m,n] (optional), i_ids / j_ids [m] int64 and
+ * mconf [m] fp32 (first *count entries valid, increasing i like torch.where), count: int32[1]. */
+NMR_API int nmr_coarse_match(nmr_handle* h, const float* im_feat, int32_t m, const float* pt_feat, int32_t n, int32_t d,
+                             const uint8_t* im_mask, const uint8_t* pt_mask, float temperature, int32_t temp_div,
+                             int32_t mutual, float threshold, float* conf, int64_t* i_ids, int64_t* j_ids,
+                             float* mconf, int32_t* count, void* stream);
+
 /* Test hooks for the tcgen05 path (NMR_PREC_BF16 only).  nmr_stage_mlp_probe evaluates the net on
  * x [P, xyz+dirs+app] and returns the post-activation output of MLP step `step` as fp32 [P,256]:
  * steps 0..7 = pts_linears.0..7 (+ReLU), 8 = views_linears.0 with feature_linear folded in (+ReLU,

@@ -42,7 +42,7 @@ struct nmr_handle {
   int num_frames = 0;
   // workspace (per ray chunk)
   int64_t ws_points = 0, ws_rays = 0;
-  DevBuf X, B[4], raw, zc, zf, misc, rays_view, tcws;
+  DevBuf X, B[4], raw, zc, zf, misc, rays_view, tcws, match;
   DevBuf stage[24];     // nmr_render_host staging
   std::string err;
   int64_t launches = 0;
@@ -156,7 +156,7 @@ extern "C" void nmr_destroy(nmr_handle* h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[i]); }
   h->app.release(); h->X.release(); h->raw.release(); h->zc.release(); h->zf.release(); h->misc.release();
-  h->rays_view.release(); h->tcws.release();
+  h->rays_view.release(); h->tcws.release(); h->match.release();
   for (auto& b : h->B) b.release();
   for (auto& b : h->stage) b.release();
   delete h;
@@ -756,6 +756,45 @@ extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P
       if (feat) NMR_CUDA(h, cudaMemcpyAsync(feat + p0 * kHid, tap, (size_t)np * kHid * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
   }
+  return NMR_OK;
+}
+
+extern "C" int nmr_coarse_match(nmr_handle* h, const float* im_feat, int32_t m, const float* pt_feat, int32_t n, int32_t d,
+                                const uint8_t* im_mask, const uint8_t* pt_mask, float temperature, int32_t temp_div,
+                                int32_t mutual, float threshold, float* conf, int64_t* i_ids, int64_t* j_ids,
+                                float* mconf, int32_t* count, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!im_feat || !pt_feat || !i_ids || !j_ids || !mconf || !count) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_coarse_match: null argument");
+  if (m <= 0 || n <= 0 || d <= 0 || d > 512) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_coarse_match: need m, n > 0 and 0 < d <= 512");
+  if (temperature == 0.f) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_coarse_match: temperature == 0");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int dp = round_up(d, 16), R = 32;
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t o_im = 0, o_pt = o_im + al((size_t)m * dp * 4), o_sim = o_pt + al((size_t)n * dp * 4),
+               o_r = o_sim + al((size_t)m * n * 4), o_c = o_r + al((size_t)m * 4) * 6, o_cp = o_c + al((size_t)n * 4) * 3,
+               total = o_cp + al((size_t)R * n * 4) * 3;
+  NMR_CUDA(h, h->match.reserve(total));
+  char* b = (char*)h->match.p;
+  float* imn = (float*)(b + o_im); float* ptn = (float*)(b + o_pt); float* sim = (float*)(b + o_sim);
+  launch_normalize_rows(im_feat, m, d, dp, imn, s);
+  launch_normalize_rows(pt_feat, n, d, dp, ptn, s);
+  NMR_LAUNCHED(h, "normalize_rows", 2);
+  GemmParams g{};
+  g.A1 = imn; g.lda1 = dp; g.W1 = ptn; g.K1 = dp; g.C = sim; g.ldc = n; g.M = m; g.N = n; g.act = 0;
+  launch_sgemm(g, s);
+  NMR_LAUNCHED(h, "similarity gemm");
+  MatchParams p{};
+  p.sim = sim; p.m = m; p.n = n; p.im_mask = im_mask; p.pt_mask = pt_mask; p.temperature = temperature; p.temp_div = temp_div;
+  const size_t rs = al((size_t)m * 4), cs = al((size_t)n * 4), ps = al((size_t)R * n * 4);
+  p.rmax = (float*)(b + o_r); p.rsum = (float*)(b + o_r + rs); p.rcmax = (float*)(b + o_r + 2 * rs);
+  p.flag = (int*)(b + o_r + 3 * rs); p.jsel = (int*)(b + o_r + 4 * rs); p.csel = (float*)(b + o_r + 5 * rs);
+  p.cmax = (float*)(b + o_c); p.csum = (float*)(b + o_c + cs); p.ccmax = (float*)(b + o_c + 2 * cs);
+  p.cpmax = (float*)(b + o_cp); p.cpsum = (float*)(b + o_cp + ps); p.ccpmax = (float*)(b + o_cp + 2 * ps);
+  p.conf = conf; p.R = R; p.mutual = mutual; p.threshold = threshold;
+  p.i_ids = i_ids; p.j_ids = j_ids; p.mconf = mconf; p.count = count;
+  const int nl = launch_match_passes(p, s);
+  NMR_LAUNCHED(h, "coarse match passes", nl);
   return NMR_OK;
 }
 

@@ -110,6 +110,25 @@ struct GemmParams {        // C = act(A1*W1^T + A2*W2^T + bias)
 };
 void launch_sgemm(const GemmParams& p, cudaStream_t s);
 
+// coarse matching (nmr_match.cu)
+struct MatchParams {
+  const float* sim; int m, n;
+  const uint8_t* im_mask; const uint8_t* pt_mask;
+  float temperature; int temp_div;
+  float* rmax; float* rsum;          // [m] softmax over n (dim=2)
+  float* cpmax; float* cpsum;        // [R][n] partial softmax stats over m (dim=1)
+  float* cmax; float* csum;          // [n]
+  float* conf;                       // [m,n] or null
+  float* rcmax; float* ccpmax; float* ccmax;   // max of conf per row [m], partial per column [R][n], per column [n]
+  int R;
+  int mutual; float threshold;
+  int* flag; int* jsel; float* csel; // per row
+  int64_t* i_ids; int64_t* j_ids; float* mconf; int* count;
+};
+
+void launch_normalize_rows(const float* x, int rows, int d, int dp, float* out, cudaStream_t s);
+int launch_match_passes(const MatchParams& p, cudaStream_t s);
+
 // Philox4x32-10 -> uniform [0,1) with 24 random bits (same granularity as torch.rand fp32)
 __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
   uint64_t p = (uint64_t)a * b;

@@ -300,18 +300,83 @@ def stage_cases(r):
     return out
 
 
+def match_cases():
+    """Reference coarse matching: NeRFMatcherCoarse.coarse_matching called unbound on a namespace that carries the two
+    attributes __init__ would set (nerfmatch_coarse_trainer.py:69-83), then the reference's extract_mutual_matches.
+    Heavy off-path imports (lightning, timm, kornia, ...) are stubbed."""
+    import importlib
+    from types import SimpleNamespace
+
+    import torch
+
+    from oracle.weights import uniform01
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            m = _Any(self.__name__ + "." + name)
+            setattr(self, name, m)
+            return m
+
+        def __call__(self, *a, **k):
+            return self
+
+    for m in ("pytorch_lightning", "pytorch_lightning.callbacks", "pytorch_lightning.loggers", "pytorch_lightning.strategies",
+              "timm", "kornia", "kornia.geometry", "kornia.geometry.subpix", "kornia.utils", "kornia.utils.grid", "transforms3d",
+              "transforms3d.quaternions"):
+        if m not in sys.modules:
+            try:
+                importlib.import_module(m)
+            except Exception:
+                sys.modules[m] = _Any(m)
+    sys.modules["pytorch_lightning"].LightningModule = torch.nn.Module
+    import nerfmatch.nerfmatch_coarse_trainer as ct
+    from nerfmatch.modules.extract_matches import extract_mutual_matches
+
+    out = {}
+    m, n, d = 300, 350, 256
+    pt = (uniform01(8, 1, n * d).reshape(n, d) - 0.5).astype(np.float32)
+    perm = (uniform01(8, 2, m) * n).astype(np.int64)
+    im = (pt[perm] + 0.35 * (uniform01(8, 3, m * d).reshape(m, d) - 0.5)).astype(np.float32)    # noisy copies -> real matches
+    im_mask = uniform01(8, 4, m) > 0.1
+    pt_mask = uniform01(8, 5, n) > 0.1
+    out["im"], out["pt"], out["im_mask"], out["pt_mask"] = im, pt, im_mask, pt_mask
+    for tag, temp, ttype, masks in (("mul10", 10.0, "mul", False), ("div01_masked", 0.1, "div", True)):
+        t = torch.tensor(temp)
+        fake = SimpleNamespace(
+            norm_feat=lambda feat: (feat / (feat.norm(dim=-1, keepdim=True) + 1e-6)),
+            apply_temperature=(lambda s: s / t) if ttype == "div" else (lambda s: s * t),
+        )
+        conf, _, _ = ct.NeRFMatcherCoarse.coarse_matching(
+            fake, torch.from_numpy(im)[None], torch.from_numpy(pt)[None],
+            im_mask=torch.from_numpy(im_mask)[None] if masks else None, pt_mask=torch.from_numpy(pt_mask)[None] if masks else None)
+        out[f"{tag}.conf"] = conf[0].numpy()
+        for mutual in (False, True):
+            for thr in (0.0, 0.2):
+                (b_ids, i_ids, j_ids), mconf, num = extract_mutual_matches(conf, mutual=mutual, threshold=thr)
+                k = f"{tag}.{'mutual' if mutual else 'rowmax'}.thr{thr}"
+                out[k + ".i"], out[k + ".j"], out[k + ".mconf"] = i_ids.numpy(), j_ids.numpy(), mconf.numpy()
+    return out
+
+
 def main():
     r = import_reference()
     gdir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
+    only = sys.argv[1:]
     for name, c in CASES.items():
+        if only:
+            continue
         out = run_case(r, name, c)
         path = os.path.join(gdir, f"render_{name}.npz")
         np.savez_compressed(path, **out)
         print(name, "n =", out["rays"].shape[0], "->", path, os.path.getsize(path) // 1024, "KiB",
               "acc_c %.3f acc_f %.3f" % (out["weights_coarse"].sum(-1).mean(), out["weights_fine"].sum(-1).mean()),
               "wmax_f %.3f" % out["weights_fine"].max(-1).mean(), str(out["case"]))
-    for fname, fn in (("raygen.npz", raygen_cases), ("stages.npz", stage_cases)):
+    for fname, fn in (("raygen.npz", raygen_cases), ("stages.npz", stage_cases), ("match.npz", lambda _r: match_cases())):
+        if only and fname not in only:
+            continue
         out = fn(r)
         path = os.path.join(gdir, fname)
         np.savez_compressed(path, **out)

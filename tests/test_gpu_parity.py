@@ -372,3 +372,27 @@ def test_options_use_disp_and_var_scale_fp32():
             # and amplify fp32 round-off of sigma; the bulk meets 1e-3, everything 1e-2
             e = ray_rel_err(out[f"{q}_fine"], ref[f"{q}_fine"])
             assert (e < 1e-3).mean() > 0.8 and (e < 1e-2).mean() > 0.98 and np.median(e) < 2e-4, (embed, q, (e < 1e-3).mean(), np.median(e))
+
+
+def test_cache_writer_matches_render_novel_view(tmp_path):
+    """the batched cache writer produces the reference's per-frame .npy dicts, identical to what
+    render_novel_view returns for the same pose."""
+    from nerfmatch_b200.cache import cache_scene_pts, load_frame_3d
+
+    c = dict(embed="normal", nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+    sd = make_state_dict(71, embed_type="normal", sigma_gain=120.0, sigma_bias=(8.0, 8.0))
+    ren = build_renderer(c, sd, precision="fp32")
+    un = make_unnorm_scene()
+    frames = [dict(img_idx=f"seq-01_frame-{i:06d}", K=K_7SCENES, c2w=un @ make_pose(20 + i)) for i in range(5)]
+    paths = cache_scene_pts(ren, frames, str(tmp_path / "ds8lin"), (480, 640), un, downsample=8, views_per_batch=2)
+    assert len(paths) == 5
+    for f, p in zip(frames, sorted(paths)):
+        item = np.load(p, allow_pickle=True).item()
+        assert set(item) == {"pt3d", "unnorm_scene", "pt_feat", "pt_color"}
+        assert item["pt3d"].shape == (4800, 3) and item["pt_feat"].shape == (4800, 256) and item["pt_color"].shape == (4800, 3)
+        assert item["pt_feat"].dtype == np.float32 and item["pt_color"].min() >= 0 and item["pt_color"].max() <= 1
+        view = ren.render_novel_view((480, 640), torch.from_numpy(K_7SCENES), torch.from_numpy(f["c2w"]), un, DEV, downsample=8)
+        np.testing.assert_array_equal(item["pt_feat"], N(view["pt_feat"]))
+        np.testing.assert_array_equal(item["pt3d"], N(view["pt3d"]))
+        pt3d, pt_feat, mask, un_r = load_frame_3d(p)
+        assert mask.all() and np.array_equal(un_r, un)
