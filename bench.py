@@ -270,6 +270,7 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    tr = ncu_traffic("r01_ncu_mlp_tc.txt")
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -279,7 +280,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "NeRF MLP (coarse + fine nets)", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tf_sust"], "traffic": None, "peak_source": pk["src"] + " sustained bf16 (MEASURED_PEAKS.json)",
+                     "frac": achieved / pk["tf_sust"], "traffic": tr["bytes"], "traffic_note": tr["note"], "peak_source": pk["src"] + " sustained bf16 (MEASURED_PEAKS.json)",
                      "flops_per_launch_set": flops_step, "ms_per_step": mlp_s * 1e3},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
     }
@@ -298,6 +299,27 @@ def run_ours(args):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the launch captured with `ncu --set full` (profiles/<name>,
+    written by scripts/ncu_summary.py from the .ncu-rep of scripts/gpu_evidence.sh).  Not measured in this run."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", name)
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot, found = 0.0, 0
+    try:
+        for ln in open(path):
+            for key in ("dram__bytes_read.sum [", "dram__bytes_write.sum ["):
+                if ln.startswith(key) and found < 2:
+                    unit = ln[len(key):ln.index("]")]
+                    tot += float(ln.split("=")[1]) * scale[unit]
+                    found += 1
+    except OSError:
+        return {"bytes": None, "note": "no ncu capture in profiles/"}
+    if found < 2:
+        return {"bytes": None, "note": "no ncu capture in profiles/"}
+    return {"bytes": tot, "note": "DRAM read+write of ONE fine-pass launch (4,194,304 sample rows) from profiles/" + name +
+            "; algorithmic bytes of that launch: 512 B bf16 tap features + 16 B raw per row = 2.21 GB, inputs (rays, z, 1.2 MB of weights) < 0.02 GB"}
 
 
 _REAL_STDOUT = None
