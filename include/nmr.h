@@ -211,8 +211,9 @@ NMR_API int nmr_debug_trap_code(void);
 /* With NMR_TC_TIMELINE=1 in the environment the tcgen05 kernel's CTA 0 records clock64 stamps for its first
  * 8 iterations: [iteration][step][4] = {MMA issue start, MMA issue end, epilogue start, epilogue end}. */
 NMR_API int nmr_debug_timeline(long long* host, int n);
-/* Tuning knob of the tcgen05 path (process-wide): size of the thread-block cluster that shares each weight
- * chunk through TMA multicast - 1 (off), 2 or 4.  Default 2, or the NMR_TC_CLUSTER environment variable. */
+/* Tuning knob of the tcgen05 path (process-wide): 1 = every CTA issues its own MMAs, 2 = CTA pairs share every MMA
+ * (tcgen05 cta_group::2: each SM streams only half of every weight chunk).  Default 1, or the NMR_TC_CG environment
+ * variable; NMR_ERR_INVALID for other values or when the device cannot co-schedule pairs. */
 NMR_API int nmr_set_tc_cluster(int cluster_size);
 
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */

@@ -43,30 +43,32 @@ constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64
 constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
 constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
 constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
-constexpr int kStages = 6;
+constexpr int kRingBytes = 6 * kStageBytes;
+constexpr int kMaxStages = 12;             // CTA pair (cta_group::2): 12 stages of half chunks; single CTA: 6 full chunks
 constexpr int kSteps = 9;                  // 8 trunk layers + (feature_linear folded into) views_linears.0
 constexpr int kViewStep = 8;
 constexpr int kThreads = 512;
+constexpr int kTlSlots = 8 * kSteps * 4 + 64;   // clock64 trace: [it][step][4] + per-step wait breakdown of iteration 2
 constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128 points
 
 constexpr int OFF_H = 0;
 constexpr int OFF_E = kHBytes;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
-constexpr int OFF_TAB = OFF_W + kStages * kStageBytes;        // fp32 table: wrgb [3][128]
+constexpr int OFF_TAB = OFF_W + kRingBytes;        // fp32 table: wrgb [3][128]
 constexpr int kTabFloats = 3 * kHalf;
 constexpr int OFF_PART = OFF_TAB + kTabFloats * 4;            // float4 per row: partial (rgb, alpha) of the odd-chunk warps
 constexpr int OFF_PARTV = OFF_PART + kTileM * 16;            // 2 x float4 per row: rgb partial sums of the two trunk-epilogue groups
 constexpr int kVbRays = 4;                                    // rays a 128-point tile can touch when S >= 43
 constexpr int OFF_VBS = OFF_PARTV + 2 * kTileM * 16;               // 2 x [kVbRays][128] fp32: per-ray view bias of the tile (double buffered)
 constexpr int OFF_BAR = OFF_VBS + 2 * kVbRays * kHalf * 4;
-constexpr int kSmemBytes = OFF_BAR + 256;                     // dynamic smem is 1024-aligned (checked at kernel entry)
+constexpr int kSmemBytes = OFF_BAR + 512;                     // dynamic smem is 1024-aligned (checked at kernel entry)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
-enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kStages, BAR_ACCFULL = BAR_WEMPTY + kStages, BAR_HREADY = BAR_ACCFULL + 2,
-       BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_VEMPTY = BAR_EEMPTY + 2, BAR_VFULL = BAR_VEMPTY + 2, BAR_VPART = BAR_VFULL + 1,
-       BAR_COUNT = BAR_VPART + 1 };
-static_assert(BAR_COUNT * 8 + 8 <= 256, "barrier area");
+enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kMaxStages, BAR_PFULL = BAR_WEMPTY + kMaxStages, BAR_ACCFULL = BAR_PFULL + kMaxStages,
+       BAR_HREADY = BAR_ACCFULL + 2, BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_VEMPTY = BAR_EEMPTY + 2, BAR_VFULL = BAR_VEMPTY + 2,
+       BAR_VPART = BAR_VFULL + 1, BAR_COUNT = BAR_VPART + 1 };
+static_assert(BAR_COUNT * 8 + 8 <= 512, "barrier area");
 
 struct TcParams {
   const uint8_t* chunks;
@@ -92,7 +94,7 @@ __host__ __device__ constexpr int step_chunks_h(int s) { return s == 0 ? 0 : 8; 
 // bf16 (lo, hi) split of the bias.  Layers fed by the encoded tile (0, 5) get it for free; the H-fed trunk layers
 // append one K=16 MMA on a "bias chunk" (A = encoded columns 80..95, all other weight rows zero).
 __host__ __device__ constexpr int step_bias_chunk(int s) { return (s >= 1 && s <= 7 && s != 5) ? 1 : 0; }
-constexpr int kViewN = 144;   // 128 views outputs + sigma head (alpha_linear weights as bf16 hi/lo rows) + padding to a multiple of 16
+constexpr int kViewN = 160;   // 128 views outputs + sigma head (alpha_linear weights as bf16 hi/lo rows) + padding to a multiple of 32
 __host__ __device__ constexpr int step_chunk_bytes(int s) { return s == kViewStep ? kViewN * 64 : 16384; }
 __host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the weight stream
   int64_t off = 0;
@@ -136,6 +138,38 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(bar, parity, error_flag, code);
 }
+// ---- CTA-pair (cta_group::2) plumbing: the leader CTA (cluster rank 0) issues every MMA for both CTAs, so the
+// barriers its MMA thread waits on collect arrivals from both CTAs (remote arrive through the cluster window).
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// (waits on barriers fed by both CTAs use the ordinary try_wait: a cluster-scope acquire on every probe costs several
+// hundred cycles - measured 4x slower MMA issue - and the data the MMA reads was made visible by the arriving side's
+// tcgen05.wait::st / fence.proxy.async before its arrive)
+template <int CG>
+__device__ __forceinline__ void mbar_wait_x(uint32_t bar, uint32_t parity, int* error_flag, int code) {
+  mbar_wait(bar, parity, error_flag, code);
+}
+// one elected lane per warp signals the leader CTA's barrier (call after the warp's own fences, converged)
+template <int CG>
+__device__ __forceinline__ void warp_arrive_leader(uint32_t bar, uint32_t rank, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    if (CG == 2 && rank != 0) mbar_arrive_cluster(mapa_rank0(bar)); else mbar_arrive(bar);
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool elect_one() {      // true in exactly one lane of a converged warp
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -163,8 +197,8 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo) {
   return d;
 }
 // instruction descriptor: kind::f16, A = B = bf16 (K-major), D = fp32, M = 128
-__device__ __forceinline__ uint32_t umma_idesc(int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(int N, int M) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -173,8 +207,44 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from TMEM (the previous layer's activations, packed bf16 in place of its accumulator), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// CTA-pair forms: one instruction drives both SMs' tensor cores (M = 256: 128 rows per CTA; each CTA supplies half of
+// B's N rows from its own shared memory, at the same offsets); commit arrives on the same barrier in both CTAs.
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <int CG> __device__ __forceinline__ void mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (CG == 2) umma2_bf16(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc);
+}
+template <int CG> __device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (CG == 2) umma2_bf16_ts(d, a, b, idesc, acc); else umma_bf16_ts(d, a, b, idesc, acc);
+}
+template <int CG> __device__ __forceinline__ void mma_commit(uint32_t bar) {
+  if (CG == 2) umma2_commit(bar); else umma_commit(bar);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -187,6 +257,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* w) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]),
+        "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -277,39 +355,29 @@ __device__ __forceinline__ void encode_row_ipe(const float m[3], const float var
   }
 }
 
-// One 32-column slice of a trunk-layer epilogue: bias + ReLU, fp32 sigma head, bf16 hand-over to the next layer.
+// One 32-column slice of a trunk-layer epilogue.  The bias is already in the accumulator, so a slice is 16 ReLU-fused
+// bf16x2 conversions (F2FP.RELU) and ONE tcgen05.st: the packed activations go back into TMEM, over the first 16 of the
+// slice's own 32 accumulator columns, where the next layer's MMAs read them as their A operand (no shared-memory
+// round trip).  Only the tapped layer (stop_layer) also stages its slice in shared memory for the bulk store home.
 struct EpiCtx {
-  const float* tab;                                                // shared-memory tables (bias | walpha | wrgb)
   uint32_t h_base; int r; int s;
-  float alpha;
 };
-// Fast path (every trunk layer but the one feeding sigma): the bias is already in the accumulator, so a slice is
-// 16 ReLU-fused bf16x2 conversions (F2FP.RELU) and four 16-byte stores.
-__device__ __forceinline__ void epi_trunk_fast(const EpiCtx& e, const uint32_t* v, int j) {
+__device__ __forceinline__ void epi_trunk(const EpiCtx& e, const uint32_t* v, uint32_t t_chunk, int j, bool tap, const TcParams& p, bool valid,
+                                          int64_t pt) {
   uint32_t w[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i)
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
+  tmem_st16(t_chunk, w);
+  if (tap) {
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.h_base + j * kBlk + sw64_off(e.r, c)), "r"(w[4 * c]), "r"(w[4 * c + 1]),
-                 "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
-}
-
-__device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, int j, const TcParams& p, bool valid, int64_t pt) {
-  if (p.debug_out == nullptr) { epi_trunk_fast(e, v, j); return; }
-  float x[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] = fmaxf(__uint_as_float(v[i]), 0.f);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t w0 = pack_bf16(x[8 * c], x[8 * c + 1]), w1 = pack_bf16(x[8 * c + 2], x[8 * c + 3]);
-    uint32_t w2 = pack_bf16(x[8 * c + 4], x[8 * c + 5]), w3 = pack_bf16(x[8 * c + 6], x[8 * c + 7]);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.h_base + j * kBlk + sw64_off(e.r, c)), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+    for (int c = 0; c < 4; ++c)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.h_base + j * kBlk + sw64_off(e.r, c)), "r"(w[4 * c]), "r"(w[4 * c + 1]),
+                   "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
   }
   if (p.debug_out && e.s == p.debug_step && valid) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = x[i];
+    for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = fmaxf(__uint_as_float(v[i]), 0.f);
   }
 }
 
@@ -364,7 +432,18 @@ __device__ __forceinline__ float4 epi_view(const float* tab, const float* vbrow,
 }
 
 // ---- the kernel ----------------------------------------------------------------------------
+// CG = 1: every CTA is on its own.  CG = 2: CTA pairs (cluster of 2) share every MMA (cta_group::2): each CTA keeps its own
+// 128-point tile, encoder, epilogues and TMEM, but streams only HALF of every weight chunk (its half of the output
+// columns) - the per-SM weight delivery from L2, which bounds the single-CTA kernel, is halved.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int kStages = CG == 2 ? kMaxStages : 6;
+  constexpr int kStageB = kRingBytes / kStages;      // 8 KB half chunks | 16 KB chunks
+  // Ring stages are RELEASED in groups: tcgen05.commit blocks the issuing thread for ~400 cycles (tools/mma_rate.cu:
+  // "MMA MMA commit" runs at 230 cycles/MMA, "MMA x4 commit" at 128), so one commit per K=32 chunk made the MMA
+  // thread, not the tensor core, the bottleneck.  Arrival stays per stage.
+  constexpr int kGroup = kStages / 3;
+  const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* gbase = smem_raw;
@@ -374,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   float4* partv = reinterpret_cast<float4*>(gbase + OFF_PARTV);
   float* vbs = reinterpret_cast<float*>(gbase + OFF_VBS);
   const bool use_vbs = p.vb_div >= 43;             // a tile then spans at most kVbRays rays
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index: provably warp-uniform
   const int G = gridDim.x;
   if (base & 1023u) {                              // the swizzled UMMA tiles need a 1024-byte aligned window
     if (threadIdx.x == 0) { atomicExch(p.error_flag, 900); __threadfence_system(); }
@@ -383,24 +462,32 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   for (int i = threadIdx.x; i < 3 * kHalf; i += kThreads) tab[i] = p.wrgb[i];
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bars + 8 * (BAR_WFULL + i), 1); mbar_init(bars + 8 * (BAR_WEMPTY + i), 1); mbar_init(bars + 8 * (BAR_PFULL + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {                    // arrivals are one elected lane per warp, from both CTAs of a pair
       mbar_init(bars + 8 * (BAR_ACCFULL + i), 1);
-      mbar_init(bars + 8 * (BAR_EFULL + i), 128);
+      mbar_init(bars + 8 * (BAR_EFULL + i), 4 * CG);
       mbar_init(bars + 8 * (BAR_EEMPTY + i), 1);
-      mbar_init(bars + 8 * (BAR_VEMPTY + i), 384);
+      mbar_init(bars + 8 * (BAR_VEMPTY + i), 12 * CG);
     }
     mbar_init(bars + 8 * BAR_VFULL, 1);
     mbar_init(bars + 8 * BAR_VPART, 256);
-    for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 128);
+    for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 4 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + BAR_COUNT * 8), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + BAR_COUNT * 8), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + BAR_COUNT * 8), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                   // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -412,80 +499,117 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         const uint8_t* src = p.chunks;
         for (int s = 0; s < kSteps; ++s) {
           const int nch = step_chunks_e(s) + step_chunks_h(s) + step_bias_chunk(s);
-          const uint32_t bytes = step_chunk_bytes(s);
+          const uint32_t bytes = step_chunk_bytes(s) / CG;      // CTA pair: this CTA's half of the chunk's output rows
           for (int c = 0; c < nch; ++c) {
-            mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
+            if (stage % kGroup == 0) mbar_wait(bars + 8 * (BAR_WEMPTY + stage / kGroup), phase ^ 1, p.error_flag, 100 + stage);
             mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
-            bulk_g2s(base + OFF_W + stage * kStageBytes, src, bytes, bars + 8 * (BAR_WFULL + stage));
-            src += bytes;
+            bulk_g2s(base + OFF_W + stage * kStageB, src + rank * bytes, bytes, bars + 8 * (BAR_WFULL + stage));
+            src += bytes * CG;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (CG == 2 && warp == 3 && rank == 1) {
+    // ===== peer CTA: tell the leader's MMA thread when this CTA's half of a weight stage has landed =====
     if (lane == 0) {
-      int stage = 0; uint32_t wphase = 0, hphase = 0;
-      uint32_t ph_efull = 0;                                       // bit eb: phase of E buffer eb (bitmask: no local-memory array)
-      int gstep = 0;                                               // running layer count: 9 steps per tile is odd, so the
-      for (int it = 0; it < p.n_iters; ++it) {                     // accumulator ping-pong must carry across tiles
-        const int eb = it & 1;
-        for (int s = 0; s < kSteps; ++s, ++gstep) {
-          const int ne = step_chunks_e(s), nh = step_chunks_h(s);
-          const uint32_t idesc = umma_idesc((s == kViewStep) ? kViewN : 256);
-          const int ab = gstep & 1;
-          const uint32_t d_tmem = tmem_base + ab * 256;            // accumulator ping-pong by layer
-          if (s == 0) {
-            mbar_wait(bars + 8 * (BAR_EFULL + eb), (ph_efull >> eb) & 1u, p.error_flag, 210 + eb);
-            ph_efull ^= 1u << eb;
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < p.n_iters; ++it)
+        for (int s = 0; s < kSteps; ++s) {
+          const int nch = step_chunks_e(s) + step_chunks_h(s) + step_bias_chunk(s);
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(bars + 8 * (BAR_WFULL + stage), phase, p.error_flag, 120 + stage);
+            mbar_arrive_cluster(mapa_rank0(bars + 8 * (BAR_PFULL + stage)));
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 0] = clock64();
-          uint32_t accumulate = 0;
-          if (step_bias_chunk(s)) {                                // + bias: ones columns of the encoded tile x (lo, hi) bias rows
-            // Issued FIRST so the tensor core has work while the epilogue hands over chunk 0.  It overwrites the other
-            // accumulator buffer, last read by the epilogue two layers back: for s >= 2 the previous layer's hand-over
-            // waits already ordered that; for s == 1 it is the previous TILE's view epilogue, which signals VEMPTY.
-            if (s == 1 && it > 0) mbar_wait(bars + 8 * (BAR_VEMPTY + ((it - 1) & 1)), ((it - 1) >> 1) & 1, p.error_flag, 240);
-            const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
-            if (!mbar_try_wait(wbar, wphase)) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
-            tc_fence_after();
-            umma_bf16(d_tmem, mk_desc(desc_lo(base + OFF_E + eb * kEBytes + 2 * kBlk) + 2), mk_desc(desc_lo(base + OFF_W + stage * kStageBytes) + 2), idesc, 0u);
-            umma_commit(bars + 8 * (BAR_WEMPTY + stage));
-            if (++stage == kStages) { stage = 0; wphase ^= 1; }
-            accumulate = 1;                                      // issued first: keeps the tensor core busy while the epilogue hands over chunk 0
-          }
-          for (int c = 0; c < ne + nh; ++c) {
-            const uint32_t wbar = bars + 8 * (BAR_WFULL + stage);
-            uint32_t a0;
-            if (c < ne) {
-              a0 = desc_lo(base + OFF_E + eb * kEBytes + c * kBlk);
-              if (!mbar_try_wait(wbar, wphase)) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
-            } else {
-              // chunk (c-ne) of the previous layer's output: handed over by the epilogue
-              a0 = desc_lo(base + OFF_H + (c - ne) * kBlk);
-              const uint32_t hbar = bars + 8 * (BAR_HREADY + (c - ne));
-              const bool ok_h = mbar_try_wait(hbar, hphase), ok_w = mbar_try_wait(wbar, wphase);   // both probes in flight
-              if (!ok_h) mbar_wait_slow(hbar, hphase, p.error_flag, 230 + (c - ne));
-              if (!ok_w) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
-            }
-            tc_fence_after();
-            const uint32_t b0 = desc_lo(base + OFF_W + stage * kStageBytes);
-            umma_bf16(d_tmem, mk_desc(a0), mk_desc(b0), idesc, accumulate);
-            umma_bf16(d_tmem, mk_desc(a0 + 2), mk_desc(b0 + 2), idesc, 1u);
-            accumulate = 1;
-            umma_commit(bars + 8 * (BAR_WEMPTY + stage));          // stage free once these MMAs retire
-            if (++stage == kStages) { stage = 0; wphase ^= 1; }
-          }
-          if (p.timeline && blockIdx.x == 0 && it < 8) p.timeline[(it * kSteps + s) * 4 + 1] = clock64();
-          if (s < kViewStep) {
-            umma_commit(bars + 8 * (BAR_ACCFULL + ab));            // accumulator complete -> trunk epilogue
-          } else {
-            umma_commit(bars + 8 * BAR_VFULL);                     // views accumulator -> view epilogue (encoder warps)
-            umma_commit(bars + 8 * (BAR_EEMPTY + eb));             // encoded tile (incl. its ones columns) no longer needed
-          }
-          if (nh) hphase ^= 1;
         }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===== MMA issuer (leader CTA of a pair issues for both) =====
+    // The WHOLE warp runs this loop converged and one elected lane issues: every operand is then warp-uniform and
+    // stays in uniform registers.  (Inside an `if (lane == 0)` region the compiler has to move each descriptor with
+    // R2UR and wrap every UTCHMMA / UTCBAR in an ELECT ... BRA.U.ANY loop - ~110 instructions per K=32 chunk on one
+    // thread, which made this thread, not the tensor core, the bottleneck: tools/mma_rate.cu, scripts/tc_timeline.py.)
+    int stage = 0; uint32_t wphase = 0, hphase = 0;
+    uint32_t ph_efull = 0;                                       // bit eb: phase of E buffer eb (bitmask: no local-memory array)
+    int gstep = 0;                                               // running layer count: 9 steps per tile is odd, so the
+    const uint32_t w_desc0 = desc_lo(base + OFF_W), e_desc0 = desc_lo(base + OFF_E);
+    const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && lane == 0;
+    for (int it = 0; it < p.n_iters; ++it) {                     // accumulator ping-pong must carry across tiles
+      const int eb = it & 1;
+      const uint32_t e_desc = e_desc0 + eb * (kEBytes >> 4);
+#pragma unroll
+      for (int s = 0; s < kSteps; ++s, ++gstep) {
+        const int ne = step_chunks_e(s), nh = step_chunks_h(s);
+        const uint32_t idesc = umma_idesc((s == kViewStep) ? kViewN : 256, kTileM * CG);
+        const int ab = gstep & 1;
+        const uint32_t d_tmem = tmem_base + ab * 256;            // accumulator ping-pong by layer
+        const uint32_t a_tmem = tmem_base + (ab ^ 1) * 256;      // previous layer's activations, packed in place of its accumulator
+        if (s == 0) {
+          mbar_wait(bars + 8 * (BAR_EFULL + eb), (ph_efull >> eb) & 1u, p.error_flag, 210 + eb);
+          ph_efull ^= 1u << eb;
+        }
+        if (tl_on && it < 8) p.timeline[(it * kSteps + s) * 4 + 0] = clock64();
+        uint32_t accumulate = 0;
+        if (step_bias_chunk(s)) {                                // + bias: ones columns of the encoded tile x (lo, hi) bias rows
+          // Issued FIRST so the tensor core has work while the epilogue hands over chunk 0.  It overwrites the other
+          // accumulator buffer, last read by the epilogue two layers back: for s >= 2 the previous layer's hand-over
+          // waits already ordered that; for s == 1 it is the previous TILE's view epilogue, which signals VEMPTY.
+          if (s == 1 && it > 0) mbar_wait(bars + 8 * (BAR_VEMPTY + ((it - 1) & 1)), ((it - 1) >> 1) & 1, p.error_flag, 240);
+          mbar_wait(bars + 8 * (BAR_WFULL + stage), wphase, p.error_flag, 220 + stage);
+          if (CG == 2) mbar_wait(bars + 8 * (BAR_PFULL + stage), wphase, p.error_flag, 250 + stage);
+          tc_fence_after();
+          if (elect_one()) {
+            mma_ss<CG>(d_tmem, mk_desc(e_desc + 2 * (kBlk >> 4) + 2), mk_desc(w_desc0 + stage * (kStageB >> 4) + 2), idesc, 0u);
+            if ((stage + 1) % kGroup == 0) mma_commit<CG>(bars + 8 * (BAR_WEMPTY + stage / kGroup));
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; wphase ^= 1; }
+          accumulate = 1;
+        }
+#pragma unroll
+        for (int c = 0; c < ne + nh; ++c) {
+          const uint32_t wbar = bars + 8 * (BAR_WFULL + stage), pbar = bars + 8 * (BAR_PFULL + stage);
+          if (c < ne) {
+            mbar_wait(wbar, wphase, p.error_flag, 220 + stage);
+            if (CG == 2) mbar_wait(pbar, wphase, p.error_flag, 250 + stage);
+          } else {
+            // chunk (c-ne) of the previous layer's output: packed by the epilogue into that layer's accumulator buffer
+            const uint32_t hbar = bars + 8 * (BAR_HREADY + (c - ne));
+            const bool ok_h = mbar_try_wait(hbar, hphase), ok_w = mbar_try_wait(wbar, wphase);   // all probes in flight
+            const bool ok_p = CG == 2 ? mbar_try_wait(pbar, wphase) : true;
+            if (!ok_h) mbar_wait_slow(hbar, hphase, p.error_flag, 230 + (c - ne));
+            if (!ok_w) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
+            if (!ok_p) mbar_wait_slow(pbar, wphase, p.error_flag, 250 + stage);
+          }
+          tc_fence_after();
+          const uint32_t b0 = w_desc0 + stage * (kStageB >> 4);
+          if (elect_one()) {
+            if (c < ne) {
+              const uint32_t a0 = e_desc + c * (kBlk >> 4);
+              mma_ss<CG>(d_tmem, mk_desc(a0), mk_desc(b0), idesc, accumulate);
+              mma_ss<CG>(d_tmem, mk_desc(a0 + 2), mk_desc(b0 + 2), idesc, 1u);
+            } else {                                               // K = 16 bf16 = 8 TMEM columns per MMA
+              mma_ts<CG>(d_tmem, a_tmem + (c - ne) * 32, mk_desc(b0), idesc, accumulate);
+              mma_ts<CG>(d_tmem, a_tmem + (c - ne) * 32 + 8, mk_desc(b0 + 2), idesc, 1u);
+            }
+            if ((stage + 1) % kGroup == 0) mma_commit<CG>(bars + 8 * (BAR_WEMPTY + stage / kGroup));   // group free (in both CTAs) once these MMAs retire
+          }
+          __syncwarp();
+          accumulate = 1;
+          if (++stage == kStages) { stage = 0; wphase ^= 1; }
+        }
+        if (tl_on && it < 8) p.timeline[(it * kSteps + s) * 4 + 1] = clock64();
+        if (elect_one()) {
+          if (s < kViewStep) {
+            mma_commit<CG>(bars + 8 * (BAR_ACCFULL + ab));         // accumulator complete -> trunk epilogue
+          } else {
+            mma_commit<CG>(bars + 8 * BAR_VFULL);                  // views accumulator -> view epilogue (encoder warps)
+            mma_commit<CG>(bars + 8 * (BAR_EEMPTY + eb));          // encoded tile (incl. its ones columns) no longer needed
+          }
+        }
+        __syncwarp();
+        if (nh) hphase ^= 1;
       }
     }
   } else if (warp >= 4 && warp < 12) {
@@ -500,13 +624,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     const bool leader = (et & 127) == 0;            // first thread of this chunk group: issues the group's feature-tap bulk stores
     bool store_pending = false;
     EpiCtx e;
-    e.h_base = h_base; e.r = r; e.tab = tab;
+    e.h_base = h_base; e.r = r;
     int gstep = 0;
     for (int it = 0; it < p.n_iters; ++it) {
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
-      e.alpha = 0.f;
       for (int s = 0; s < kViewStep; ++s, ++gstep) {
         e.s = s;
         const int ab = gstep & 1;
@@ -515,22 +638,24 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         ph_acc ^= 1u << ab;
         tc_fence_after();
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 2] = clock64();
-        if (store_pending) {                        // this group's tap stores (a layer ago) have finished reading H
+        const bool tap = (s == p.stop_step) && p.want_feat;
+        if (tap && store_pending) {                 // this group's tap stores (a tile ago) have finished reading the staging tile
           if (leader) bulk_wait_read0();
           named_bar_sync(1 + g, 128);
           store_pending = false;
         }
-        const bool tap = (s == p.stop_step) && p.want_feat;
         auto hand_over = [&](int j) {
-          fence_proxy_async();                       // generic-proxy writes -> visible to UMMA / bulk copy
+          tmem_st_wait();                            // packed activations are in TMEM ...
+          tc_fence_before();                         // ... and ordered before the MMA thread's reads
           if (tap) {                                 // tapped layer: the chunk also goes home as tiled bf16 features
+            fence_proxy_async();                     // generic-proxy writes -> visible to the bulk copy
             named_bar_sync(1 + g, 128);
             if (leader && tile * kTileM < p.P) {
               bulk_s2g(p.feat_tiles + (size_t)tile * kFeatTileBytes + j * kBlk, h_base + j * kBlk, kBlk);
               bulk_commit();
             }
           }
-          mbar_arrive(bars + 8 * (BAR_HREADY + j));
+          warp_arrive_leader<CG>(bars + 8 * (BAR_HREADY + j), rank, lane);
         };
         uint32_t va[32], vb[32];
         tmem_ld32(t_lane + g * 32, va);
@@ -539,11 +664,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           const int j = g + 2 * jj;
           tmem_ld_wait();
           tmem_ld32(t_lane + (j + 2) * 32, vb);
-          epi_trunk(e, va, j, p, valid, pt);
+          epi_trunk(e, va, t_lane + j * 32, j, tap, p, valid, pt);
           hand_over(j);
           tmem_ld_wait();
           if (jj + 2 < 4) tmem_ld32(t_lane + (j + 4) * 32, va);
-          epi_trunk(e, vb, j + 2, p, valid, pt);
+          epi_trunk(e, vb, t_lane + (j + 2) * 32, j + 2, tap, p, valid, pt);
           hand_over(j + 2);
         }
         if (tap) store_pending = true;
@@ -565,7 +690,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         tc_fence_before();
         partv[g * kTileM + r] = pv;
         mbar_arrive(bars + 8 * BAR_VPART);
-        mbar_arrive(bars + 8 * (BAR_VEMPTY + (it & 1)));
+        warp_arrive_leader<CG>(bars + 8 * (BAR_VEMPTY + (it & 1)), rank, lane);
       }
       ++gstep;
     }
@@ -625,7 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         encode_row_fourier<15>(m, rw);
       }
       fence_proxy_async();
-      mbar_arrive(bars + 8 * (BAR_EFULL + eb));
+      warp_arrive_leader<CG>(bars + 8 * (BAR_EFULL + eb), rank, lane);
     };
     encode_tile(0);
     for (int it = 0; it < p.n_iters; ++it) {
@@ -666,16 +791,18 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
       }
       if (p.timeline && blockIdx.x == 0 && it < 8 && r == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 3] = clock64();
-      mbar_arrive(bars + 8 * (BAR_VEMPTY + (it & 1)));   // views accumulator drained (MMA of the next tile's layer 1 may overwrite it)
+      warp_arrive_leader<CG>(bars + 8 * (BAR_VEMPTY + (it & 1)), rank, lane);   // views accumulator drained (the next tile's layer 1 may overwrite it)
     }
   }
 
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                   // neither CTA leaves (or frees TMEM) while its peer can still reach it
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -782,6 +909,9 @@ int* g_trap_host = nullptr;   // mapped pinned int: survives a trapped launch
 int* g_trap_dev = nullptr;
 long long* g_timeline = nullptr;
 
+int g_cta_group = 0;           // 1 | 2 (CTA pairs); 0: not decided yet (NMR_TC_CG, default 1)
+int g_pair_ctas = 0;           // 2 x clusters of two that can be resident at once
+
 int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std::string* err) {
   static int num_sms = 0;
   if (!g_trap_host) {
@@ -792,19 +922,43 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
     *g_trap_host = 0;
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
+    if (g_cta_group == 0) {
+      const char* ev = getenv("NMR_TC_CG");
+      g_cta_group = (ev && atoi(ev) == 2) ? 2 : 1;
+    }
+    cudaLaunchConfig_t qc{};
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    qc.gridDim = dim3(num_sms & ~1); qc.blockDim = dim3(kThreads); qc.dynamicSmemBytes = kSmemBytes; qc.attrs = qa; qc.numAttrs = 1;
+    int ncl = 0;
+    e = cudaOccupancyMaxActiveClusters(&ncl, nerf_mlp_tc_kernel<2>, &qc);
+    if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); g_cta_group = 1; }
+    g_pair_ctas = 2 * ncl;
   }
   p.error_flag = g_trap_dev;
-  if (!g_timeline && getenv("NMR_TC_TIMELINE")) { cudaMalloc((void**)&g_timeline, (8 * kSteps * 4 + 32) * sizeof(long long)); cudaMemset(g_timeline, 0, (8 * kSteps * 4 + 32) * sizeof(long long)); }
+  if (!g_timeline && getenv("NMR_TC_TIMELINE")) { cudaMalloc((void**)&g_timeline, (kTlSlots) * sizeof(long long)); cudaMemset(g_timeline, 0, (kTlSlots) * sizeof(long long)); }
   p.timeline = g_timeline;
   int64_t tiles = (p.P + kTileM - 1) / kTileM;
-  int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(tiles, 1));
-  p.n_iters = (int)((tiles + grid - 1) / grid);
   p.chunks = net.chunks; p.bias = net.bias; p.walpha = net.walpha; p.wrgb = net.wrgb;
   p.balpha = net.balpha; p.brgb0 = net.brgb[0]; p.brgb1 = net.brgb[1]; p.brgb2 = net.brgb[2];
-  nerf_mlp_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e;
+  if (g_cta_group == 2) {
+    int grid = (int)std::min<int64_t>(g_pair_ctas, (std::max<int64_t>(tiles, 1) + 1) / 2 * 2);
+    p.n_iters = (int)((tiles + grid - 1) / grid);
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s; cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc_kernel<2>, p);
+  } else {
+    int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(tiles, 1));
+    p.n_iters = (int)((tiles + grid - 1) / grid);
+    nerf_mlp_tc_kernel<1><<<grid, kThreads, kSmemBytes, s>>>(p);
+    e = cudaGetLastError();
+  }
   if (e != cudaSuccess) { *err = std::string("nerf_mlp_tc_kernel launch: ") + cudaGetErrorString(e); return -1; }
   *launches += 1;
   return 0;
@@ -913,13 +1067,16 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
   return 0;
 }
 
-int tc_set_cluster(int cs) {   // kept for ABI stability: measured no gain from TMA multicast at cluster <= 4 on B200
-  return (cs == 1 || cs == 2 || cs == 4) ? 0 : -1;
+int tc_set_cluster(int cs) {   // 1: independent CTAs (default), 2: CTA pairs sharing every MMA (cta_group::2)
+  if (cs != 1 && cs != 2) return -1;
+  if (cs == 2 && g_trap_host && g_pair_ctas < 2) return -1;   // pairs cannot be co-scheduled on this device
+  g_cta_group = cs;
+  return 0;
 }
 
 int tc_read_timeline(long long* host, int n) {
   if (!g_timeline) return 0;
-  int m = std::min(n, 8 * kSteps * 4 + 32);
+  int m = std::min(n, kTlSlots);
   cudaMemcpy(host, g_timeline, m * sizeof(long long), cudaMemcpyDeviceToHost);
   return m;
 }

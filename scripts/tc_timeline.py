@@ -24,13 +24,9 @@ rays, _, _ = eng.raygen(K_7SCENES, make_pose(1), 480, 640, 4)     # 19200 rays: 
 for _ in range(2):
     ren.predict(rays, 1, 1)
 torch.cuda.synchronize()
-buf = (C.c_longlong * (8 * 9 * 4 + 32))()
+buf = (C.c_longlong * (8 * 9 * 4 + 64))()
 n = L.load().nmr_debug_timeline(buf, len(buf))
 t = np.array(buf[:8 * 9 * 4], dtype=np.int64).reshape(8, 9, 4)
-tr = np.array(buf[8 * 9 * 4:8 * 9 * 4 + 5], dtype=np.int64)
-print('view-step trace (it 2): epi_view, wait partials, combine+store, barrier =', np.diff(tr))
-tk = np.array(buf[8 * 9 * 4 + 8:8 * 9 * 4 + 13], dtype=np.int64)
-print('trunk chunk trace (it 2, step 2): ld wait+prefetch, math+STS, proxy fence, mbar arrive =', np.diff(tk))
 t0 = t[1:6]
 print("per step (cycles), iterations 1..5 averaged")
 print("step  mma_issue  mma_end->epi_start  epilogue  epi_end->next_mma_start   total")
