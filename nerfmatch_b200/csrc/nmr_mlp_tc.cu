@@ -43,32 +43,35 @@ constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64
 constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
 constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
 constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
-constexpr int kRingBytes = 6 * kStageBytes;
-constexpr int kMaxStages = 12;             // CTA pair (cta_group::2): 12 stages of half chunks; single CTA: 6 full chunks
+constexpr int kRingBytes = 8 * kStageBytes;
+constexpr int kMaxStages = 16;             // CTA pair (cta_group::2): 16 stages of half chunks; single CTA: 8 full chunks
 constexpr int kSteps = 9;                  // 8 trunk layers + (feature_linear folded into) views_linears.0
 constexpr int kViewStep = 8;
 constexpr int kThreads = 512;
+#ifndef NMR_TC_GROUPS
+#define NMR_TC_GROUPS 4                    // ring release granularity: kStages / NMR_TC_GROUPS stages per commit
+#endif
 constexpr int kTlSlots = 8 * kSteps * 4 + 64;   // clock64 trace: [it][step][4] + per-step wait breakdown of iteration 2
 constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128 points
 
-constexpr int OFF_H = 0;
-constexpr int OFF_E = kHBytes;
+constexpr int OFF_E = 0;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
-constexpr int OFF_TAB = OFF_W + kRingBytes;        // fp32 table: wrgb [3][128]
+constexpr int OFF_TAP = OFF_W + kRingBytes;                   // feature-tap staging: 8 epilogue warps x 2 buffers x [32 rows x 64 B]
+constexpr int kTapBytes = 2048;
+constexpr int OFF_TAB = OFF_TAP + 8 * 2 * kTapBytes;        // fp32 table: wrgb [3][128]
 constexpr int kTabFloats = 3 * kHalf;
-constexpr int OFF_PART = OFF_TAB + kTabFloats * 4;            // float4 per row: partial (rgb, alpha) of the odd-chunk warps
-constexpr int OFF_PARTV = OFF_PART + kTileM * 16;            // 2 x float4 per row: rgb partial sums of the two trunk-epilogue groups
+constexpr int OFF_PARTV = OFF_TAB + kTabFloats * 4;           // 2 tiles x 2 groups x float4 per row: (rgb partial sums, sigma) of the views epilogue
 constexpr int kVbRays = 4;                                    // rays a 128-point tile can touch when S >= 43
-constexpr int OFF_VBS = OFF_PARTV + 2 * kTileM * 16;               // 2 x [kVbRays][128] fp32: per-ray view bias of the tile (double buffered)
+constexpr int OFF_VBS = OFF_PARTV + 4 * kTileM * 16;          // 2 x [kVbRays][128] fp32: per-ray view bias of the tile (double buffered)
 constexpr int OFF_BAR = OFF_VBS + 2 * kVbRays * kHalf * 4;
-constexpr int kSmemBytes = OFF_BAR + 512;                     // dynamic smem is 1024-aligned (checked at kernel entry)
+constexpr int kSmemBytes = OFF_BAR + 1024;                     // dynamic smem is 1024-aligned (checked at kernel entry)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
 enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kMaxStages, BAR_PFULL = BAR_WEMPTY + kMaxStages, BAR_ACCFULL = BAR_PFULL + kMaxStages,
        BAR_HREADY = BAR_ACCFULL + 2, BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_VEMPTY = BAR_EEMPTY + 2, BAR_VFULL = BAR_VEMPTY + 2,
        BAR_VPART = BAR_VFULL + 1, BAR_COUNT = BAR_VPART + 1 };
-static_assert(BAR_COUNT * 8 + 8 <= 512, "barrier area");
+static_assert(BAR_COUNT * 8 + 8 <= 1024, "barrier area");
 
 struct TcParams {
   const uint8_t* chunks;
@@ -170,23 +173,20 @@ __device__ __forceinline__ bool elect_one() {      // true in exactly one lane o
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 
 // UMMA shared-memory descriptor, K-major, SWIZZLE_64B: rows of 64 B, 8-row groups 512 B apart (SBO), version 1.
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
@@ -360,7 +360,7 @@ __device__ __forceinline__ void encode_row_ipe(const float m[3], const float var
 // slice's own 32 accumulator columns, where the next layer's MMAs read them as their A operand (no shared-memory
 // round trip).  Only the tapped layer (stop_layer) also stages its slice in shared memory for the bulk store home.
 struct EpiCtx {
-  uint32_t h_base; int r; int s;
+  uint32_t tap_st; int r; int s;       // tap_st: this row's 64-byte segment in the warp's staging buffer 0
 };
 __device__ __forceinline__ void epi_trunk(const EpiCtx& e, const uint32_t* v, uint32_t t_chunk, int j, bool tap, const TcParams& p, bool valid,
                                           int64_t pt) {
@@ -369,11 +369,11 @@ __device__ __forceinline__ void epi_trunk(const EpiCtx& e, const uint32_t* v, ui
   for (int i = 0; i < 16; ++i)
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
   tmem_st16(t_chunk, w);
-  if (tap) {
+  if (tap) {                             // stage the row's 64-byte segment (same swizzle as the UMMA tiles); buffer alternates by chunk
 #pragma unroll
     for (int c = 0; c < 4; ++c)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.h_base + j * kBlk + sw64_off(e.r, c)), "r"(w[4 * c]), "r"(w[4 * c + 1]),
-                   "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.tap_st + ((j >> 1) & 1) * kTapBytes + ((c ^ ((e.r & 7) >> 1)) << 4)),
+                   "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
   }
   if (p.debug_out && e.s == p.debug_step && valid) {
 #pragma unroll
@@ -390,7 +390,7 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { u
 // views_linears.0 epilogue (run by the encoder warps so the trunk epilogue warps can move on to the next tile):
 // four 32-column slices: per-ray view bias + ReLU, rgb_linear + sigmoid, raw [P,4] store.
 // Slices [j0, j0 + NS) of the 128 views columns; returns this warp's partial rgb dot products.
-template <int NS>
+template <int NS, int JSTRIDE>
 __device__ __forceinline__ float4 epi_view(const float* tab, const float* vbrow, uint32_t t_lane, int j0, const TcParams& p, bool valid,
                                            int64_t pt) {
   uint64_t q0 = 0, q1 = 0, q2 = 0;                 // (even, odd) partial sums of the three rgb dot products
@@ -401,8 +401,8 @@ __device__ __forceinline__ float4 epi_view(const float* tab, const float* vbrow,
     for (int h = 0; h < NS; ++h) {
       uint32_t* v = h == 0 ? va : vb;
       tmem_ld_wait();
-      if (h + 1 < NS) tmem_ld32(t_lane + (j0 + 1) * 32, vb);
-      const int jj = j0 + h;
+      if (h + 1 < NS) tmem_ld32(t_lane + (j0 + JSTRIDE) * 32, vb);
+      const int jj = j0 + h * JSTRIDE;
       float x[32];
       const float4* w0 = reinterpret_cast<const float4*>(tab + jj * 32);
       const float4* w1 = w0 + kHalf / 4;
@@ -437,12 +437,12 @@ __device__ __forceinline__ float4 epi_view(const float* tab, const float* vbrow,
 // columns) - the per-SM weight delivery from L2, which bounds the single-CTA kernel, is halved.
 template <int CG>
 __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_constant__ TcParams p) {
-  constexpr int kStages = CG == 2 ? kMaxStages : 6;
+  constexpr int kStages = CG == 2 ? kMaxStages : kMaxStages / 2;
   constexpr int kStageB = kRingBytes / kStages;      // 8 KB half chunks | 16 KB chunks
   // Ring stages are RELEASED in groups: tcgen05.commit blocks the issuing thread for ~400 cycles (tools/mma_rate.cu:
   // "MMA MMA commit" runs at 230 cycles/MMA, "MMA x4 commit" at 128), so one commit per K=32 chunk made the MMA
   // thread, not the tensor core, the bottleneck.  Arrival stays per stage.
-  constexpr int kGroup = kStages / 3;
+  constexpr int kGroup = kStages / NMR_TC_GROUPS;
   const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       mbar_init(bars + 8 * (BAR_ACCFULL + i), 1);
       mbar_init(bars + 8 * (BAR_EFULL + i), 4 * CG);
       mbar_init(bars + 8 * (BAR_EEMPTY + i), 1);
-      mbar_init(bars + 8 * (BAR_VEMPTY + i), 12 * CG);
+      mbar_init(bars + 8 * (BAR_VEMPTY + i), 8 * CG);
     }
     mbar_init(bars + 8 * BAR_VFULL, 1);
     mbar_init(bars + 8 * BAR_VPART, 256);
@@ -618,18 +618,18 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int r = q * 32 + lane;                    // row of the tile
     const int et = (warp - 4) * 32 + lane;          // 0..255
-    const uint32_t h_base = base + OFF_H;
     uint32_t ph_acc = 0;                            // bit ab: phase of accumulator buffer ab
     uint32_t ph_vfull = 0;
-    const bool leader = (et & 127) == 0;            // first thread of this chunk group: issues the group's feature-tap bulk stores
-    bool store_pending = false;
     EpiCtx e;
-    e.h_base = h_base; e.r = r;
+    e.r = r;
+    const uint32_t tap_buf = base + OFF_TAP + (warp - 4) * 2 * kTapBytes;   // this warp's two staging buffers
+    e.tap_st = tap_buf + ((lane >> 3) << 9) + ((lane & 7) << 6);
     int gstep = 0;
     for (int it = 0; it < p.n_iters; ++it) {
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
+      uint8_t* tap_dst = p.feat_tiles + (size_t)tile * kFeatTileBytes + q * kTapBytes;   // this warp's 32 rows of chunk 0: 2 KB contiguous
       for (int s = 0; s < kViewStep; ++s, ++gstep) {
         e.s = s;
         const int ab = gstep & 1;
@@ -638,24 +638,21 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         ph_acc ^= 1u << ab;
         tc_fence_after();
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 2] = clock64();
-        const bool tap = (s == p.stop_step) && p.want_feat;
-        if (tap && store_pending) {                 // this group's tap stores (a tile ago) have finished reading the staging tile
-          if (leader) bulk_wait_read0();
-          named_bar_sync(1 + g, 128);
-          store_pending = false;
-        }
+        const bool tap = (s == p.stop_step) && p.want_feat && tile * kTileM < p.P;   // tapped layer: also goes home as tiled bf16 features
         auto hand_over = [&](int j) {
           tmem_st_wait();                            // packed activations are in TMEM ...
           tc_fence_before();                         // ... and ordered before the MMA thread's reads
-          if (tap) {                                 // tapped layer: the chunk also goes home as tiled bf16 features
-            fence_proxy_async();                     // generic-proxy writes -> visible to the bulk copy
-            named_bar_sync(1 + g, 128);
-            if (leader && tile * kTileM < p.P) {
-              bulk_s2g(p.feat_tiles + (size_t)tile * kFeatTileBytes + j * kBlk, h_base + j * kBlk, kBlk);
-              bulk_commit();
-            }
-          }
           warp_arrive_leader<CG>(bars + 8 * (BAR_HREADY + j), rank, lane);
+          if (tap) {                                 // the warp's 32 rows x 64 B of this chunk are one contiguous 2 KB block of the tile
+            fence_proxy_async();                     // generic-proxy writes -> visible to the bulk copy
+            __syncwarp();
+            if (lane == 0) {
+              bulk_s2g(tap_dst + j * kBlk, tap_buf + ((j >> 1) & 1) * kTapBytes, kTapBytes);
+              bulk_commit();
+              bulk_wait_read1();                     // the other buffer (this warp's previous chunk) may be rewritten
+            }
+            __syncwarp();
+          }
         };
         uint32_t va[32], vb[32];
         tmem_ld32(t_lane + g * 32, va);
@@ -671,11 +668,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           epi_trunk(e, vb, t_lane + (j + 2) * 32, j + 2, tap, p, valid, pt);
           hand_over(j + 2);
         }
-        if (tap) store_pending = true;
         tc_fence_before();
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 3] = clock64();
       }
-      {  // views layer: this warp takes slice g of the 128 columns (the encoder warps take slices 2, 3 and finish the row)
+      {  // views layer: this warp takes slices g and g + 2 of the 128 columns; group 0 also fetches the sigma head's two
+         // columns.  The encoder warps only combine the partial sums (they never touch TMEM), so the accumulator is
+         // free again - and the next tile's layer 1 can start - as soon as these eight warps are through.
         const int ab = gstep & 1;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
         const float* vbrow = nullptr;
@@ -686,21 +684,29 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         mbar_wait(bars + 8 * BAR_VFULL, ph_vfull, p.error_flag, 430);
         ph_vfull ^= 1;
         tc_fence_after();
-        const float4 pv = epi_view<1>(tab, vbrow, t_lane, g, p, valid, pt);
+        if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 2] = clock64();
+        float4 pv = epi_view<2, 2>(tab, vbrow, t_lane, g, p, valid, pt);
+        if (g == 0) {                                // sigma = h7 . (w_hi + w_lo), accumulated in fp32 by the tensor core
+          uint32_t a0, a1;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(t_lane + kHalf) : "memory");
+          tmem_ld_wait();
+          pv.w = __uint_as_float(a0) + __uint_as_float(a1);
+        }
         tc_fence_before();
-        partv[g * kTileM + r] = pv;
+        partv[((it & 1) * 2 + g) * kTileM + r] = pv;
         mbar_arrive(bars + 8 * BAR_VPART);
         warp_arrive_leader<CG>(bars + 8 * (BAR_VEMPTY + (it & 1)), rank, lane);
+        if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 3] = clock64();
       }
       ++gstep;
     }
-    if (leader) bulk_wait0();
+    if (lane == 0) bulk_wait0();
   } else if (warp >= 12) {
     // ===== encoder warps: (1) sampling data -> positional encoding -> bf16 A tile of layer 0 / skip, one tile ahead;
     //                      (2) the views-layer epilogue of the current tile (rgb + sigma -> raw) =====
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    uint32_t ph_eempty = 0, ph_vfull = 0, ph_vpart = 0;
+    uint32_t ph_eempty = 0, ph_vpart = 0;
     auto encode_tile = [&](int it) {
       const int eb = it & 1;
       const int64_t tile = (int64_t)it * G + blockIdx.x;
@@ -755,43 +761,20 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     encode_tile(0);
     for (int it = 0; it < p.n_iters; ++it) {
       if (it + 1 < p.n_iters) encode_tile(it + 1);
-      // ---- views-layer epilogue of tile `it` ----
+      // ---- finish the views layer of tile `it`: add the eight trunk warps' partial sums, sigmoid, raw [P,4] store ----
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
-      const bool valid = pt < p.P;
-      const int ab = (it * kSteps + kViewStep) & 1;
-      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
-      const float* vbrow = nullptr;
-      if (valid) {
-        const int64_t ray = pt / p.vb_div;
-        vbrow = use_vbs ? vbs + ((it & 1) * kVbRays + (int)(ray - (tile * kTileM) / p.vb_div)) * kHalf : p.vbias + ray * kHalf;
-      }
-      mbar_wait(bars + 8 * BAR_VFULL, ph_vfull, p.error_flag, 420);
-      ph_vfull ^= 1;
-      tc_fence_after();
-      if (p.timeline && blockIdx.x == 0 && it < 8 && r == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 2] = clock64();
-      float4 pv = epi_view<2>(tab, vbrow, t_lane, 2, p, valid, pt);
-      float sig_hi, sig_lo;
-      {
-        uint32_t a0, a1;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(t_lane + kHalf) : "memory");
-        tmem_ld_wait();
-        sig_hi = __uint_as_float(a0); sig_lo = __uint_as_float(a1);
-      }
-      tc_fence_before();
       mbar_wait(bars + 8 * BAR_VPART, ph_vpart, p.error_flag, 440);      // the trunk warps' partial sums are in shared memory
       ph_vpart ^= 1;
-      if (valid) {
-        const float4 p0 = partv[r], p1 = partv[kTileM + r];
+      if (pt < p.P) {
+        const float4 p0 = partv[((it & 1) * 2) * kTileM + r], p1 = partv[((it & 1) * 2 + 1) * kTileM + r];
         float4 o;
-        o.x = 1.f / (1.f + __expf(-(pv.x + p0.x + p1.x + p.brgb0)));
-        o.y = 1.f / (1.f + __expf(-(pv.y + p0.y + p1.y + p.brgb1)));
-        o.z = 1.f / (1.f + __expf(-(pv.z + p0.z + p1.z + p.brgb2)));
-        o.w = sig_hi + sig_lo + p.balpha;          // sigma = h7 . (w_hi + w_lo), accumulated in fp32 by the tensor core
+        o.x = 1.f / (1.f + __expf(-(p0.x + p1.x + p.brgb0)));
+        o.y = 1.f / (1.f + __expf(-(p0.y + p1.y + p.brgb1)));
+        o.z = 1.f / (1.f + __expf(-(p0.z + p1.z + p.brgb2)));
+        o.w = p0.w + p.balpha;
         *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
       }
-      if (p.timeline && blockIdx.x == 0 && it < 8 && r == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 3] = clock64();
-      warp_arrive_leader<CG>(bars + 8 * (BAR_VEMPTY + (it & 1)), rank, lane);   // views accumulator drained (the next tile's layer 1 may overwrite it)
     }
   }
 
