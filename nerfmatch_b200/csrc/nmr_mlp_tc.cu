@@ -43,35 +43,33 @@ constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64
 constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
 constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
 constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
-constexpr int kRingBytes = 8 * kStageBytes;
-constexpr int kMaxStages = 16;             // CTA pair (cta_group::2): 16 stages of half chunks; single CTA: 8 full chunks
+constexpr int kRingBytes = 6 * kStageBytes;
+constexpr int kMaxStages = 12;             // CTA pair (cta_group::2): 12 stages of half chunks; single CTA: 6 full chunks
 constexpr int kSteps = 9;                  // 8 trunk layers + (feature_linear folded into) views_linears.0
 constexpr int kViewStep = 8;
 constexpr int kThreads = 512;
-#ifndef NMR_TC_GROUPS
-#define NMR_TC_GROUPS 4                    // ring release granularity: kStages / NMR_TC_GROUPS stages per commit
-#endif
 constexpr int kTlSlots = 8 * kSteps * 4 + 64;   // clock64 trace: [it][step][4] + per-step wait breakdown of iteration 2
 constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128 points
 
 constexpr int OFF_E = 0;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
-constexpr int OFF_TAP = OFF_W + kRingBytes;                   // feature-tap staging: 8 epilogue warps x 2 buffers x [32 rows x 64 B]
-constexpr int kTapBytes = 2048;
-constexpr int OFF_TAB = OFF_TAP + 8 * 2 * kTapBytes;        // fp32 table: wrgb [3][128]
+constexpr int OFF_TAP = OFF_W + kRingBytes;                   // feature-tap staging: 8 epilogue warps x 4 buffers x [32 rows x 64 B]
+constexpr int kTapBytes = 2048;                               // (a whole tile: the tap warps drain it in the background)
+constexpr int kTapBufs = 4;
+constexpr int OFF_TAB = OFF_TAP + 8 * kTapBufs * kTapBytes;        // fp32 table: wrgb [3][128]
 constexpr int kTabFloats = 3 * kHalf;
 constexpr int OFF_PARTV = OFF_TAB + kTabFloats * 4;           // 2 tiles x 2 groups x float4 per row: (rgb partial sums, sigma) of the views epilogue
 constexpr int kVbRays = 4;                                    // rays a 128-point tile can touch when S >= 43
 constexpr int OFF_VBS = OFF_PARTV + 4 * kTileM * 16;          // 2 x [kVbRays][128] fp32: per-ray view bias of the tile (double buffered)
 constexpr int OFF_BAR = OFF_VBS + 2 * kVbRays * kHalf * 4;
-constexpr int kSmemBytes = OFF_BAR + 1024;                     // dynamic smem is 1024-aligned (checked at kernel entry)
+constexpr int kSmemBytes = OFF_BAR + 1280;                     // dynamic smem is 1024-aligned (checked at kernel entry)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // barrier slots (8 bytes each) inside the OFF_BAR area
 enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kMaxStages, BAR_PFULL = BAR_WEMPTY + kMaxStages, BAR_ACCFULL = BAR_PFULL + kMaxStages,
        BAR_HREADY = BAR_ACCFULL + 2, BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_VEMPTY = BAR_EEMPTY + 2, BAR_VFULL = BAR_VEMPTY + 2,
-       BAR_VPART = BAR_VFULL + 1, BAR_COUNT = BAR_VPART + 1 };
-static_assert(BAR_COUNT * 8 + 8 <= 1024, "barrier area");
+       BAR_VPART = BAR_VFULL + 1, BAR_TAPFULL = BAR_VPART + 1, BAR_TAPFREE = BAR_TAPFULL + 8 * kTapBufs, BAR_TAPREAD = BAR_TAPFREE + 8 * kTapBufs, BAR_COUNT = BAR_TAPREAD + 1 };
+static_assert(BAR_COUNT * 8 + 8 <= 1280, "barrier area");
 
 struct TcParams {
   const uint8_t* chunks;
@@ -173,12 +171,6 @@ __device__ __forceinline__ bool elect_one() {      // true in exactly one lane o
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -361,20 +353,38 @@ __device__ __forceinline__ void encode_row_ipe(const float m[3], const float var
 // round trip).  Only the tapped layer (stop_layer) also stages its slice in shared memory for the bulk store home.
 struct EpiCtx {
   uint32_t tap_st; int r; int s;       // tap_st: this row's 64-byte segment in the warp's staging buffer 0
+  uint32_t tap_bars; uint32_t tap_n;   // this warp's TAPFULL barrier pair; running count of staged chunks
+  int* error_flag;
 };
-__device__ __forceinline__ void epi_trunk(const EpiCtx& e, const uint32_t* v, uint32_t t_chunk, int j, bool tap, const TcParams& p, bool valid,
+// Tapped layer (stop_layer): after the hand-over, the packed slice is read back from TMEM (it stays valid until the layer
+// after next starts) and staged - the row's 64-byte segment, same swizzle as the UMMA tiles - for the tap warps, which
+// stream it home with coalesced stores.  One staging buffer per chunk of the tile: nothing here waits in steady state.
+__device__ __forceinline__ void tap_chunk(EpiCtx& e, uint32_t t_chunk) {
+  uint32_t w[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+        "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+      : "r"(t_chunk) : "memory");
+  const uint32_t b = e.tap_n % kTapBufs;
+  mbar_wait(e.tap_bars + 8 * (8 * kTapBufs + b), ((e.tap_n / kTapBufs) & 1u) ^ 1u, e.error_flag, 500);   // TAPFREE
+  tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.tap_st + b * kTapBytes + ((c ^ ((e.r & 7) >> 1)) << 4)),
+                 "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(e.tap_bars + 8 * b);                            // TAPFULL
+  ++e.tap_n;
+}
+
+__device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, uint32_t t_chunk, int j, const TcParams& p, bool valid,
                                           int64_t pt) {
   uint32_t w[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i)
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
   tmem_st16(t_chunk, w);
-  if (tap) {                             // stage the row's 64-byte segment (same swizzle as the UMMA tiles); buffer alternates by chunk
-#pragma unroll
-    for (int c = 0; c < 4; ++c)
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e.tap_st + ((j >> 1) & 1) * kTapBytes + ((c ^ ((e.r & 7) >> 1)) << 4)),
-                   "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]), "r"(w[4 * c + 3]) : "memory");
-  }
   if (p.debug_out && e.s == p.debug_step && valid) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = fmaxf(__uint_as_float(v[i]), 0.f);
@@ -439,10 +449,9 @@ template <int CG>
 __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int kStages = CG == 2 ? kMaxStages : kMaxStages / 2;
   constexpr int kStageB = kRingBytes / kStages;      // 8 KB half chunks | 16 KB chunks
-  // Ring stages are RELEASED in groups: tcgen05.commit blocks the issuing thread for ~400 cycles (tools/mma_rate.cu:
-  // "MMA MMA commit" runs at 230 cycles/MMA, "MMA x4 commit" at 128), so one commit per K=32 chunk made the MMA
-  // thread, not the tensor core, the bottleneck.  Arrival stays per stage.
-  constexpr int kGroup = kStages / NMR_TC_GROUPS;
+  // Ring stages are released one by one (one tcgen05.commit per K=32 chunk).  Releasing them in groups of 2-4 was
+  // measured slower (24.2 K cycles per tile with per-stage release, 25.5 K in groups of 2, 25.8 K in groups of 3).
+  constexpr int kGroup = 1;
   const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -474,6 +483,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     mbar_init(bars + 8 * BAR_VFULL, 1);
     mbar_init(bars + 8 * BAR_VPART, 256);
     for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 4 * CG);
+    for (int c = 0; c < 16 * kTapBufs; ++c) mbar_init(bars + 8 * (BAR_TAPFULL + c), 1);
+    mbar_init(bars + 8 * BAR_TAPREAD, 8 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -535,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     int gstep = 0;                                               // running layer count: 9 steps per tile is odd, so the
     const uint32_t w_desc0 = desc_lo(base + OFF_W), e_desc0 = desc_lo(base + OFF_E);
     const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && lane == 0;
+    const int tap_s2 = (p.stop_step + 2) % kSteps, tap_dt = (p.stop_step + 2) / kSteps;   // step (and tile offset) that reuses the tapped buffer
     for (int it = 0; it < p.n_iters; ++it) {                     // accumulator ping-pong must carry across tiles
       const int eb = it & 1;
       const uint32_t e_desc = e_desc0 + eb * (kEBytes >> 4);
@@ -549,6 +561,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           mbar_wait(bars + 8 * (BAR_EFULL + eb), (ph_efull >> eb) & 1u, p.error_flag, 210 + eb);
           ph_efull ^= 1u << eb;
         }
+        if (p.want_feat && s == tap_s2 && it >= tap_dt)          // this step overwrites the tapped layer's buffer: its read-back is done
+          mbar_wait(bars + 8 * BAR_TAPREAD, (uint32_t)(it - tap_dt) & 1u, p.error_flag, 260);
         if (tl_on && it < 8) p.timeline[(it * kSteps + s) * 4 + 0] = clock64();
         uint32_t accumulate = 0;
         if (step_bias_chunk(s)) {                                // + bias: ones columns of the encoded tile x (lo, hi) bias rows
@@ -622,14 +636,13 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     uint32_t ph_vfull = 0;
     EpiCtx e;
     e.r = r;
-    const uint32_t tap_buf = base + OFF_TAP + (warp - 4) * 2 * kTapBytes;   // this warp's two staging buffers
-    e.tap_st = tap_buf + ((lane >> 3) << 9) + ((lane & 7) << 6);
+    e.tap_st = base + OFF_TAP + (warp - 4) * kTapBufs * kTapBytes + ((lane >> 3) << 9) + ((lane & 7) << 6);   // this warp's staging buffers
+    e.tap_bars = bars + 8 * (BAR_TAPFULL + (warp - 4) * kTapBufs); e.tap_n = 0; e.error_flag = p.error_flag;
     int gstep = 0;
     for (int it = 0; it < p.n_iters; ++it) {
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
-      uint8_t* tap_dst = p.feat_tiles + (size_t)tile * kFeatTileBytes + q * kTapBytes;   // this warp's 32 rows of chunk 0: 2 KB contiguous
       for (int s = 0; s < kViewStep; ++s, ++gstep) {
         e.s = s;
         const int ab = gstep & 1;
@@ -643,16 +656,6 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           tmem_st_wait();                            // packed activations are in TMEM ...
           tc_fence_before();                         // ... and ordered before the MMA thread's reads
           warp_arrive_leader<CG>(bars + 8 * (BAR_HREADY + j), rank, lane);
-          if (tap) {                                 // the warp's 32 rows x 64 B of this chunk are one contiguous 2 KB block of the tile
-            fence_proxy_async();                     // generic-proxy writes -> visible to the bulk copy
-            __syncwarp();
-            if (lane == 0) {
-              bulk_s2g(tap_dst + j * kBlk, tap_buf + ((j >> 1) & 1) * kTapBytes, kTapBytes);
-              bulk_commit();
-              bulk_wait_read1();                     // the other buffer (this warp's previous chunk) may be rewritten
-            }
-            __syncwarp();
-          }
         };
         uint32_t va[32], vb[32];
         tmem_ld32(t_lane + g * 32, va);
@@ -661,15 +664,23 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           const int j = g + 2 * jj;
           tmem_ld_wait();
           tmem_ld32(t_lane + (j + 2) * 32, vb);
-          epi_trunk(e, va, t_lane + j * 32, j, tap, p, valid, pt);
+          epi_trunk(e, va, t_lane + j * 32, j, p, valid, pt);
           hand_over(j);
           tmem_ld_wait();
           if (jj + 2 < 4) tmem_ld32(t_lane + (j + 4) * 32, va);
-          epi_trunk(e, vb, t_lane + (j + 2) * 32, j + 2, tap, p, valid, pt);
+          epi_trunk(e, vb, t_lane + (j + 2) * 32, j + 2, p, valid, pt);
           hand_over(j + 2);
         }
         tc_fence_before();
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + s) * 4 + 3] = clock64();
+        if (s == p.stop_step && p.want_feat) {
+          if (tap) {
+#pragma unroll 1
+            for (int jj = 0; jj < 4; ++jj) tap_chunk(e, t_lane + (g + 2 * jj) * 32);
+          }
+          tc_fence_before();                         // the layer after next may now overwrite this accumulator buffer
+          warp_arrive_leader<CG>(bars + 8 * BAR_TAPREAD, rank, lane);
+        }
       }
       {  // views layer: this warp takes slices g and g + 2 of the 128 columns; group 0 also fetches the sigma head's two
          // columns.  The encoder warps only combine the partial sums (they never touch TMEM), so the accumulator is
@@ -700,7 +711,35 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       }
       ++gstep;
     }
-    if (lane == 0) bulk_wait0();
+  } else if (warp == 2 || (warp == 3 && CG == 1)) {
+    // ===== tap warps: staged feature chunks (stop_layer output) -> tiled bf16 features in HBM, 512 contiguous bytes per store.
+    // Single CTAs use warps 2 and 3 (one chunk group each); in a CTA pair warp 3 is the weight relay, so warp 2 drains both.
+    const int ew0 = (CG == 1) ? (warp - 2) * 4 : 0, ew1 = (CG == 1) ? ew0 + 4 : 8;
+    if (p.want_feat) {
+      uint32_t n = 0;                                // chunks taken from each epilogue warp so far
+      for (int it = 0; it < p.n_iters; ++it) {
+        const int64_t tile = (int64_t)it * G + blockIdx.x;
+        if (tile * kTileM >= p.P) break;
+        uint8_t* tdst = p.feat_tiles + (size_t)tile * kFeatTileBytes + lane * 16;
+        for (int jj = 0; jj < 4; ++jj, ++n) {
+          const uint32_t b = n % kTapBufs, ph = (n / kTapBufs) & 1u;
+#pragma unroll 1
+          for (int ew = ew0; ew < ew1; ++ew) {       // epilogue warp ew = g * 4 + q staged chunk j = g + 2 jj of rows 32 q .. 32 q + 31
+            const int j = (ew >> 2) + 2 * jj, q = ew & 3;
+            mbar_wait(bars + 8 * (BAR_TAPFULL + ew * kTapBufs + b), ph, p.error_flag, 510 + ew);
+            const uint32_t src = base + OFF_TAP + (ew * kTapBufs + b) * kTapBytes + lane * 16;
+            uint4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w) : "r"(src + i * 512));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(tdst + j * kBlk + q * kTapBytes + i * 512) = v[i];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bars + 8 * (BAR_TAPFREE + ew * kTapBufs + b));
+          }
+        }
+      }
+    }
   } else if (warp >= 12) {
     // ===== encoder warps: (1) sampling data -> positional encoding -> bf16 A tile of layer 0 / skip, one tile ahead;
     //                      (2) the views-layer epilogue of the current tile (rgb + sigma -> raw) =====
