@@ -319,7 +319,7 @@ def ncu_traffic(name):
     if found < 2:
         return {"bytes": None, "note": "no ncu capture in profiles/"}
     return {"bytes": tot, "note": "DRAM read+write of ONE fine-pass launch (4,194,304 sample rows) from profiles/" + name +
-            "; algorithmic bytes of that launch: 512 B bf16 tap features + 16 B raw per row = 2.21 GB, inputs (rays, z, 1.2 MB of weights) < 0.02 GB"}
+            "; algorithmic bytes of that launch: 512 B bf16 tap features + 16 B raw per row = 2.21 GB, inputs (rays, z, view bias, 1.2 MB of weights) 0.03 GB"}
 
 
 _REAL_STDOUT = None

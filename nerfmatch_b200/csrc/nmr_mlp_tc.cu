@@ -1,34 +1,41 @@
 // Kernel (b): the NeRF MLP (models/nerf.py:94-144) as one persistent, warp-specialised sm_100a kernel.
 //
 //   * every Linear layer is a 128 x N x K tile GEMM on the 5th-gen tensor cores: tcgen05.mma
-//     (kind::f16, bf16 operands, fp32 accumulate) issued by ONE thread, accumulators in TMEM;
+//     (kind::f16, bf16 operands, fp32 accumulate), accumulators in TMEM;
 //   * positional encoding (kernel (a)'s encode half) is fused in: four encoder warps turn ray /
-//     sample data into the bf16 A-operand tile directly in shared memory - the encoded inputs never
-//     touch HBM;
-//   * activations never leave the SM: the epilogue warps read the accumulator with tcgen05.ld, add
-//     bias, apply ReLU, round to bf16 and write the next layer's A operand in place, in the UMMA
-//     K-major 64B-swizzled layout.  The skip connection is a second K segment into the same
-//     accumulator; feature_linear (no activation) is folded into views_linears on the host
-//     (W_view_f * W_feat: one layer and 11 % of the weights disappear); the sigma head (alpha_linear) rides in
-//     that GEMM as two extra output rows (bf16 hi / lo split of its weights, fp32 accumulation); rgb
-//     (rgb_linear + sigmoid) is an fp32 dot product in the views epilogue; the [dirs | appearance] part of
-//     views_linears is a per-ray fp32 bias computed once per ray; trunk biases ride in the GEMM as well
-//     (ones columns of the encoded tile x bf16 hi / lo bias rows);
+//     sample data into the bf16 A-operand tile of layer 0 / the skip layer directly in shared memory -
+//     the encoded inputs never touch HBM;
+//   * activations never leave the tensor core's own memory: the epilogue warps read the accumulator with
+//     tcgen05.ld, apply ReLU, round to bf16 and write the packed result back INTO TMEM (tcgen05.st, over the
+//     first half of the slice's own accumulator columns), where the next layer's MMAs take it as their A
+//     operand (A-from-TMEM form of tcgen05.mma) - no shared-memory round trip, no swizzle, no proxy fence.
+//     The skip connection is a second K segment into the same accumulator; feature_linear (no activation) is
+//     folded into views_linears on the host (W_view_f * W_feat: one layer and 11 % of the weights disappear);
+//     the sigma head (alpha_linear) rides in that GEMM as two extra output rows (bf16 hi / lo split of its
+//     weights, fp32 accumulation); rgb (rgb_linear + sigmoid) is an fp32 dot product in the views epilogue;
+//     the [dirs | appearance] part of views_linears is a per-ray fp32 bias computed once per ray; trunk biases
+//     ride in the GEMM as well (ones columns of the encoded tile x bf16 hi / lo bias rows);
 //   * the accumulator is double buffered in TMEM (2 x 256 columns, alternating by layer) and the epilogue
 //     hands the next layer's operand over in 32-column chunks (one mbarrier per chunk), so the tensor core
 //     starts layer l+1 on chunk 0 while the epilogue is still draining layer l.  Eight epilogue warps
 //     (two per TMEM lane quarter, even / odd chunks) keep the hand-over faster than the MMA consumes it;
+//   * the MMA-issuing warp runs its loop CONVERGED and one elected lane issues (elect.sync): descriptors then
+//     live in uniform registers.  Inside an `if (lane == 0)` region every UTCHMMA / UTCBAR is wrapped in R2UR
+//     moves and an ELECT ... BRA.U.ANY loop, ~110 instructions per K=32 chunk on one thread, which starved
+//     the tensor core (36.6 K -> 28.0 K cycles per tile from this change alone; tools/mma_rate.cu);
 //   * weights stream from L2 through a 6-stage ring of 16 KB shared-memory stages filled by the bulk-copy
 //     (TMA) engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the host, so no tensor
-//     map is needed.  Measured on B200 (tools/smem_fill_bw.cu): L2 -> SM delivery caps at ~27 B/cycle/SM for
-//     every fill mechanism and TMA multicast does not lower it at cluster sizes <= 4, so this kernel's
-//     ceiling is the weight stream: 1.06 MB per 128-point tile;
-//   * bias / head-weight tables live in shared memory (indexed constant-bank or L1-less global loads cost
-//     the epilogue 2-3x, measured); the tapped feature tile (stop_layer) leaves as one 64 KB bulk store
-//     shared->global in the same tiled layout the compositor reads.
+//     map is needed;
+//   * the tapped feature tile (stop_layer) is read back from TMEM after the hand-over (off the critical path),
+//     staged per warp in shared memory and streamed home by two otherwise idle warps with fully coalesced
+//     stores, in the tiled layout the compositor reads;
+//   * optional CTA-pair mode (NMR_TC_CG=2, tcgen05 cta_group::2): one leader thread issues M=256 MMAs for two
+//     CTAs, each streaming only half of every weight chunk.  Correct and tested, but the cross-CTA hand-over
+//     latency costs more cycles (26.7 K vs 24.1 K per tile) than the halved L2 traffic returns.
 //
-// Warp roles (512 threads): 0 weight producer, 1 MMA issuer (+ feature-tap bulk stores), 2 TMEM allocator, 3 idle,
-// 4-7 trunk epilogue (even chunks), 8-11 trunk epilogue (odd chunks), 12-15 encoder (one tile ahead) + views epilogue.
+// Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator + tap drain, 3 tap drain (pair mode:
+// weight-arrival relay of the peer CTA), 4-7 trunk epilogue (even chunks), 8-11 trunk epilogue (odd chunks) - both
+// also run the views-layer epilogue -, 12-15 encoder (one tile ahead) + final rgb / sigma combine and raw store.
 #include <cstdlib>
 #include <cstring>
 
