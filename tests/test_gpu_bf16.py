@@ -214,3 +214,62 @@ def test_bf16_chunking_is_invisible():
     b = build_renderer(c, sd, precision="bf16", max_chunk_points=192 * 211).predict(rays, 1, 1)   # 211-ray chunks
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_full_size_properties_bf16():
+    """BASELINE config 2 (7-Scenes 480x640 = 307200 rays, 64 + 128 samples, bf16 MLP): invariants that need no oracle."""
+    c = dict(embed="normal", nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+    sd = make_state_dict(52, embed_type="normal", sigma_gain=120.0, sigma_bias=(8.0, 8.0))
+    ren = build_renderer(c, sd, precision="bf16")
+    eng = ren.engine(torch.device(DEV))
+    rays, (h, w), missed = eng.raygen(K_7SCENES, make_pose(3), 480, 640, 1)
+    assert rays.shape[0] == 307200
+    out = ren.render_rays(rays, validation=True, _intermediates=True)
+    assert all(torch.isfinite(v).all() for v in out.values())
+    wf, zf, raw = out["weights_fine"], out["z_fine"], out["raw_fine"]
+    wsum = wf.sum(-1)
+    assert (wf >= 0).all() and (wsum <= 1 + 1e-4).all()
+    assert (zf[:, 1:] >= zf[:, :-1]).all() and (zf[:, 0] >= rays[:, 6] - 1e-6).all() and (zf[:, -1] <= rays[:, 7] + 1e-6).all()
+    zc = out["z_coarse"]
+    assert (torch.searchsorted(zf.contiguous(), zc.contiguous()) < zf.shape[1]).all()       # every coarse z survives the merge
+    # compositing is the weighted sum of what the MLP produced: rgb, depth, points (classic mode: acc * o + depth * d)
+    rgb = (wf[..., None] * raw[..., :3]).sum(1)
+    assert (rgb - out["rgb_fine"].reshape(-1, 3)).abs().max() < 2e-4
+    depth = (wf * zf).sum(1)
+    assert (depth - out["depth_fine"].reshape(-1)).abs().max() < 2e-4
+    pts = wsum[:, None] * rays[:, :3] + depth[:, None] * rays[:, 3:6]
+    assert (pts - out["pts_fine"]).abs().max() < 5e-4
+    # features are convex-ish combinations of post-ReLU activations: non-negative, bounded by the row maximum times acc
+    assert (out["feat_fine"] >= 0).all()
+    again = ren.render_rays(rays, validation=True)
+    assert torch.equal(again["feat_fine"], out["feat_fine"]) and torch.equal(again["pts_fine"], out["pts_fine"])   # same bits
+
+
+def test_cta_pair_mode_same_bits():
+    """NMR_TC_CG=2 (tcgen05 cta_group::2, M=256 MMAs issued by the leader CTA of a pair) computes the same GEMMs:
+    the hi/lo bias and sigma rows, chunk order and accumulation order are identical, so the outputs agree bit for bit."""
+    from nerfmatch_b200 import _lib as L
+
+    lib = L.load()
+    embed = "mip"
+    cfg = O.RenderConfig(embed_type=embed)
+    sd = make_state_dict(65, embed_type=embed, sigma_gain=30.0, sigma_bias=1.0)
+    wts = {k: torch.from_numpy(v) for k, v in O.split_state_dict(sd, "nerf_fine.").items()}
+    P = 128 * 301 + 77                      # odd tile count: the last pair has one empty tile
+    x = (torch.rand(P, cfg.xyz_dim + cfg.dirs_dim, device=DEV, generator=torch.Generator(DEV).manual_seed(3)) * 2 - 1)
+    eng = engine(embed_type=embed, precision="bf16"); eng.set_weights(0, wts)
+    r1, f1 = eng.stage_mlp(0, x, 3)
+    if lib.nmr_set_tc_cluster(2) != 0:
+        pytest.skip("device cannot co-schedule CTA pairs")
+    try:
+        r2, f2 = eng.stage_mlp(0, x, 3)
+        c = dict(embed="normal", nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+        sd2 = make_state_dict(47, embed_type="normal", sigma_gain=60.0, sigma_bias=(4.0, 4.0))
+        rays = T(O.sample_nerf_rays(480, 640, K_7SCENES, make_pose(4), ds=6, embed_type="normal"))
+        pair = build_renderer(c, sd2, precision="bf16").predict(rays, 1, 1)
+    finally:
+        assert lib.nmr_set_tc_cluster(1) == 0
+    single = build_renderer(c, sd2, precision="bf16").predict(rays, 1, 1)
+    assert torch.equal(r1, r2) and torch.equal(f1, f2)
+    for k in single:
+        assert torch.equal(single[k], pair[k]), k
