@@ -842,39 +842,54 @@ struct VbParams {
   int mip; int fd; int dirs; int app; int dap;
   const float* wview_d; const float* bview; int64_t n; float* out;
 };
-constexpr int kVbRows = 32;   // rays (rows) per block: the transposed weight panel is staged once per block
+constexpr int kVbRows = 64;   // rays (rows) per block: the transposed weight panel is staged once per block
+constexpr int kVbBatch = 8;   // rows per inner iteration: one weight load feeds eight independent FMA chains
 __global__ void __launch_bounds__(128) view_bias_kernel(VbParams p) {
   __shared__ float wt[48][129];
-  __shared__ float de[2][48];
+  __shared__ __align__(16) float de[48][kVbBatch];   // [k][row of the batch]: encoded dirs | appearance
   const int t = threadIdx.x;
   const int nk = p.dirs + p.app;
   for (int i = t; i < kHalf * p.dap; i += 128) { int o = i / p.dap, k = i - o * p.dap; wt[k][o] = p.wview_d[i]; }
   const float bv = p.bview[t];
   const int64_t row0 = (int64_t)blockIdx.x * kVbRows;
-  for (int rr = 0; rr < kVbRows; ++rr) {
-    const int64_t row = row0 + rr;
-    if (row >= p.n) break;
-    float* d = de[rr & 1];
-    if (t < p.dap) {
+  for (int rb = 0; rb < kVbRows; rb += kVbBatch) {
+    if (row0 + rb >= p.n) break;
+    __syncthreads();                                   // previous batch consumed (first pass: weight panel staged)
+    for (int i = t; i < p.dap * kVbBatch; i += 128) {  // element (k, rr) of the batch
+      const int k = i / kVbBatch, rr = i - k * kVbBatch;
+      const int64_t row = row0 + rb + rr;
       float v = 0.f;
-      if (p.mode == 1) {
-        v = p.X[row * p.kx + p.xyzp + t];
-      } else if (t < p.dirs) {
-        const float* ry = p.rays + row * p.ncols;
-        const float* vd = (p.ncols >= 11) ? ry + 8 : ry + 3;
-        float v3[3] = {vd[0], vd[1], vd[2]};
-        v = p.mip ? pe_col(v3, p.fd, t) : fourier_col(v3, p.fd, t);
-      } else if (t < nk) {
-        int64_t id = p.ray_id ? p.ray_id[row] : 1;
-        id = id < 0 ? 0 : (id >= p.num_frames ? p.num_frames - 1 : id);
-        v = p.app_table[id * p.app + (t - p.dirs)];
+      if (row < p.n) {
+        if (p.mode == 1) {
+          v = p.X[row * p.kx + p.xyzp + k];
+        } else if (k < p.dirs) {
+          const float* ry = p.rays + row * p.ncols;
+          const float* vd = (p.ncols >= 11) ? ry + 8 : ry + 3;
+          float v3[3] = {vd[0], vd[1], vd[2]};
+          v = p.mip ? pe_col(v3, p.fd, k) : fourier_col(v3, p.fd, k);
+        } else if (k < nk) {
+          int64_t id = p.ray_id ? p.ray_id[row] : 1;
+          id = id < 0 ? 0 : (id >= p.num_frames ? p.num_frames - 1 : id);
+          v = p.app_table[id * p.app + (k - p.dirs)];
+        }
       }
-      d[t] = v;
+      de[k][rr] = v;
     }
     __syncthreads();
-    float acc = 0.f;
-    for (int k = 0; k < nk; ++k) acc = fmaf(d[k], wt[k][t], acc);
-    p.out[row * kHalf + t] = acc + bv;
+    float acc[kVbBatch];
+#pragma unroll
+    for (int rr = 0; rr < kVbBatch; ++rr) acc[rr] = 0.f;
+    for (int k = 0; k < nk; ++k) {                     // same k order as before: bit-identical sums
+      const float w = wt[k][t];
+      const float4 d0 = *reinterpret_cast<const float4*>(&de[k][0]), d1 = *reinterpret_cast<const float4*>(&de[k][4]);
+      acc[0] = fmaf(d0.x, w, acc[0]); acc[1] = fmaf(d0.y, w, acc[1]); acc[2] = fmaf(d0.z, w, acc[2]); acc[3] = fmaf(d0.w, w, acc[3]);
+      acc[4] = fmaf(d1.x, w, acc[4]); acc[5] = fmaf(d1.y, w, acc[5]); acc[6] = fmaf(d1.z, w, acc[6]); acc[7] = fmaf(d1.w, w, acc[7]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < kVbBatch; ++rr) {
+      const int64_t row = row0 + rb + rr;
+      if (row < p.n) p.out[row * kHalf + t] = acc[rr] + bv;
+    }
   }
 }
 
