@@ -74,9 +74,10 @@ def test_tc_mlp_is_deterministic():
     P = 128 * 700 + 11
     x = (torch.rand(P, cfg.xyz_dim + cfg.dirs_dim, device=DEV, generator=torch.Generator(DEV).manual_seed(2)) * 2 - 1)
     eng = engine(embed_type=embed, precision="bf16"); eng.set_weights(0, wts)
-    r1, f1 = eng.stage_mlp(0, x, 3)
-    r2, f2 = eng.stage_mlp(0, x, 3)
-    assert torch.equal(r1, r2) and torch.equal(f1, f2)
+    for stop in (3, 6, 7):                  # the tapped layer's read-back is ordered against the reuse of its TMEM buffer
+        r1, f1 = eng.stage_mlp(0, x, stop)  # two, three and (across the tile boundary) one step later
+        r2, f2 = eng.stage_mlp(0, x, stop)
+        assert torch.equal(r1, r2) and torch.equal(f1, f2), stop
 
 
 @pytest.mark.parametrize("embed,app", [("mip", False), ("normal", True)])
@@ -102,7 +103,7 @@ def test_tc_mlp_step_by_step(embed, app):
     raw, feat = eng.stage_mlp(0, T(x), 3)
     np.testing.assert_allclose(N(raw), raw_ref, rtol=2e-3, atol=2e-3)
     assert rel_l2(N(feat), bf16(outs[3])) < 2e-3
-    for stop in (-1, 0, 7):
+    for stop in (-1, 0, 5, 6, 7):
         _, f = eng.stage_mlp(0, T(x), stop)
         assert rel_l2(N(f), bf16(outs[7 if stop < 0 else stop])) < 2e-3, stop
 
