@@ -216,6 +216,13 @@ NMR_API int nmr_debug_timeline(long long* host, int n);
  * variable; NMR_ERR_INVALID for other values or when the device cannot co-schedule pairs. */
 NMR_API int nmr_set_tc_cluster(int cluster_size);
 
+/* bf16 path, linear feat_comb, >= 43 samples per ray: composite the tapped features tile by tile INSIDE the MLP kernel
+ * (one 256-vector per ray segment of a 128-point tile leaves the SM instead of 128 x 512 B of per-sample features; the
+ * compositor scales each segment by the transmittance in front of it).  On by default (NMR_TC_FUSE=0 turns it off at
+ * nmr_create); off: the MLP kernel writes tiled bf16 features and the compositor streams them, as the fp32 path and
+ * feat_comb="max" always do. */
+NMR_API int nmr_set_fuse_composite(nmr_handle* h, int enable);
+
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 NMR_API int64_t nmr_launch_count(const nmr_handle* h);
 /* Milliseconds spent in the MLP kernels of the last nmr_render* call on this handle, measured with

@@ -86,6 +86,7 @@ SYMBOLS = {
     "nmr_debug_timeline": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "nmr_launch_count": (_i64, [_vp]),
     "nmr_set_timing": (C.c_int, [_vp, C.c_int]),
+    "nmr_set_fuse_composite": (C.c_int, [_vp, C.c_int]),
     "nmr_last_stage_ms": (C.c_int, [_vp, _fp, _fp, _fp]),
 }
 

@@ -35,6 +35,7 @@ struct nmr_handle {
   nmr_config cfg;
   Dims d;
   int device = 0;
+  bool fuse_composite = true;   // bf16 path: composite the tapped features tile-locally inside the MLP kernel (NMR_TC_FUSE=0: off)
   NetF32 net[2];
   DevBuf wpool[2];
   TcNet tc[2];
@@ -145,6 +146,7 @@ extern "C" int nmr_create(const nmr_config* cfg, nmr_handle** out) {
   if (h->auto_chunk) h->cfg.max_chunk_points = (int64_t)1 << 20;
   h->d = d;
   h->device = dev;
+  if (const char* fv = getenv("NMR_TC_FUSE")) h->fuse_composite = atoi(fv) != 0;
   for (int i = 0; i < 2; ++i) { memset(&h->net[i], 0, sizeof(NetF32)); h->tc[i] = TcNet{}; }
   *out = h;
   return NMR_OK;
@@ -309,6 +311,12 @@ static void stage_end(nmr_handle* h, cudaStream_t s) {
   cudaEventRecord(h->events.back().b, s);
 }
 
+extern "C" int nmr_set_fuse_composite(nmr_handle* h, int enable) {
+  if (!h) return NMR_ERR_INVALID;
+  h->fuse_composite = enable != 0;
+  return NMR_OK;
+}
+
 extern "C" int nmr_set_timing(nmr_handle* h, int enable) {
   if (!h) return NMR_ERR_INVALID;
   h->timing = enable != 0;
@@ -468,7 +476,10 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
         NMR_LAUNCHED(h, "sample_coarse");
       }
       const float* feat = nullptr; int feat_bf16 = 0;
+      const float* partials = nullptr;
       float* raw_pass = raw;
+      const bool want_feat = pfeat && (pass == 1 ? a->feat_fine != nullptr
+                                                 : (a->feat_coarse != nullptr && !(a->flags & NMR_FLAG_SKIP_COARSE_FEAT)));
       if (!bf16) {
         EncodeParams ep{};
         ep.rays = rays; ep.n = nr; ep.ncols = a->ncols; ep.S = S; ep.d = d; ep.var_scale = c.mip_var_scale;
@@ -486,9 +497,10 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
         TcRun tr{};
         tr.rays = rays; tr.n = nr; tr.ncols = a->ncols; tr.S = S; tr.z = z; tr.ray_id = rid;
         tr.app_table = app_table; tr.num_frames = h->num_frames; tr.var_scale = c.mip_var_scale;
-        tr.stop_layer = stop; tr.want_feat = pfeat; tr.ws = h->tcws.p;
+        tr.stop_layer = stop; tr.want_feat = want_feat; tr.ws = h->tcws.p;
+        tr.fuse_composite = h->fuse_composite && !(a->flags & NMR_FLAG_FEAT_MAX);
         std::string terr; int nl = 0;
-        if (tc_run(d, h->tc[pass], tr, &raw_pass, (const void**)&feat, &nl, s, &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_run: %s", terr.c_str());
+        if (tc_run(d, h->tc[pass], tr, &raw_pass, (const void**)&feat, &partials, &nl, s, &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_run: %s", terr.c_str());
         NMR_LAUNCHED(h, "tcgen05 mlp", nl);
         feat_bf16 = 1;
         stage_end(h, s);
@@ -498,9 +510,8 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
       CompositeParams cp{};
       cp.raw = raw_pass; cp.z = z; cp.rays = rays; cp.ncols = a->ncols; cp.n = nr; cp.S = S; cp.mip = d.mip;
       cp.flags = a->flags;
-      const bool want_feat = pfeat && (pass == 1 ? a->feat_fine != nullptr
-                                                 : (a->feat_coarse != nullptr && !(a->flags & NMR_FLAG_SKIP_COARSE_FEAT)));
       cp.feats = want_feat ? feat : nullptr; cp.feats_bf16 = feat_bf16;
+      cp.partials = want_feat ? partials : nullptr;
       float* fo = pass == 0 ? a->feat_coarse : a->feat_fine;
       cp.feat_out = (want_feat && fo) ? fo + r0 * kHid : nullptr;
       float* po = pass == 0 ? a->pts_coarse : a->pts_fine;

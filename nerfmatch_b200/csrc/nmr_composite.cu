@@ -102,8 +102,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     double run = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) run = 1.0;
     for (int s = s0; s < s1; ++s) {
-      sw[s] = sa[s] * (float)run;
-      run *= (double)st[s];
+      const float T = (float)run;                  // exclusive transmittance in front of sample s
+      const double f = (double)st[s];
+      sw[s] = sa[s] * T;
+      st[s] = T;                                   // kept for the segment-wise feature compositing below
+      run *= f;
     }
     __syncwarp();
   } else {
@@ -180,8 +183,29 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     }
     if (p.weights) for (int s = lane; s < S; s += 32) p.weights[ray * S + s] = sw[s];
 
-    // ---- feature compositing: the HBM-heavy read ---------------------------------------------
-    if (p.feats && p.feat_out) {
+    // ---- feature compositing ---------------------------------------------------------------------
+    if (p.partials && p.feat_out) {
+      // The tcgen05 kernel already reduced the tapped features inside each 128-point tile with tile-local weights
+      // (one 256-vector per ray segment of the tile): scale every segment of this ray by the transmittance in front of
+      // its first sample and add.  ~1 KB per segment instead of S x 512 B of per-sample features.
+      const int64_t p0 = ray * S;
+      float a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = 0.f;
+      for (int64_t t = p0 >> 7; t <= (p0 + S - 1) >> 7; ++t) {
+        const int64_t tstart = t << 7;
+        const int sfirst = tstart > p0 ? (int)(tstart - p0) : 0;
+        const int seg = (int)(ray - tstart / S);
+        const float T = st[sfirst];
+        const float4* src = reinterpret_cast<const float4*>(p.partials + ((size_t)t * 4 + seg) * kHid) + lane * 2;
+        const float4 x = __ldcs(src), y = __ldcs(src + 1);
+        a[0] = fmaf(T, x.x, a[0]); a[1] = fmaf(T, x.y, a[1]); a[2] = fmaf(T, x.z, a[2]); a[3] = fmaf(T, x.w, a[3]);
+        a[4] = fmaf(T, y.x, a[4]); a[5] = fmaf(T, y.y, a[5]); a[6] = fmaf(T, y.z, a[6]); a[7] = fmaf(T, y.w, a[7]);
+      }
+      float4* out = reinterpret_cast<float4*>(p.feat_out + ray * kHid) + lane * 2;
+      out[0] = make_float4(a[0], a[1], a[2], a[3]);
+      out[1] = make_float4(a[4], a[5], a[6], a[7]);
+    } else if (p.feats && p.feat_out) {
       float a[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = 0.f;

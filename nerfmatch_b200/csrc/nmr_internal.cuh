@@ -92,6 +92,7 @@ struct CompositeParams {
   const float* rays_d;     // [n,3] (stage API)
   int64_t n; int S; int mip; uint32_t flags;
   const void* feats; int feats_bf16;   // [n,S,256] fp32 | bf16, or null
+  const float* partials;               // or: per 128-point tile and ray segment, locally composited features [tiles][4][256] (nmr_tc.cuh)
   const float* pts_in;     // [n,S,3] explicit points (stage API) or null -> recomputed from rays/z
   float* rgb; float* depth; float* acc; float* disp; float* weights;
   float* feat_out; float* pts_out; float* pt3d;

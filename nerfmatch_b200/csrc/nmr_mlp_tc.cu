@@ -26,16 +26,22 @@
 //   * weights stream from L2 through a 6-stage ring of 16 KB shared-memory stages filled by the bulk-copy
 //     (TMA) engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the host, so no tensor
 //     map is needed;
-//   * the tapped feature tile (stop_layer) is read back from TMEM after the hand-over (off the critical path),
-//     staged per warp in shared memory and streamed home by two otherwise idle warps with fully coalesced
-//     stores, in the tiled layout the compositor reads;
+//   * the tapped feature tile (stop_layer) is read back from TMEM after the hand-over (off the critical path) and
+//     staged in shared memory, where it waits for the tile's densities (five layers later).  The encoder warps then
+//     compute tile-local compositing weights (alpha, segmented exclusive product of 1 - alpha over the rows of the
+//     same ray) and reduce the tile to ONE 256-vector per ray segment; the compositor only scales each segment by the
+//     transmittance in front of it.  The per-sample features (512 B each, 100 GB per 480x640 view) never reach HBM.
+//     Without that fusion (fp32 consumers of the stage API, feat_comb = max, < 43 samples per ray, NMR_TC_FUSE=0)
+//     two otherwise idle warps stream the staged tile home with fully coalesced stores, in the tiled layout the
+//     compositor reads;
 //   * optional CTA-pair mode (NMR_TC_CG=2, tcgen05 cta_group::2): one leader thread issues M=256 MMAs for two
 //     CTAs, each streaming only half of every weight chunk.  Correct and tested, but the cross-CTA hand-over
 //     latency costs more cycles (26.7 K vs 24.1 K per tile) than the halved L2 traffic returns.
 //
-// Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator + tap drain, 3 tap drain (pair mode:
-// weight-arrival relay of the peer CTA), 4-7 trunk epilogue (even chunks), 8-11 trunk epilogue (odd chunks) - both
-// also run the views-layer epilogue -, 12-15 encoder (one tile ahead) + final rgb / sigma combine and raw store.
+// Warp roles (512 threads): 0 weight producer, 1 MMA issuer, 2 TMEM allocator + tap drain (unfused), 3 tap drain (pair
+// mode: weight-arrival relay of the peer CTA), 4-7 trunk epilogue (even chunks), 8-11 trunk epilogue (odd chunks) - both
+// also run the views-layer epilogue -, 12-15 encoder (one tile ahead) + final rgb / sigma combine, raw store and the
+// tile-local feature compositing.
 #include <cstdlib>
 #include <cstring>
 
@@ -68,7 +74,9 @@ constexpr int kTabFloats = 3 * kHalf;
 constexpr int OFF_PARTV = OFF_TAB + kTabFloats * 4;           // 2 tiles x 2 groups x float4 per row: (rgb partial sums, sigma) of the views epilogue
 constexpr int kVbRays = 4;                                    // rays a 128-point tile can touch when S >= 43
 constexpr int OFF_VBS = OFF_PARTV + 4 * kTileM * 16;          // 2 x [kVbRays][128] fp32: per-ray view bias of the tile (double buffered)
-constexpr int OFF_BAR = OFF_VBS + 2 * kVbRays * kHalf * 4;
+constexpr int OFF_WL = OFF_VBS + 2 * kVbRays * kHalf * 4;     // 2 x [128] fp32 local compositing weights + 2 x 4 x (value, flag) scan carries
+constexpr int OFF_BAR = OFF_WL + 2 * kTileM * 4 + 64;
+constexpr int kSeg = kVbRays;                                 // ray segments a 128-point tile can hold when S >= 43
 constexpr int kSmemBytes = OFF_BAR + 1280;                     // dynamic smem is 1024-aligned (checked at kernel entry)
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
@@ -91,6 +99,7 @@ struct TcParams {
   int64_t P; int n_iters;
   int stop_step; int want_feat;
   float* raw; uint8_t* feat_tiles;
+  float* partials;         // fused local compositing (mode 0, S >= 43): [tile][kSeg][256] fp32 instead of feat_tiles
   int debug_step; float* debug_out;
   int* error_flag;
   long long* timeline;   // optional clock64 trace of CTA 0 (NMR_TC_TIMELINE=1): [it][step][4]
@@ -722,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     // ===== tap warps: staged feature chunks (stop_layer output) -> tiled bf16 features in HBM, 512 contiguous bytes per store.
     // Single CTAs use warps 2 and 3 (one chunk group each); in a CTA pair warp 3 is the weight relay, so warp 2 drains both.
     const int ew0 = (CG == 1) ? (warp - 2) * 4 : 0, ew1 = (CG == 1) ? ew0 + 4 : 8;
-    if (p.want_feat) {
+    if (p.want_feat && !p.partials) {
       uint32_t n = 0;                                // chunks taken from each epilogue warp so far
       for (int it = 0; it < p.n_iters; ++it) {
         const int64_t tile = (int64_t)it * G + blockIdx.x;
@@ -752,7 +761,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     //                      (2) the views-layer epilogue of the current tile (rgb + sigma -> raw) =====
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    uint32_t ph_eempty = 0, ph_vpart = 0;
+    uint32_t ph_eempty = 0, ph_vpart = 0, tapn = 0;
     auto encode_tile = [&](int it) {
       const int eb = it & 1;
       const int64_t tile = (int64_t)it * G + blockIdx.x;
@@ -812,6 +821,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       const int64_t pt = tile * kTileM + r;
       mbar_wait(bars + 8 * BAR_VPART, ph_vpart, p.error_flag, 440);      // the trunk warps' partial sums are in shared memory
       ph_vpart ^= 1;
+      float sigma = 0.f;
       if (pt < p.P) {
         const float4 p0 = partv[((it & 1) * 2) * kTileM + r], p1 = partv[((it & 1) * 2 + 1) * kTileM + r];
         float4 o;
@@ -819,7 +829,104 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         o.y = 1.f / (1.f + __expf(-(p0.y + p1.y + p.brgb1)));
         o.z = 1.f / (1.f + __expf(-(p0.z + p1.z + p.brgb2)));
         o.w = p0.w + p.balpha;
+        sigma = o.w;
         *reinterpret_cast<float4*>(p.raw + pt * 4) = o;
+      }
+      if (p.partials && p.want_feat) {
+        // ---- local compositing weights of the tile (volume_render_radiance_field, render_utils.py:176-230, restricted to the
+        //      tile): alpha_r and the exclusive product of (1 - alpha + 1e-10) over the earlier rows of the SAME ray ----
+        float alpha = 0.f, f = 1.f;
+        bool head = (lane == 0 && q == 0);
+        if (pt < p.P) {
+          const int64_t ray = pt / p.S;
+          const int sidx = (int)(pt - ray * p.S);
+          head = head || sidx == 0;
+          const float* rr = p.rays + ray * p.ncols;
+          const float d0 = __ldg(rr + 3), d1 = __ldg(rr + 4), d2 = __ldg(rr + 5);
+          float dist;
+          if (p.mip) { const float* z = p.z + ray * (p.S + 1); dist = __ldg(z + sidx + 1) - __ldg(z + sidx); }
+          else dist = (sidx < p.S - 1) ? (__ldg(p.z + pt + 1) - __ldg(p.z + pt)) : 1e10f;
+          dist = dist * sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+          alpha = 1.0f - expf(-fmaxf(sigma, 0.0f) * dist);
+          f = 1.0f - alpha + 1e-10f;
+        }
+        float v = f; int flag = head ? 1 : 0;                   // segmented inclusive product scan inside the warp
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const float uv = __shfl_up_sync(0xffffffffu, v, off);
+          const int uf = __shfl_up_sync(0xffffffffu, flag, off);
+          if (lane >= off) { if (!flag) v *= uv; flag |= uf; }
+        }
+        float* scan = reinterpret_cast<float*>(gbase + OFF_WL + 2 * kTileM * 4) + (it & 1) * 8;
+        if (lane == 31) { scan[2 * q] = v; scan[2 * q + 1] = __int_as_float(flag); }
+        asm volatile("bar.sync 1, 128;" ::: "memory");              // the four encoder warps
+        float carry = 1.f;                                         // product reaching this warp from the rows before it
+        for (int w = 0; w < q; ++w) carry = __float_as_int(scan[2 * w + 1]) ? scan[2 * w] : carry * scan[2 * w];
+        const float incl = flag ? v : carry * v;
+        const float up = __shfl_up_sync(0xffffffffu, incl, 1);
+        const float excl = head ? 1.f : (lane == 0 ? carry : up);
+        float* wl = reinterpret_cast<float*>(gbase + OFF_WL) + (it & 1) * kTileM;
+        wl[r] = alpha * excl;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // ---- F[seg][c] = sum_r wl_r f[r][c] per ray segment of the tile.  The tile's tapped features have been sitting in the
+        //      staging area since layer stop_layer; warp q reduces chunks 2q and 2q + 1 (staging buffer q of all eight
+        //      epilogue warps).  The compositor then only scales each segment by the transmittance in front of it - the
+        //      per-sample features never go to HBM. ----
+        const int64_t pt0 = tile * kTileM;
+        if (pt0 < p.P) {
+          const int rows = (int)((p.P - pt0 < kTileM) ? (p.P - pt0) : kTileM);
+          const int64_t ray0 = pt0 / p.S;
+          const int nseg = (int)((pt0 + rows - 1) / p.S - ray0) + 1;
+          const int pc = lane & 3, rsub = lane >> 2;               // 16-byte piece (8 channels) of the row's 64 B; row = 8 i + rsub
+          for (int ew = 0; ew < 8; ++ew) mbar_wait(bars + 8 * (BAR_TAPFULL + ew * kTapBufs + q), tapn & 1u, p.error_flag, 510 + ew);
+#pragma unroll 1
+          for (int k = 0; k < nseg; ++k) {
+            const int64_t a64 = (ray0 + k) * p.S - pt0, b64 = a64 + p.S;
+            const int ra = a64 < 0 ? 0 : (int)a64, rb = b64 > rows ? rows : (int)b64;
+            float acc[2][8];
+#pragma unroll
+            for (int gg = 0; gg < 2; ++gg)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[gg][c] = 0.f;
+            for (int qq = ra >> 5; qq <= (rb - 1) >> 5; ++qq) {
+              const uint32_t unit = base + OFF_TAP + (qq * kTapBufs + q) * kTapBytes;     // epilogue warp (gg, qq), buffer q
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = 8 * i + rsub, row = qq * 32 + rr;
+                const float w = (row >= ra && row < rb) ? wl[row] : 0.f;
+                const uint32_t src = unit + rr * 64 + ((pc ^ ((rr & 7) >> 1)) << 4);
+#pragma unroll
+                for (int gg = 0; gg < 2; ++gg) {
+                  uint32_t v0, v1, v2, v3;
+                  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                               : "r"(src + gg * 4 * kTapBufs * kTapBytes));
+                  acc[gg][0] = fmaf(w, __uint_as_float(v0 << 16), acc[gg][0]); acc[gg][1] = fmaf(w, __uint_as_float(v0 & 0xffff0000u), acc[gg][1]);
+                  acc[gg][2] = fmaf(w, __uint_as_float(v1 << 16), acc[gg][2]); acc[gg][3] = fmaf(w, __uint_as_float(v1 & 0xffff0000u), acc[gg][3]);
+                  acc[gg][4] = fmaf(w, __uint_as_float(v2 << 16), acc[gg][4]); acc[gg][5] = fmaf(w, __uint_as_float(v2 & 0xffff0000u), acc[gg][5]);
+                  acc[gg][6] = fmaf(w, __uint_as_float(v3 << 16), acc[gg][6]); acc[gg][7] = fmaf(w, __uint_as_float(v3 & 0xffff0000u), acc[gg][7]);
+                }
+              }
+            }
+#pragma unroll
+            for (int gg = 0; gg < 2; ++gg) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                float v = acc[gg][c];
+                v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+                acc[gg][c] = v;
+              }
+              if (lane < 4) {                                      // lanes 0..3 hold the four 8-channel pieces of chunk gg + 2 q
+                float4* dst = reinterpret_cast<float4*>(p.partials + ((size_t)tile * kSeg + k) * kHid + (gg + 2 * q) * 32 + pc * 8);
+                dst[0] = make_float4(acc[gg][0], acc[gg][1], acc[gg][2], acc[gg][3]);
+                dst[1] = make_float4(acc[gg][4], acc[gg][5], acc[gg][6], acc[gg][7]);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0)
+            for (int ew = 0; ew < 8; ++ew) mbar_arrive(bars + 8 * (BAR_TAPFREE + ew * kTapBufs + q));
+          ++tapn;
+        }
       }
     }
   }
@@ -932,7 +1039,7 @@ void pack_chunk(std::vector<uint8_t>& out, const float* W, int rows, int ldw, in
 }
 
 struct TcWs {   // carved from one device allocation
-  float* raw; uint8_t* feat; float* vbias; int* error_flag; float* xfeat;
+  float* raw; uint8_t* feat; float* vbias; int* error_flag; float* xfeat; float* partials;
 };
 size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep) {
   size_t off = 0;
@@ -942,9 +1049,10 @@ size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep) {
   size_t o_feat = take((size_t)tiles * kFeatTileBytes);
   size_t o_vb = take((size_t)std::max<int64_t>(vb_rows, 1) * kHalf * sizeof(float));
   size_t o_err = take(1024);
+  size_t o_part = take((size_t)tiles * kSeg * kHid * sizeof(float));
   if (w && basep) {
     w->raw = (float*)(basep + o_raw); w->feat = basep + o_feat; w->vbias = (float*)(basep + o_vb);
-    w->error_flag = (int*)(basep + o_err);
+    w->error_flag = (int*)(basep + o_err); w->partials = (float*)(basep + o_part);
   }
   return off;
 }
@@ -1149,8 +1257,10 @@ int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* ca
   return reserve(ws, cap, need, err);
 }
 
-int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, const void** feat_out, int* launches,
-           cudaStream_t s, std::string* err) {
+static_assert(kSeg == kTcSegs, "partial layout");
+
+int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, const void** feat_out, const float** partials_out,
+           int* launches, cudaStream_t s, std::string* err) {
   if (!net.set) { *err = "weights not packed"; return -1; }
   if (r.S < 1) { *err = "S < 1"; return -1; }
   TcWs w{};
@@ -1167,8 +1277,10 @@ int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, con
   p.P = r.n * r.S;
   p.stop_step = r.stop_layer < 0 ? kLayers - 1 : r.stop_layer; p.want_feat = r.want_feat ? 1 : 0;
   p.raw = w.raw; p.feat_tiles = w.feat; p.debug_step = -1; p.debug_out = nullptr; p.error_flag = w.error_flag;
+  const bool fuse = r.fuse_composite && r.want_feat && r.S >= kTcMinFuseS;
+  p.partials = fuse ? w.partials : nullptr;
   if (launch_tc(net, p, launches, s, err) != 0) return -1;
-  *raw_out = w.raw; *feat_out = w.feat;
+  *raw_out = w.raw; *feat_out = w.feat; *partials_out = p.partials;
   return 0;
 }
 

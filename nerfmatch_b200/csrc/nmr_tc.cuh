@@ -35,6 +35,7 @@ struct TcRun {
   const int64_t* ray_id; const float* app_table; int num_frames;
   float var_scale;
   int stop_layer; bool want_feat;
+  bool fuse_composite;          // tile-local feature compositing inside the kernel (needs S >= 43, linear feat_comb)
   void* ws;
 };
 
@@ -42,10 +43,13 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
 void tc_free_net(TcNet* n);
 int64_t tc_round_chunk_rays(const Dims& d, int64_t chunk_rays, int64_t n);
 int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err);
-// Sample rows of one pass (encode + MLP fused): writes raw [n*S,4] fp32 and tiled bf16 features
-// into the workspace and returns their addresses.
-int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, const void** feat_out, int* launches,
-           cudaStream_t s, std::string* err);
+// Sample rows of one pass (encode + MLP fused): writes raw [n*S,4] fp32 and either tiled bf16 features or
+// (fuse_composite) per-tile, per-ray-segment partial composites [tiles][4][256] fp32 into the workspace and
+// returns their addresses (*partials_out is null when not fused).
+int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, const void** feat_out, const float** partials_out,
+           int* launches, cudaStream_t s, std::string* err);
+constexpr int kTcSegs = 4;      // partial vectors per 128-point tile
+constexpr int kTcMinFuseS = 43; // at most 4 rays touch a tile when S >= 43
 // Explicit padded fp32 rows X[P,kx] -> raw [P,4], feat fp32 [P,256] (stage API).  debug_steps > 0 also
 // dumps the post-activation output of step (debug_steps-1) into debug_out [P,256] (unit tests).
 int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int stop_layer, float* raw, float* feat,

@@ -159,6 +159,10 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.nmr_launch_count(self.h))
 
+    def set_fuse_composite(self, on: bool):
+        """bf16 path: tile-local feature compositing inside the MLP kernel (default on) vs. per-sample features through HBM."""
+        self.check(self.lib.nmr_set_fuse_composite(self.h, int(on)), "nmr_set_fuse_composite")
+
     def set_timing(self, on: bool):
         self.check(self.lib.nmr_set_timing(self.h, int(on)), "nmr_set_timing")
 

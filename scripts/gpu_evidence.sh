@@ -12,5 +12,6 @@ timeout 600 python bench.py --precision fp32 --steps 2 --warmup 3 --no-cpu > gpu
 B="python bench.py --steps 1 --warmup 1 --no-cpu"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $B > gpurun_out/launches.log 2>&1; echo "launch list exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:nerf_mlp_tc -s 3 -c 1 -o gpurun_out/prof_mlp -f $B > gpurun_out/prof_mlp.log 2>&1; echo "mlp capture exit $?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:composite_kernel -s 2 -c 2 -o gpurun_out/prof_composite -f $B > gpurun_out/prof_composite.log 2>&1; echo "composite capture exit $?"
+NMR_TC_FUSE=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:composite_kernel -s 2 -c 2 -o gpurun_out/prof_composite -f $B > gpurun_out/prof_composite.log 2>&1; echo "composite capture (per-sample features streamed, NMR_TC_FUSE=0) exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:composite_kernel -s 2 -c 2 -o gpurun_out/prof_composite_fused -f $B > gpurun_out/prof_composite_fused.log 2>&1; echo "composite capture (product path) exit $?"
 timeout 300 python scripts/config3.py > gpurun_out/config3.json 2> gpurun_out/config3.err; echo "config3 exit $?"; cat gpurun_out/config3.json
