@@ -88,9 +88,8 @@ static_assert(BAR_COUNT * 8 + 8 <= 1280, "barrier area");
 
 struct TcParams {
   const uint8_t* chunks;
-  const float* bias;       // [8][256] pts_linears.0..7 bias   (read through L1 with LDG.128: indexed constant-bank
-  const float* walpha;     // [256]                              loads (LDC) cost ~45 serialized cycles each - measured)
-  const float* wrgb;       // [3][128]
+  const float* wrgb;       // [3][128] rgb_linear weights (staged in shared memory: indexed constant-bank or L1-less global loads
+                           //          cost the epilogue 2-3x, measured); trunk biases and the sigma head ride in the GEMMs
   float balpha; float brgb0, brgb1, brgb2;
   const float* vbias; int vb_div;          // view bias row = point / vb_div
   // input mode 0: rays + z (fused sampling-to-encoding); mode 1: padded fp32 rows X[P,kx]
@@ -167,10 +166,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 // (waits on barriers fed by both CTAs use the ordinary try_wait: a cluster-scope acquire on every probe costs several
 // hundred cycles - measured 4x slower MMA issue - and the data the MMA reads was made visible by the arriving side's
 // tcgen05.wait::st / fence.proxy.async before its arrive)
-template <int CG>
-__device__ __forceinline__ void mbar_wait_x(uint32_t bar, uint32_t parity, int* error_flag, int code) {
-  mbar_wait(bar, parity, error_flag, code);
-}
 // one elected lane per warp signals the leader CTA's barrier (call after the warp's own fences, converged)
 template <int CG>
 __device__ __forceinline__ void warp_arrive_leader(uint32_t bar, uint32_t rank, int lane) {
@@ -1094,7 +1089,7 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
   if (!g_timeline && getenv("NMR_TC_TIMELINE")) { cudaMalloc((void**)&g_timeline, (kTlSlots) * sizeof(long long)); cudaMemset(g_timeline, 0, (kTlSlots) * sizeof(long long)); }
   p.timeline = g_timeline;
   int64_t tiles = (p.P + kTileM - 1) / kTileM;
-  p.chunks = net.chunks; p.bias = net.bias; p.walpha = net.walpha; p.wrgb = net.wrgb;
+  p.chunks = net.chunks; p.wrgb = net.wrgb;
   p.balpha = net.balpha; p.brgb0 = net.brgb[0]; p.brgb1 = net.brgb[1]; p.brgb2 = net.brgb[2];
   cudaError_t e;
   if (g_cta_group == 2) {
