@@ -326,13 +326,16 @@ __device__ __forceinline__ void encode_row_fourier(const float m[3], const RowWr
 
 template <int F>
 __device__ __forceinline__ void encode_row_ipe(const float m[3], const float var[3], const RowWriter& w) {
+  // The output order is [all sin columns | all cos columns]: the octave chain is walked once, the cos half is kept in
+  // registers (3F values, compile-time indexed) and written when its columns come up.
   float f[8];
   float sn[3], cs[3], dm[3];
+  float cosv[3 * F];
 #pragma unroll
   for (int col = 0; col < 96; ++col) {
     float v = 0.f;
-    if (col < 6 * F) {
-      const int half = col / (3 * F), jj = col % (3 * F), k = jj / 3, c = jj % 3;
+    if (col < 3 * F) {
+      const int k = col / 3, c = col % 3;
       if (c == 0) {
         if (k % 5 == 0) {
 #pragma unroll
@@ -349,7 +352,10 @@ __device__ __forceinline__ void encode_row_ipe(const float m[3], const float var
           for (int i = 0; i < 3; ++i) { float d2 = dm[i] * dm[i]; dm[i] = d2 * d2; }
         }
       }
-      v = dm[c] * (half == 0 ? sn[c] : cs[c]);
+      v = dm[c] * sn[c];
+      cosv[col] = dm[c] * cs[c];
+    } else if (col < 6 * F) {
+      v = cosv[col - 3 * F];
     } else if (col >= 94) {
       v = 1.0f;                                    // bias carrier columns
     }
@@ -700,8 +706,9 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
         const float* vbrow = nullptr;
         if (valid) {
-          const int64_t ray = pt / p.vb_div;
-          vbrow = use_vbs ? vbs + ((it & 1) * kVbRays + (int)(ray - (tile * kTileM) / p.vb_div)) * kHalf : p.vbias + ray * kHalf;
+          const uint32_t ray = (uint32_t)pt / (uint32_t)p.vb_div;
+          vbrow = use_vbs ? vbs + ((it & 1) * kVbRays + (int)(ray - (uint32_t)(tile * kTileM) / (uint32_t)p.vb_div)) * kHalf
+                          : p.vbias + (size_t)ray * kHalf;
         }
         mbar_wait(bars + 8 * BAR_VFULL, ph_vfull, p.error_flag, 430);
         ph_vfull ^= 1;
@@ -757,29 +764,38 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
     const int q = warp & 3;
     const int r = q * 32 + lane;
     uint32_t ph_eempty = 0, ph_vpart = 0, tapn = 0;
-    auto encode_tile = [&](int it) {
+    // Returns the row's sample interval times |d| (negative at the first sample of a ray), which the tile-local
+    // compositing of the same tile needs one iteration later (kept in a register: same thread, same row).
+    auto encode_tile = [&](int it) -> float {
       const int eb = it & 1;
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
       float m[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
       const float* xrow = nullptr;
+      float dist = 0.f;
       if (valid) {
         if (p.mode == 0) {
-          const int64_t ray = pt / p.S;
-          const int sidx = (int)(pt - ray * p.S);
-          const float* rr = p.rays + ray * p.ncols;
+          const uint32_t ray = (uint32_t)pt / (uint32_t)p.S;   // points per launch < 2^31 (checked on the host): 32-bit division
+          const int sidx = (int)((uint32_t)pt - ray * (uint32_t)p.S);
+          const float* rr = p.rays + (size_t)ray * p.ncols;
+          float d0, d1, d2;
           if (p.mip) {
-            const float* z = p.z + ray * (p.S + 1);
+            const float* z = p.z + (size_t)ray * (p.S + 1);
             float rl[12];
 #pragma unroll
             for (int i = 0; i < 12; ++i) rl[i] = __ldg(rr + i);
-            frustum_gaussian(rl, __ldg(z + sidx), __ldg(z + sidx + 1), p.var_scale, m, vv);
+            const float t0 = __ldg(z + sidx), t1 = __ldg(z + sidx + 1);
+            frustum_gaussian(rl, t0, t1, p.var_scale, m, vv);
+            dist = t1 - t0; d0 = rl[3]; d1 = rl[4]; d2 = rl[5];
           } else {
             const float zz = __ldg(p.z + pt);
-#pragma unroll
-            for (int c = 0; c < 3; ++c) m[c] = __ldg(rr + c) + __ldg(rr + 3 + c) * zz;
+            d0 = __ldg(rr + 3); d1 = __ldg(rr + 4); d2 = __ldg(rr + 5);
+            m[0] = __ldg(rr) + d0 * zz; m[1] = __ldg(rr + 1) + d1 * zz; m[2] = __ldg(rr + 2) + d2 * zz;
+            dist = (sidx < p.S - 1) ? (__ldg(p.z + pt + 1) - zz) : 1e10f;
           }
+          dist = dist * sqrtf(d0 * d0 + d1 * d1 + d2 * d2);          // volume_render_radiance_field: delta * |rays_d|
+          if (sidx == 0) dist = -dist;                               // marks the head of a ray segment (intervals are >= 0)
         } else {
           xrow = p.X + pt * p.kx;
         }
@@ -787,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       mbar_wait(bars + 8 * (BAR_EEMPTY + eb), ((ph_eempty >> eb) & 1u) ^ 1u, p.error_flag, 400 + eb);
       ph_eempty ^= 1u << eb;
       if (use_vbs) {                               // per-ray view bias of this tile's (<= 4) rays -> shared memory
-        const int64_t ray = (tile * kTileM) / p.vb_div + (r >> 5);   // (this buffer's last reader was our own view epilogue)
+        const int64_t ray = (int64_t)((uint32_t)(tile * kTileM) / (uint32_t)p.vb_div) + (r >> 5);   // (this buffer's last reader was our own view epilogue)
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
         if (ray * p.vb_div < p.P) t = __ldg(reinterpret_cast<const float4*>(p.vbias + ray * kHalf) + (r & 31));
         reinterpret_cast<float4*>(vbs + (eb * kVbRays + (r >> 5)) * kHalf)[r & 31] = t;
@@ -807,15 +823,21 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       }
       fence_proxy_async();
       warp_arrive_leader<CG>(bars + 8 * (BAR_EFULL + eb), rank, lane);
+      return dist;
     };
-    encode_tile(0);
+    float dist_cur = encode_tile(0);
+    const bool etl = p.timeline != nullptr && blockIdx.x == 0 && r == 0;      // encoder-side stamps of iterations 2..5
     for (int it = 0; it < p.n_iters; ++it) {
-      if (it + 1 < p.n_iters) encode_tile(it + 1);
+      if (etl && it >= 2 && it < 6) p.timeline[8 * kSteps * 4 + (it - 2) * 4 + 0] = clock64();
+      float dist_next = 0.f;
+      if (it + 1 < p.n_iters) dist_next = encode_tile(it + 1);
+      if (etl && it >= 2 && it < 6) p.timeline[8 * kSteps * 4 + (it - 2) * 4 + 1] = clock64();
       // ---- finish the views layer of tile `it`: add the eight trunk warps' partial sums, sigmoid, raw [P,4] store ----
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
       mbar_wait(bars + 8 * BAR_VPART, ph_vpart, p.error_flag, 440);      // the trunk warps' partial sums are in shared memory
       ph_vpart ^= 1;
+      if (etl && it >= 2 && it < 6) p.timeline[8 * kSteps * 4 + (it - 2) * 4 + 2] = clock64();
       float sigma = 0.f;
       if (pt < p.P) {
         const float4 p0 = partv[((it & 1) * 2) * kTileM + r], p1 = partv[((it & 1) * 2 + 1) * kTileM + r];
@@ -833,16 +855,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         float alpha = 0.f, f = 1.f;
         bool head = (lane == 0 && q == 0);
         if (pt < p.P) {
-          const int64_t ray = pt / p.S;
-          const int sidx = (int)(pt - ray * p.S);
-          head = head || sidx == 0;
-          const float* rr = p.rays + ray * p.ncols;
-          const float d0 = __ldg(rr + 3), d1 = __ldg(rr + 4), d2 = __ldg(rr + 5);
-          float dist;
-          if (p.mip) { const float* z = p.z + ray * (p.S + 1); dist = __ldg(z + sidx + 1) - __ldg(z + sidx); }
-          else dist = (sidx < p.S - 1) ? (__ldg(p.z + pt + 1) - __ldg(p.z + pt)) : 1e10f;
-          dist = dist * sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-          alpha = 1.0f - expf(-fmaxf(sigma, 0.0f) * dist);
+          head = head || dist_cur < 0.f || __float_as_uint(dist_cur) == 0x80000000u;   // (-0.0: zero-length first interval)
+          alpha = 1.0f - expf(-fmaxf(sigma, 0.0f) * fabsf(dist_cur));
           f = 1.0f - alpha + 1e-10f;
         }
         float v = f; int flag = head ? 1 : 0;                   // segmented inclusive product scan inside the warp
@@ -870,8 +884,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         const int64_t pt0 = tile * kTileM;
         if (pt0 < p.P) {
           const int rows = (int)((p.P - pt0 < kTileM) ? (p.P - pt0) : kTileM);
-          const int64_t ray0 = pt0 / p.S;
-          const int nseg = (int)((pt0 + rows - 1) / p.S - ray0) + 1;
+          const int64_t ray0 = (uint32_t)pt0 / (uint32_t)p.S;
+          const int nseg = (int)((uint32_t)(pt0 + rows - 1) / (uint32_t)p.S - (uint32_t)ray0) + 1;
           const int pc = lane & 3, rsub = lane >> 2;               // 16-byte piece (8 channels) of the row's 64 B; row = 8 i + rsub
           for (int ew = 0; ew < 8; ++ew) mbar_wait(bars + 8 * (BAR_TAPFULL + ew * kTapBufs + q), tapn & 1u, p.error_flag, 510 + ew);
 #pragma unroll 1
@@ -923,6 +937,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           ++tapn;
         }
       }
+      if (etl && it >= 2 && it < 6) p.timeline[8 * kSteps * 4 + (it - 2) * 4 + 3] = clock64();
+      dist_cur = dist_next;
     }
   }
 
@@ -1061,6 +1077,7 @@ int g_pair_ctas = 0;           // 2 x clusters of two that can be resident at on
 
 int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std::string* err) {
   static int num_sms = 0;
+  if (p.P >= ((int64_t)1 << 31)) { *err = "more than 2^31 sample points in one launch: lower max_chunk_points"; return -1; }
   if (!g_trap_host) {
     if (cudaHostAlloc((void**)&g_trap_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&g_trap_dev, g_trap_host, 0) != cudaSuccess) {

@@ -37,4 +37,8 @@ for s in range(9):
     nxt = t[1:6, s + 1, 0] if s < 8 else t[2:7, 0, 0]
     lat2 = (nxt - t0[:, s, 3]).mean()
     print(f"{s:4d} {issue:10.0f} {lat1:18.0f} {epi:9.0f} {lat2:22.0f} {issue + lat1 + epi + lat2:8.0f}")
+en = np.array(buf[8 * 9 * 4:8 * 9 * 4 + 16], dtype=np.int64).reshape(4, 4)
+print("encoder warps, iterations 2..5 (cycles): encode next tile, wait for the views partial sums, combine + local compositing")
+for i in range(4):
+    print(f"{i + 2:4d} {en[i, 1] - en[i, 0]:8d} {en[i, 2] - en[i, 1]:8d} {en[i, 3] - en[i, 2]:8d}")
 print("iteration period:", np.diff(t[1:7, 0, 0]).mean())
