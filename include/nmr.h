@@ -164,6 +164,18 @@ NMR_API int nmr_render_view(nmr_handle* h, const float* K, const float* c2w, int
                     const nmr_render_args* args, void* stream);
 
 /* ---- per-stage entry points (unit parity, ncu, and the reference's free functions) ------ */
+
+/* get_ray_dirs (nerf/render_utils.py:23-34): dirs[H,W,3] = [x, y, 1] @ inv(K)^T at integer pixel coordinates (optionally
+ * times (1,-1,-1)).  K: 9 host floats.  get_rays_c2w (:37-41): rays_d = dirs @ R^T, rays_o = t, viewdirs = rays_d / |rays_d|
+ * for n directions; c2w: 12 (or 16) host floats, row major.  prepare_rays_data (:81-104): rays[H*W, 8 (+3) (+1)] =
+ * cat(o, d, near, far[, viewdirs][, radii]); near / far are per-ray device arrays or, when null, the scalars; radii
+ * (comp_radii) need the [H,W] shape of rays_d.  All arrays are device pointers except K and c2w. */
+NMR_API int nmr_ray_dirs(nmr_handle* h, const float* K, int32_t H, int32_t W, int32_t flipped_yz, float* dirs, void* stream);
+NMR_API int nmr_rays_c2w(nmr_handle* h, const float* dirs, int64_t n, const float* c2w, float* rays_o, float* rays_d, float* viewdirs,
+                         void* stream);
+NMR_API int nmr_prepare_rays(nmr_handle* h, const float* rays_o, const float* rays_d, const float* viewdirs, const float* near,
+                             float near_s, const float* far, float far_s, int32_t H, int32_t W, int32_t comp_radii, float* rays,
+                             void* stream);
 /* sample_smth_along_rays, coarse branch (render_utils.py:267-323 -> 405-450 | 107-129).
  * mip:    z [n,S+1], pts = means [n,S,3], var [n,S,3];   normal: z [n,S], pts [n,S,3], var NULL. */
 NMR_API int nmr_stage_sample_coarse(nmr_handle* h, const float* rays, int64_t n, int32_t ncols, const float* t_rand,

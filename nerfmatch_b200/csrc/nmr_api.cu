@@ -597,6 +597,53 @@ extern "C" int nmr_raygen(nmr_handle* h, const float* K, const float* c2w, int32
   return NMR_OK;
 }
 
+// ---- the reference's ray helpers as separate device ops (render_utils.py:23-41, 81-104) ----
+extern "C" int nmr_ray_dirs(nmr_handle* h, const float* K, int32_t H, int32_t W, int32_t flipped_yz, float* dirs_dev, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!K || !dirs_dev || H < 1 || W < 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_ray_dirs: bad argument");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  RayOpsParams p{};
+  invert3x3(K, p.kinv);
+  p.H = H; p.W = W; p.flip = flipped_yz; p.out = dirs_dev;
+  launch_ray_op(0, p, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "ray_dirs");
+  return NMR_OK;
+}
+
+extern "C" int nmr_rays_c2w(nmr_handle* h, const float* dirs_dev, int64_t n, const float* c2w, float* rays_o, float* rays_d,
+                            float* viewdirs, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (n < 0 || !c2w || (n > 0 && (!dirs_dev || !rays_o || !rays_d || !viewdirs))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_rays_c2w: bad argument");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  RayOpsParams p{};
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) p.rot[3 * i + j] = c2w[4 * i + j];
+    p.org[i] = c2w[4 * i + 3];
+  }
+  p.n = n; p.dirs = dirs_dev; p.o = rays_o; p.d = rays_d; p.v = viewdirs;
+  launch_ray_op(1, p, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "rays_c2w");
+  return NMR_OK;
+}
+
+extern "C" int nmr_prepare_rays(nmr_handle* h, const float* rays_o, const float* rays_d, const float* viewdirs, const float* near_dev,
+                                float near_s, const float* far_dev, float far_s, int32_t H, int32_t W, int32_t comp_radii,
+                                float* rays_out, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (H < 1 || W < 1 || !rays_o || !rays_d || !rays_out) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_prepare_rays: bad argument");
+  if (comp_radii && H < 3) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_prepare_rays: radii need at least 3 image rows");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  RayOpsParams p{};
+  p.H = H; p.W = W; p.n = (int64_t)H * W; p.comp_radii = comp_radii;
+  p.o = const_cast<float*>(rays_o); p.d = const_cast<float*>(rays_d); p.v = const_cast<float*>(viewdirs);
+  p.near = near_dev; p.near_s = near_s; p.far = far_dev; p.far_s = far_s;
+  p.ncols = 8 + (viewdirs ? 3 : 0) + (comp_radii ? 1 : 0);
+  p.out = rays_out;
+  launch_ray_op(2, p, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "prepare_rays");
+  return NMR_OK;
+}
+
 extern "C" int nmr_render_view(nmr_handle* h, const float* K, const float* c2w, int32_t H, int32_t W, int32_t ds,
                                const nmr_render_args* args, void* stream) {
   if (!h) return NMR_ERR_INVALID;

@@ -58,6 +58,15 @@ struct RayGenParams {
 void launch_raygen(const RayGenParams& p, cudaStream_t s);
 void launch_far_fallback(float* rays, int64_t n, int ncols, const int* miss_flag, cudaStream_t s);
 
+struct RayOpsParams {     // get_ray_dirs / get_rays_c2w / prepare_rays_data as separate ops
+  float kinv[9]; float rot[9]; float org[3];
+  int H, W, flip, comp_radii, ncols; int64_t n;
+  const float* dirs; const float* near; const float* far; float near_s, far_s;
+  float* o; float* d; float* v;   // op 1: outputs; op 2: inputs (v may be null)
+  float* out;
+};
+void launch_ray_op(int op, const RayOpsParams& p, cudaStream_t s);   // 0 dirs, 1 c2w, 2 prepare
+
 struct SampleParams {
   const float* rays; int64_t n; int ncols; int64_t ray0;  // ray0: global index of first ray (Philox)
   int S; int mip; int use_disp;

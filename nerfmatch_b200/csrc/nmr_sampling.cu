@@ -76,6 +76,57 @@ void launch_far_fallback(float* rays, int64_t n, int ncols, const int* miss_flag
   far_fallback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rays, n, ncols, miss_flag);
 }
 
+// ---- the reference's ray helper functions as separate ops (render_utils.py:23-41, 81-104) -------------------
+__global__ void ray_dirs_kernel(RayOpsParams p) {          // get_ray_dirs: [x, y, 1] @ inv(K)^T (* (1,-1,-1))
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.H * p.W) return;
+  const float fx = (float)(idx % p.W), fy = (float)(idx / p.W);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float c = fmaf(fx, p.kinv[3 * i + 0], fmaf(fy, p.kinv[3 * i + 1], p.kinv[3 * i + 2]));
+    if (p.flip && i > 0) c = -c;
+    p.out[(int64_t)idx * 3 + i] = c;
+  }
+}
+__global__ void rays_c2w_kernel(RayOpsParams p) {          // get_rays_c2w: d = dirs @ R^T, o = t, viewdirs = d / |d|
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.n) return;
+  const float* c = p.dirs + idx * 3;
+  float d[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) d[i] = fmaf(c[0], p.rot[3 * i + 0], fmaf(c[1], p.rot[3 * i + 1], c[2] * p.rot[3 * i + 2]));
+  const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { p.o[idx * 3 + i] = p.org[i]; p.d[idx * 3 + i] = d[i]; p.v[idx * 3 + i] = d[i] / nrm; }
+}
+__global__ void prepare_rays_kernel(RayOpsParams p) {      // prepare_rays_data: cat(o, d, near, far[, viewdirs][, radii])
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.n) return;
+  float* r = p.out + idx * p.ncols;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { r[i] = p.o[idx * 3 + i]; r[3 + i] = p.d[idx * 3 + i]; }
+  r[6] = p.near ? p.near[idx] : p.near_s;
+  r[7] = p.far ? p.far[idx] : p.far_s;
+  int col = 8;
+  if (p.v) { r[8] = p.v[idx * 3]; r[9] = p.v[idx * 3 + 1]; r[10] = p.v[idx * 3 + 2]; col = 11; }
+  if (p.comp_radii) {                                      // |d[y] - d[y+1]| * 2 / sqrt(12); last row: the pair (H-3, H-2)
+    const int y = (int)(idx / p.W), x = (int)(idx % p.W);
+    const int ya = (y < p.H - 1) ? y : p.H - 3;
+    const float* a = p.d + ((int64_t)ya * p.W + x) * 3;
+    const float* b = a + (int64_t)p.W * 3;
+    const float e0 = a[0] - b[0], e1 = a[1] - b[1], e2 = a[2] - b[2];
+    r[col] = sqrtf(e0 * e0 + e1 * e1 + e2 * e2) * 2.0f / 3.4641016151377544f;
+  }
+}
+void launch_ray_op(int op, const RayOpsParams& p, cudaStream_t s) {
+  const int64_t n = op == 0 ? (int64_t)p.H * p.W : p.n;
+  if (n == 0) return;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (op == 0) ray_dirs_kernel<<<grid, 256, 0, s>>>(p);
+  else if (op == 1) rays_c2w_kernel<<<grid, 256, 0, s>>>(p);
+  else prepare_rays_kernel<<<grid, 256, 0, s>>>(p);
+}
+
 // ------------------------------------------------------------------------------------------
 // coarse sampling
 // ------------------------------------------------------------------------------------------

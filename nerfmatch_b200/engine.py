@@ -184,6 +184,38 @@ class Engine:
         self.check(st, "nmr_raygen")
         return rays, (h, w), bool(flag.value)
 
+    # ---- the reference's ray helper functions as device ops (render_utils.py:23-41, 81-104) ----
+    def ray_dirs(self, K, H: int, W: int, flipped_yz: bool = False):
+        Kc = (C.c_float * 9)(*[float(v) for v in torch.as_tensor(K, dtype=torch.float32).reshape(-1).tolist()])
+        dirs = torch.empty(H, W, 3, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_ray_dirs(self.h, Kc, H, W, int(bool(flipped_yz)), _ptr(dirs), self.stream())
+        self.check(st, "nmr_ray_dirs")
+        return dirs
+
+    def rays_c2w(self, dirs, c2w):
+        c2w_c = (C.c_float * 12)(*[float(v) for v in torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()[:3, :4].reshape(-1).tolist()])
+        dirs = dirs.detach().float().contiguous()
+        o, d, v = torch.empty_like(dirs), torch.empty_like(dirs), torch.empty_like(dirs)
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_rays_c2w(self.h, _ptr(dirs), dirs.numel() // 3, c2w_c, _ptr(o), _ptr(d), _ptr(v), self.stream())
+        self.check(st, "nmr_rays_c2w")
+        return o, d, v
+
+    def prepare_rays(self, rays_o, rays_d, viewdirs, near, far, H: int, W: int, comp_radii: bool):
+        f = lambda t: None if t is None else t.detach().float().contiguous()
+        rays_o, rays_d, viewdirs = f(rays_o), f(rays_d), f(viewdirs)
+        near_t = f(near) if isinstance(near, torch.Tensor) else None
+        far_t = f(far) if isinstance(far, torch.Tensor) else None
+        ncols = 8 + (3 if viewdirs is not None else 0) + (1 if comp_radii else 0)
+        out = torch.empty(H * W, ncols, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_prepare_rays(self.h, _ptr(rays_o), _ptr(rays_d), _ptr(viewdirs), _ptr(near_t),
+                                           0.0 if near_t is not None else float(near), _ptr(far_t),
+                                           0.0 if far_t is not None else float(far), H, W, int(bool(comp_radii)), _ptr(out), self.stream())
+        self.check(st, "nmr_prepare_rays")
+        return out
+
     def make_args(self, n: int, ncols: int, rays=None, ray_id=None, t_rand=None, u_jitter=None, flags=0,
                   rng_mode=L.NMR_RNG_NONE, seed=0, unnorm=None, outs: Optional[Dict[str, torch.Tensor]] = None):
         a = L.NmrRenderArgs()

@@ -36,6 +36,51 @@ def sample_nerf_rays(H, W, K, c2w, ds=8, embed_type="mip", device=None):
     return rays
 
 
+def get_K(H, W, focal_x, focal_y):
+    """render_utils.py:15-20 (a 3x3 host tensor, as in the reference)."""
+    return torch.tensor([[focal_x, 0, 0.5 * W], [0, focal_y, 0.5 * H], [0, 0, 1]], dtype=torch.float32)
+
+
+def get_ray_dirs(H, W, K, flipped_yz=False, return_xys=False, device=None):
+    """render_utils.py:23-34: camera-frame directions of all pixels, [H, W, 3] on ``device``."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    dirs = _engine(device).ray_dirs(torch.as_tensor(K).detach().cpu(), int(H), int(W), flipped_yz)
+    if return_xys:
+        ys, xs = torch.meshgrid(torch.arange(int(H), device=device), torch.arange(int(W), device=device), indexing="ij")
+        return dirs, torch.stack([xs, ys, torch.ones_like(xs)], dim=-1).float()
+    return dirs
+
+
+def get_rays_c2w(dirs, c2w):
+    """render_utils.py:37-41: (rays_o, rays_d, viewdirs), each shaped like ``dirs``."""
+    _need_cuda(dirs, "get_rays_c2w")
+    o, d, v = _engine(dirs.device).rays_c2w(dirs, c2w)
+    return o, d, v
+
+
+def prepare_rays_data(rays_o, rays_d, viewdirs=None, near=0.0, far=1.0, flatten=True, comp_radii=False):
+    """render_utils.py:81-104: rays = cat(o, d, near, far[, viewdirs][, radii]); ``rays_d`` is [H, W, 3] (the radii are
+    finite differences along the image rows) or [n, 3] without radii."""
+    _need_cuda(rays_d, "prepare_rays_data")
+    if rays_d.dim() == 3:
+        H, W = rays_d.shape[:2]
+    else:
+        if comp_radii:
+            raise ValueError("comp_radii needs rays_d of shape [H, W, 3]")
+        H, W = 1, rays_d.shape[0]
+    rays = _engine(rays_d.device).prepare_rays(rays_o, rays_d, viewdirs, near, far, H, W, comp_radii)
+    return rays if flatten else rays.reshape(*rays_d.shape[:-1], rays.shape[-1])
+
+
+def prepare_rays_from_pose(c2w, K, near=0.0, far=1.0, flipped_yz=False, comp_radii=False, device=None):
+    """render_utils.py:44-53: full-resolution rays of one pose (un-normalised rays_d, constant near / far)."""
+    K = torch.as_tensor(K).detach().cpu()
+    w, h = (K[:2, 2].numpy().astype(np.int32) * 2).tolist()
+    dirs = get_ray_dirs(h, w, K, flipped_yz=flipped_yz, device=device)
+    rays_o, rays_d, viewdirs = get_rays_c2w(dirs, torch.as_tensor(c2w))
+    return prepare_rays_data(rays_o, rays_d, viewdirs, near, far, comp_radii=comp_radii).float()
+
+
 def rays_intersect_sphere(rays_o, rays_d, r=1):
     """scene_utils.py:101-120 - tiny and only used as a host-side helper by the reference datasets;
     kept as a torch expression on whatever device the inputs live on."""

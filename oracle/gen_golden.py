@@ -360,6 +360,34 @@ def match_cases():
     return out
 
 
+def rayhelper_cases(r):
+    """get_ray_dirs / get_rays_c2w / prepare_rays_data / prepare_rays_from_pose of the reference (render_utils.py:23-53, 81-104)."""
+    import torch
+
+    from oracle.weights import make_pose
+
+    ru = sys.modules["nerfmatch.nerf.render_utils"]
+    K = np.array([[30.0, 0, 20], [0, 31.0, 12], [0, 0, 1]], np.float32)      # -> w, h = 40, 24 in prepare_rays_from_pose
+    H, W = 24, 40
+    c2w = make_pose(12)
+    out = {"K": K, "c2w": c2w, "hw": np.array([H, W])}
+    for flip in (0, 1):
+        dirs, xys = ru.get_ray_dirs(H, W, torch.from_numpy(K), flipped_yz=bool(flip), return_xys=True)
+        out[f"dirs{flip}"] = dirs.numpy()
+        out[f"xys{flip}"] = xys.numpy()
+    o, d, v = ru.get_rays_c2w(torch.from_numpy(out["dirs0"]), torch.from_numpy(c2w))
+    out["rays_o"], out["rays_d"], out["viewdirs"] = o.numpy().copy(), d.numpy(), v.numpy()
+    far = torch.from_numpy(np.linspace(0.7, 1.9, H * W, dtype=np.float32).reshape(H, W, 1))
+    out["far"] = far.numpy()
+    out["prep_mip"] = ru.prepare_rays_data(o, d, v, 0.01, far, comp_radii=True).numpy()            # tensor far, radii
+    out["prep_plain"] = ru.prepare_rays_data(o, v, v, 0.05, 2.5, comp_radii=False).numpy()          # scalars, rays_d := viewdirs
+    out["prep_nodirs"] = ru.prepare_rays_data(o, d, None, 0.0, 1.0, flatten=False, comp_radii=True).numpy()
+    for flip in (0, 1):
+        out[f"pose{flip}"] = ru.prepare_rays_from_pose(c2w, torch.from_numpy(K), 0.2, 3.0, flipped_yz=bool(flip), comp_radii=True).numpy()
+    out["pose_plain"] = ru.prepare_rays_from_pose(c2w, torch.from_numpy(K), 0.0, 1.0).numpy()
+    return out
+
+
 def main():
     r = import_reference()
     gdir = os.path.join(os.path.dirname(HERE), "tests", "golden")
@@ -374,7 +402,8 @@ def main():
         print(name, "n =", out["rays"].shape[0], "->", path, os.path.getsize(path) // 1024, "KiB",
               "acc_c %.3f acc_f %.3f" % (out["weights_coarse"].sum(-1).mean(), out["weights_fine"].sum(-1).mean()),
               "wmax_f %.3f" % out["weights_fine"].max(-1).mean(), str(out["case"]))
-    for fname, fn in (("raygen.npz", raygen_cases), ("stages.npz", stage_cases), ("match.npz", lambda _r: match_cases())):
+    for fname, fn in (("raygen.npz", raygen_cases), ("stages.npz", stage_cases), ("match.npz", lambda _r: match_cases()),
+                      ("rayhelpers.npz", rayhelper_cases)):
         if only and fname not in only:
             continue
         out = fn(r)

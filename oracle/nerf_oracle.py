@@ -106,12 +106,13 @@ def rowsum_f64(x: np.ndarray) -> np.ndarray:
 # ----------------------------------------------------------------------------------
 # ray generation   (render_utils.py:23-41, 56-104; scene_utils.py:101-120)
 # ----------------------------------------------------------------------------------
-def get_ray_dirs(H: int, W: int, K: np.ndarray) -> np.ndarray:
+def get_ray_dirs(H: int, W: int, K: np.ndarray, flipped_yz: bool = False) -> np.ndarray:
     """render_utils.py:23-34 - pixel centres are the INTEGER coordinates (no +0.5)."""
     ys, xs = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
     xys = np.stack([xs, ys, np.ones_like(xs)], axis=-1).astype(F32)
     Kinv = np.linalg.inv(K.astype(F32)).astype(F32)
-    return (xys.reshape(-1, 3) @ Kinv.T).astype(F32).reshape(H, W, 3)
+    dirs = (xys.reshape(-1, 3) @ Kinv.T).astype(F32).reshape(H, W, 3)
+    return dirs * np.array([1, -1, -1], F32) if flipped_yz else dirs
 
 
 def get_rays_c2w(dirs: np.ndarray, c2w: np.ndarray):
@@ -141,7 +142,7 @@ def prepare_rays_data(rays_o, rays_d, viewdirs, near, far, comp_radii: bool):
     H, W, _ = rays_d.shape
     near = np.broadcast_to(np.asarray(near, F32), (H, W, 1)) if np.ndim(near) == 0 else near
     far = np.broadcast_to(np.asarray(far, F32), (H, W, 1)) if np.ndim(far) == 0 else far
-    cols = [rays_o, rays_d, near.astype(F32), far.astype(F32), viewdirs]
+    cols = [rays_o, rays_d, near.astype(F32), far.astype(F32)] + ([viewdirs] if viewdirs is not None else [])
     if comp_radii:
         diff = rays_d[:-1] - rays_d[1:]
         dx = np.sqrt(np.sum(diff * diff, axis=-1, dtype=F32))
@@ -149,6 +150,14 @@ def prepare_rays_data(rays_o, rays_d, viewdirs, near, far, comp_radii: bool):
         radii = (dx[..., None] * F32(2.0) / F32(np.sqrt(12.0))).astype(F32)
         cols.append(radii)
     return np.concatenate(cols, axis=-1).astype(F32)
+
+
+def prepare_rays_from_pose(c2w, K, near=0.0, far=1.0, flipped_yz=False, comp_radii=False) -> np.ndarray:
+    """render_utils.py:44-53: full-resolution rays, rays_d NOT normalised, constant near / far."""
+    w, h = (K[:2, 2].astype(np.int32) * 2).tolist()
+    rays_o, rays_d, viewdirs = get_rays_c2w(get_ray_dirs(h, w, K, flipped_yz), c2w)
+    rays = prepare_rays_data(rays_o, rays_d, viewdirs, F32(near), F32(far), comp_radii)
+    return np.ascontiguousarray(rays.reshape(-1, rays.shape[-1]))
 
 
 def sample_nerf_rays(H, W, K, c2w, ds: int = 8, embed_type: str = "mip") -> np.ndarray:

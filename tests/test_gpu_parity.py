@@ -43,6 +43,43 @@ def test_raygen_matches_reference_and_oracle():
             np.testing.assert_allclose(got[:, 11], ref[:, 11], rtol=3e-3, atol=0)
 
 
+def test_ray_helper_functions_match_reference():
+    """The reference's free ray functions (render_utils.py:23-53, 81-104) as device ops, against reference fixtures."""
+    from nerfmatch_b200 import render_utils as RU
+
+    g = load_golden("rayhelpers.npz")
+    H, W = [int(v) for v in g["hw"]]
+    K, c2w = torch.from_numpy(g["K"]), torch.from_numpy(g["c2w"])
+
+    def check(got, ref, ncols_exact, has_radii):
+        got = N(got)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got[..., :ncols_exact], ref[..., :ncols_exact], rtol=3e-6, atol=3e-6)
+        if has_radii:
+            np.testing.assert_allclose(got[..., -1], ref[..., -1], rtol=3e-3, atol=0)
+
+    for flip in (0, 1):
+        dirs, xys = RU.get_ray_dirs(H, W, K, flipped_yz=bool(flip), return_xys=True, device=DEV)
+        np.testing.assert_allclose(N(dirs), g[f"dirs{flip}"], rtol=2e-6, atol=2e-7)
+        assert np.array_equal(N(xys), g[f"xys{flip}"])
+    o, d, v = RU.get_rays_c2w(T(g["dirs0"]), c2w)
+    assert np.array_equal(N(o), g["rays_o"])
+    np.testing.assert_allclose(N(d), g["rays_d"], rtol=3e-6, atol=3e-7)
+    np.testing.assert_allclose(N(v), g["viewdirs"], rtol=3e-6, atol=3e-7)
+    check(RU.prepare_rays_data(o, d, v, 0.01, T(g["far"]), comp_radii=True), g["prep_mip"], 11, True)
+    check(RU.prepare_rays_data(o, v, v, 0.05, 2.5, comp_radii=False), g["prep_plain"], 11, False)
+    check(RU.prepare_rays_data(o, d, None, 0.0, 1.0, flatten=False, comp_radii=True), g["prep_nodirs"], 8, True)
+    for flip in (0, 1):
+        check(RU.prepare_rays_from_pose(c2w, K, 0.2, 3.0, flipped_yz=bool(flip), comp_radii=True, device=DEV), g[f"pose{flip}"], 11, True)
+    rays = RU.prepare_rays_from_pose(g["c2w"], K, 0.0, 1.0, device=DEV)
+    check(rays, g["pose_plain"], 11, False)
+    # and such rays (un-normalised rays_d, constant near / far) render: NerfEvaluator.render_single_view (nerf_evaluator.py:404-413)
+    c = dict(embed="normal", nc=32, nf=32, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+    ren = build_renderer(c, make_state_dict(5, embed_type="normal", sigma_gain=60.0, sigma_bias=(4.0, 4.0)), precision="fp32")
+    preds = ren.predict(rays, H, W)
+    assert preds["rgb_fine"].shape == (W, H, 3) and torch.isfinite(preds["rgb_fine"]).all()
+
+
 def test_raygen_far_fallback_outside_sphere():
     eng = engine(embed_type="mip")
     c2w = make_pose(3)
