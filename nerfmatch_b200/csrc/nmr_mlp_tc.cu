@@ -53,7 +53,6 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kBlk = 8192;                 // one [128 rows x 32 bf16] block, 64B swizzle
-constexpr int kHBytes = 8 * kBlk;          // 256-wide activation tile
 constexpr int kEBytes = 3 * kBlk;          // 96-wide encoded-xyz tile
 constexpr int kStageBytes = 16384;         // one [256 x 32] weight chunk
 constexpr int kRingBytes = 6 * kStageBytes;
@@ -61,13 +60,13 @@ constexpr int kMaxStages = 12;             // CTA pair (cta_group::2): 12 stages
 constexpr int kSteps = 9;                  // 8 trunk layers + (feature_linear folded into) views_linears.0
 constexpr int kViewStep = 8;
 constexpr int kThreads = 512;
-constexpr int kTlSlots = 8 * kSteps * 4 + 64;   // clock64 trace: [it][step][4] + per-step wait breakdown of iteration 2
-constexpr int kFeatTileBytes = kHBytes;    // tiled bf16 features: 64 KB per 128 points
+constexpr int kTlSlots = 8 * kSteps * 4 + 64;   // clock64 trace: [it][step][4] of the MMA / epilogue warps + encoder-side stamps of iterations 2..5
+constexpr int kFeatTileBytes = 8 * kBlk;   // tiled bf16 features (unfused tap): 64 KB per 128 points
 
 constexpr int OFF_E = 0;
 constexpr int OFF_W = OFF_E + 2 * kEBytes;
 constexpr int OFF_TAP = OFF_W + kRingBytes;                   // feature-tap staging: 8 epilogue warps x 4 buffers x [32 rows x 64 B]
-constexpr int kTapBytes = 2048;                               // (a whole tile: the tap warps drain it in the background)
+constexpr int kTapBytes = 2048;                               // (a whole tile: it waits there for the tile's densities)
 constexpr int kTapBufs = 4;
 constexpr int OFF_TAB = OFF_TAP + 8 * kTapBufs * kTapBytes;        // fp32 table: wrgb [3][128]
 constexpr int kTabFloats = 3 * kHalf;
