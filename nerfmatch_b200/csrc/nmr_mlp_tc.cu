@@ -82,7 +82,7 @@ static_assert(kSmemBytes <= 232448, "shared memory budget");
 // barrier slots (8 bytes each) inside the OFF_BAR area
 enum { BAR_WFULL = 0, BAR_WEMPTY = BAR_WFULL + kMaxStages, BAR_PFULL = BAR_WEMPTY + kMaxStages, BAR_ACCFULL = BAR_PFULL + kMaxStages,
        BAR_HREADY = BAR_ACCFULL + 2, BAR_EFULL = BAR_HREADY + 8, BAR_EEMPTY = BAR_EFULL + 2, BAR_VEMPTY = BAR_EEMPTY + 2, BAR_VFULL = BAR_VEMPTY + 2,
-       BAR_VPART = BAR_VFULL + 1, BAR_TAPFULL = BAR_VPART + 1, BAR_TAPFREE = BAR_TAPFULL + 8 * kTapBufs, BAR_TAPREAD = BAR_TAPFREE + 8 * kTapBufs, BAR_COUNT = BAR_TAPREAD + 1 };
+       BAR_VPART = BAR_VFULL + 1, BAR_TAPFULL = BAR_VPART + 1, BAR_TAPFREE = BAR_TAPFULL + 8 * kTapBufs, BAR_TAPREAD = BAR_TAPFREE + 8 * kTapBufs, BAR_S0FULL = BAR_TAPREAD + 1, BAR_COUNT = BAR_S0FULL + 1 };
 static_assert(BAR_COUNT * 8 + 8 <= 1280, "barrier area");
 
 struct TcParams {
@@ -416,45 +416,30 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { u
 // views_linears.0 epilogue (run by the encoder warps so the trunk epilogue warps can move on to the next tile):
 // four 32-column slices: per-ray view bias + ReLU, rgb_linear + sigmoid, raw [P,4] store.
 // Slices [j0, j0 + NS) of the 128 views columns; returns this warp's partial rgb dot products.
-template <int NS, int JSTRIDE>
-__device__ __forceinline__ float4 epi_view(const float* tab, const float* vbrow, uint32_t t_lane, int j0, const TcParams& p, bool valid,
-                                           int64_t pt) {
-  uint64_t q0 = 0, q1 = 0, q2 = 0;                 // (even, odd) partial sums of the three rgb dot products
-  uint32_t va[32], vb[32];
-  tmem_ld32(t_lane + j0 * 32, va);
-  {
+// Math of one 32-column slice jj of the views layer, accumulator values already in registers.
+__device__ __forceinline__ void epi_view_slice(const float* tab, const float* vbrow, const uint32_t* v, int jj, uint64_t& q0, uint64_t& q1,
+                                               uint64_t& q2, const TcParams& p, bool valid, int64_t pt) {
+  float x[32];
+  const float4* w0 = reinterpret_cast<const float4*>(tab + jj * 32);
+  const float4* w1 = w0 + kHalf / 4;
+  const float4* w2 = w1 + kHalf / 4;
 #pragma unroll
-    for (int h = 0; h < NS; ++h) {
-      uint32_t* v = h == 0 ? va : vb;
-      tmem_ld_wait();
-      if (h + 1 < NS) tmem_ld32(t_lane + (j0 + JSTRIDE) * 32, vb);
-      const int jj = j0 + h * JSTRIDE;
-      float x[32];
-      const float4* w0 = reinterpret_cast<const float4*>(tab + jj * 32);
-      const float4* w1 = w0 + kHalf / 4;
-      const float4* w2 = w1 + kHalf / 4;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {                // packed fp32x2: bias add (FADD2), rgb dot products (FFMA2)
-        float4 t = vbrow ? reinterpret_cast<const float4*>(vbrow + jj * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        upk2(add2(pk2u(v[4 * i], v[4 * i + 1]), pk2(t.x, t.y)), x[4 * i], x[4 * i + 1]);
-        upk2(add2(pk2u(v[4 * i + 2], v[4 * i + 3]), pk2(t.z, t.w)), x[4 * i + 2], x[4 * i + 3]);
-        x[4 * i] = fmaxf(x[4 * i], 0.f); x[4 * i + 1] = fmaxf(x[4 * i + 1], 0.f);
-        x[4 * i + 2] = fmaxf(x[4 * i + 2], 0.f); x[4 * i + 3] = fmaxf(x[4 * i + 3], 0.f);
-        const uint64_t xa = pk2(x[4 * i], x[4 * i + 1]), xb = pk2(x[4 * i + 2], x[4 * i + 3]);
-        float4 a = w0[i], b = w1[i], c = w2[i];
-        q0 = fma2(xb, pk2(a.z, a.w), fma2(xa, pk2(a.x, a.y), q0));
-        q1 = fma2(xb, pk2(b.z, b.w), fma2(xa, pk2(b.x, b.y), q1));
-        q2 = fma2(xb, pk2(c.z, c.w), fma2(xa, pk2(c.x, c.y), q2));
-      }
-      if (p.debug_out && p.debug_step == kViewStep && valid) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + jj * 32 + i] = x[i];
-      }
-    }
+  for (int i = 0; i < 8; ++i) {                // packed fp32x2: bias add (FADD2), rgb dot products (FFMA2)
+    float4 t = vbrow ? reinterpret_cast<const float4*>(vbrow + jj * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    upk2(add2(pk2u(v[4 * i], v[4 * i + 1]), pk2(t.x, t.y)), x[4 * i], x[4 * i + 1]);
+    upk2(add2(pk2u(v[4 * i + 2], v[4 * i + 3]), pk2(t.z, t.w)), x[4 * i + 2], x[4 * i + 3]);
+    x[4 * i] = fmaxf(x[4 * i], 0.f); x[4 * i + 1] = fmaxf(x[4 * i + 1], 0.f);
+    x[4 * i + 2] = fmaxf(x[4 * i + 2], 0.f); x[4 * i + 3] = fmaxf(x[4 * i + 3], 0.f);
+    const uint64_t xa = pk2(x[4 * i], x[4 * i + 1]), xb = pk2(x[4 * i + 2], x[4 * i + 3]);
+    float4 a = w0[i], b = w1[i], c = w2[i];
+    q0 = fma2(xb, pk2(a.z, a.w), fma2(xa, pk2(a.x, a.y), q0));
+    q1 = fma2(xb, pk2(b.z, b.w), fma2(xa, pk2(b.x, b.y), q1));
+    q2 = fma2(xb, pk2(c.z, c.w), fma2(xa, pk2(c.x, c.y), q2));
   }
-  float c0, c1, c2, d0, d1, d2;
-  upk2(q0, c0, d0); upk2(q1, c1, d1); upk2(q2, c2, d2);
-  return make_float4(c0 + d0, c1 + d1, c2 + d2, 0.f);
+  if (p.debug_out && p.debug_step == kViewStep && valid) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + jj * 32 + i] = x[i];
+  }
 }
 
 // ---- the kernel ----------------------------------------------------------------------------
@@ -478,6 +463,9 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
   float4* partv = reinterpret_cast<float4*>(gbase + OFF_PARTV);
   float* vbs = reinterpret_cast<float*>(gbase + OFF_VBS);
   const bool use_vbs = p.vb_div >= 43;             // a tile then spans at most kVbRays rays
+  // Tile boundary: the trunk epilogue warps are busy with the views layer of tile i exactly when layer 0 of tile i+1
+  // completes, so the (otherwise idle) encoder warps run that one epilogue - unless layer 0 is the tapped layer.
+  const bool enc_step0 = !(p.want_feat && p.stop_step == 0);
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index: provably warp-uniform
   const int G = gridDim.x;
   if (base & 1023u) {                              // the swizzled UMMA tiles need a 1024-byte aligned window
@@ -497,10 +485,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       mbar_init(bars + 8 * (BAR_VEMPTY + i), 8 * CG);
     }
     mbar_init(bars + 8 * BAR_VFULL, 1);
-    mbar_init(bars + 8 * BAR_VPART, 256);
+    mbar_init(bars + 8 * BAR_VPART, 8);
     for (int c = 0; c < 8; ++c) mbar_init(bars + 8 * (BAR_HREADY + c), 4 * CG);
     for (int c = 0; c < 16 * kTapBufs; ++c) mbar_init(bars + 8 * (BAR_TAPFULL + c), 1);
     mbar_init(bars + 8 * BAR_TAPREAD, 8 * CG);
+    mbar_init(bars + 8 * BAR_S0FULL, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -631,7 +620,9 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         }
         if (tl_on && it < 8) p.timeline[(it * kSteps + s) * 4 + 1] = clock64();
         if (elect_one()) {
-          if (s < kViewStep) {
+          if (s == 0 && enc_step0) {
+            mma_commit<CG>(bars + 8 * BAR_S0FULL);                 // layer-0 accumulator complete -> encoder warps (one phase per tile)
+          } else if (s < kViewStep) {
             mma_commit<CG>(bars + 8 * (BAR_ACCFULL + ab));         // accumulator complete -> trunk epilogue
           } else {
             mma_commit<CG>(bars + 8 * BAR_VFULL);                  // views accumulator -> view epilogue (encoder warps)
@@ -663,6 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         e.s = s;
         const int ab = gstep & 1;
         const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
+        if (s == 0 && enc_step0) continue;          // layer 0's epilogue belongs to the encoder warps (below; its own barrier)
         mbar_wait(bars + 8 * (BAR_ACCFULL + ab), (ph_acc >> ab) & 1u, p.error_flag, 300 + ab);
         ph_acc ^= 1u << ab;
         tc_fence_after();
@@ -713,17 +705,24 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         ph_vfull ^= 1;
         tc_fence_after();
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 2] = clock64();
-        float4 pv = epi_view<2, 2>(tab, vbrow, t_lane, g, p, valid, pt);
-        if (g == 0) {                                // sigma = h7 . (w_hi + w_lo), accumulated in fp32 by the tensor core
-          uint32_t a0, a1;
-          asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(t_lane + kHalf) : "memory");
-          tmem_ld_wait();
-          pv.w = __uint_as_float(a0) + __uint_as_float(a1);
-        }
+        // Pull this warp's two slices (and the sigma head) into registers, release the accumulator at once - the next tile's
+        // layer 1 overwrites it - and only then do the arithmetic.
+        uint32_t va[32], vb[32], a0 = 0, a1 = 0;
+        tmem_ld32(t_lane + g * 32, va);
+        tmem_ld32(t_lane + (g + 2) * 32, vb);
+        if (g == 0) asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a0), "=r"(a1) : "r"(t_lane + kHalf) : "memory");
+        tmem_ld_wait();
         tc_fence_before();
-        partv[((it & 1) * 2 + g) * kTileM + r] = pv;
-        mbar_arrive(bars + 8 * BAR_VPART);
         warp_arrive_leader<CG>(bars + 8 * (BAR_VEMPTY + (it & 1)), rank, lane);
+        uint64_t q0 = 0, q1 = 0, q2 = 0;                 // (even, odd) partial sums of the three rgb dot products
+        epi_view_slice(tab, vbrow, va, g, q0, q1, q2, p, valid, pt);
+        epi_view_slice(tab, vbrow, vb, g + 2, q0, q1, q2, p, valid, pt);
+        float c0, c1, c2, d0, d1, d2;
+        upk2(q0, c0, d0); upk2(q1, c1, d1); upk2(q2, c2, d2);
+        // sigma = h7 . (w_hi + w_lo), accumulated in fp32 by the tensor core
+        partv[((it & 1) * 2 + g) * kTileM + r] = make_float4(c0 + d0, c1 + d1, c2 + d2, __uint_as_float(a0) + __uint_as_float(a1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 8 * BAR_VPART);
         if (p.timeline && blockIdx.x == 0 && it < 8 && et == 0) p.timeline[(it * kSteps + kViewStep) * 4 + 3] = clock64();
       }
       ++gstep;
@@ -824,13 +823,42 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       warp_arrive_leader<CG>(bars + 8 * (BAR_EFULL + eb), rank, lane);
       return dist;
     };
+    // Layer-0 epilogue of tile t (see enc_step0): this warp's quarter of the rows, all eight 32-column chunks.
+    auto step0_epilogue = [&](int t) {
+      const int g0 = t * kSteps, ab = g0 & 1;                          // layer 0 of tile t is global step 9 t
+      const int64_t pt = ((int64_t)t * G + blockIdx.x) * kTileM + r;
+      EpiCtx e0;
+      e0.r = r; e0.s = 0; e0.tap_st = 0; e0.tap_bars = 0; e0.tap_n = 0; e0.error_flag = p.error_flag;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
+      mbar_wait(bars + 8 * BAR_S0FULL, (uint32_t)t & 1u, p.error_flag, 310 + ab);
+      tc_fence_after();
+      if (p.timeline && blockIdx.x == 0 && t < 8 && r == 0) p.timeline[(t * kSteps) * 4 + 2] = clock64();
+      uint32_t va[32], vb[32];
+      tmem_ld32(t_lane, va);
+#pragma unroll 1
+      for (int j = 0; j < 8; j += 2) {
+        tmem_ld_wait();
+        tmem_ld32(t_lane + (j + 1) * 32, vb);
+        epi_trunk(e0, va, t_lane + j * 32, j, p, pt < p.P, pt);
+        tmem_st_wait(); tc_fence_before();
+        warp_arrive_leader<CG>(bars + 8 * (BAR_HREADY + j), rank, lane);
+        tmem_ld_wait();
+        if (j + 2 < 8) tmem_ld32(t_lane + (j + 2) * 32, va);
+        epi_trunk(e0, vb, t_lane + (j + 1) * 32, j + 1, p, pt < p.P, pt);
+        tmem_st_wait(); tc_fence_before();
+        warp_arrive_leader<CG>(bars + 8 * (BAR_HREADY + j + 1), rank, lane);
+      }
+      if (p.timeline && blockIdx.x == 0 && t < 8 && r == 0) p.timeline[(t * kSteps) * 4 + 3] = clock64();
+    };
     float dist_cur = encode_tile(0);
+    if (enc_step0) step0_epilogue(0);
     const bool etl = p.timeline != nullptr && blockIdx.x == 0 && r == 0;      // encoder-side stamps of iterations 2..5
     for (int it = 0; it < p.n_iters; ++it) {
       if (etl && it >= 2 && it < 6) p.timeline[8 * kSteps * 4 + (it - 2) * 4 + 0] = clock64();
       float dist_next = 0.f;
       if (it + 1 < p.n_iters) dist_next = encode_tile(it + 1);
       if (etl && it >= 2 && it < 6) p.timeline[8 * kSteps * 4 + (it - 2) * 4 + 1] = clock64();
+      if (enc_step0 && it + 1 < p.n_iters) step0_epilogue(it + 1);
       // ---- finish the views layer of tile `it`: add the eight trunk warps' partial sums, sigmoid, raw [P,4] store ----
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
