@@ -440,7 +440,7 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
   const nmr_config& c = h->cfg;
   const bool bf16 = c.precision == NMR_PREC_BF16;
   const int smax = std::max(d.sc, d.sf);
-  // fp32 path: ~3.7 KB of workspace per point; bf16 path: 0.5 KB (tiled features) -> larger chunks
+  // fp32 path: ~3.7 KB of workspace per point; bf16 path: ~0.6 KB (raw, tiled features for the unfused tap, partials) -> larger chunks
   const int64_t max_points = (bf16 && h->auto_chunk) ? ((int64_t)1 << 22) : c.max_chunk_points;
   int64_t chunk_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, max_points / smax));
   if (bf16) chunk_rays = tc_round_chunk_rays(d, chunk_rays, a->n);

@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = 0.f;
       if (p.feats_bf16) {
-        // tiled layout written by the tcgen05 kernel's bulk store: 64 KB per 128 points, eight
+        // tiled layout written by the tcgen05 kernel's tap warps (fusion off): 64 KB per 128 points, eight
         // [128 x 32] blocks, rows of 64 B with the UMMA 64B swizzle.  Lane l reads the 16-byte chunk
         // holding channels [8l, 8l+8) of the sample's row.
         const uint8_t* fb = reinterpret_cast<const uint8_t*>(p.feats);
