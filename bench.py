@@ -212,9 +212,9 @@ def run_ours(args):
 
     def step_host():
         eng.render_host(hargs)
-        if world > 1:   # host results of every rank travel to rank 0 over NVLink: re-upload, gather
+        if world > 1:   # the matcher's rank also needs the other ranks' feature maps: gather the device-side staging copies
             for k in ("feat_fine", "pt3d"):
-                outs_back[k].copy_(outs_h[k], non_blocking=True)
+                eng.copy_host_staging(k, outs_back[k])
             gather_to_matcher(outs_back)
 
     def barrier():

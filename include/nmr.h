@@ -158,6 +158,11 @@ NMR_API int nmr_render(nmr_handle* h, const nmr_render_args* args, void* stream)
  * copies the requested outputs device->host on `stream`, then synchronises.  This is the
  * end-to-end entry bench.py times as `e2e`. */
 NMR_API int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void* stream);
+/* After nmr_render_host the device-side staging copy of every requested output is still resident: copy output
+ * `output_index` (position among the output pointers of nmr_render_args: 0 feat_coarse, 1 feat_fine, 2 pts_coarse,
+ * 3 pts_fine, 4 rgb_coarse, 5 rgb_fine, 6 depth_coarse, 7 depth_fine, 8 pt3d, ...) device-to-device into dst, e.g. to feed
+ * the NCCL gather of the rendered feature map without re-uploading it.  Valid until the next nmr_render_host. */
+NMR_API int nmr_copy_host_staging(nmr_handle* h, int32_t output_index, void* dst_dev, size_t bytes, void* stream);
 /* NerfRenderer.render_novel_view (renderer.py:315-333) for a HOST pose: raygen + render +
  * un-normalisation; outputs in `args` are device pointers, args->rays is ignored. */
 NMR_API int nmr_render_view(nmr_handle* h, const float* K, const float* c2w, int32_t H, int32_t W, int32_t ds,

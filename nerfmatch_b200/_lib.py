@@ -88,6 +88,7 @@ SYMBOLS = {
     "nmr_ray_dirs": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "nmr_rays_c2w": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp]),
     "nmr_prepare_rays": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_float, _vp, C.c_float, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "nmr_copy_host_staging": (C.c_int, [_vp, C.c_int32, _vp, C.c_size_t, _vp]),
     "nmr_set_timing": (C.c_int, [_vp, C.c_int]),
     "nmr_set_fuse_composite": (C.c_int, [_vp, C.c_int]),
     "nmr_last_stage_ms": (C.c_int, [_vp, _fp, _fp, _fp]),

@@ -311,6 +311,16 @@ static void stage_end(nmr_handle* h, cudaStream_t s) {
   cudaEventRecord(h->events.back().b, s);
 }
 
+extern "C" int nmr_copy_host_staging(nmr_handle* h, int32_t output_index, void* dst_dev, size_t bytes, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (output_index < 0 || output_index >= 16 || !dst_dev) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_copy_host_staging: bad argument");
+  DevBuf& b = h->stage[4 + output_index];            // slots 0..3 are the inputs of nmr_render_host
+  if (!b.p || b.cap < bytes) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_copy_host_staging: output %d was not produced by the last nmr_render_host (or is smaller)", output_index);
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  NMR_CUDA(h, cudaMemcpyAsync(dst_dev, b.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return NMR_OK;
+}
+
 extern "C" int nmr_set_fuse_composite(nmr_handle* h, int enable) {
   if (!h) return NMR_ERR_INVALID;
   h->fuse_composite = enable != 0;

@@ -159,6 +159,15 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.nmr_launch_count(self.h))
 
+    HOST_OUTPUTS = ("feat_coarse", "feat_fine", "pts_coarse", "pts_fine", "rgb_coarse", "rgb_fine", "depth_coarse", "depth_fine", "pt3d")
+
+    def copy_host_staging(self, name: str, dst: torch.Tensor):
+        """Device copy of output ``name`` of the last render_host call -> ``dst`` (device tensor), device to device."""
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_copy_host_staging(self.h, self.HOST_OUTPUTS.index(name), _ptr(dst), dst.numel() * dst.element_size(), self.stream())
+        self.check(st, "nmr_copy_host_staging")
+        return dst
+
     def set_fuse_composite(self, on: bool):
         """bf16 path: tile-local feature compositing inside the MLP kernel (default on) vs. per-sample features through HBM."""
         self.check(self.lib.nmr_set_fuse_composite(self.h, int(on)), "nmr_set_fuse_composite")

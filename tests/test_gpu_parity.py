@@ -300,6 +300,10 @@ def test_render_host_and_view_entry_points():
     eng.render_host(args)
     for k, v in outs.items():
         assert np.array_equal(v.numpy(), dev[k]), k
+    # the device-side staging copies stay resident for a following collective (bench.py, N > 1)
+    for k in ("feat_fine", "pt3d", "depth_coarse"):
+        mirror = eng.copy_host_staging(k, torch.empty(outs[k].shape, device=DEV))
+        assert np.array_equal(N(mirror), outs[k].numpy()), k
     # render_novel_view: device ray generation from the pose, same draws via the torch generator
     un = g["unnorm_scene"]
     c2w_world = un @ g["c2w"]
