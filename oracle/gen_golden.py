@@ -388,6 +388,87 @@ def rayhelper_cases(r):
     return out
 
 
+def inerf_cases(r):
+    """One iNeRF refinement step's differentiable graph (nerfmatch_evaluator.py:236-285 ray generation from the pose,
+    :336-424 coarse pass without grad, fine pass with grad, white-background volume rendering, MSE photometric loss),
+    built from the reference's own functions under torch autograd; the fixture holds the loss and d loss / d pose.
+    (The evaluator module itself needs pytorch_lightning / pycolmap / kornia, so its few glue lines are restated.)"""
+    import torch
+
+    from oracle.weights import K_7SCENES, make_pose, make_state_dict
+
+    torch.set_grad_enabled(True)
+    out = {}
+    for tag, seed, gain, bias in (("smooth", 21, 60.0, 4.0), ("peaky", 22, 400.0, 20.0)):
+        torch.manual_seed(0)
+        ren = r.NerfRenderer(ref_config("mip", 128, 128, False, True), num_frames=None, training=False, stop_layer=3).eval()
+        sd = make_state_dict(seed, embed_type="mip", sigma_gain=gain, sigma_bias=(bias, bias))
+        ren.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        for prm in ren.parameters():
+            prm.requires_grad_(False)
+        H, W, ds = 480, 640, 40
+        K = torch.from_numpy(K_7SCENES)
+        cam_pose = torch.from_numpy(make_pose(seed).astype(np.float32))[None].clone().requires_grad_(True)
+        # gen_rays (nerfmatch_evaluator.py:236-285)
+        ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        xys = torch.stack([xs, ys, torch.ones_like(xs)], dim=-1).float()
+        dirs = xys @ torch.linalg.inv(K).T
+        cam_centers = cam_pose[:, None, None, :3, 3].expand(-1, H, W, -1)[0]
+        cam_raydir = torch.matmul(cam_pose[:, None, None, :3, :3], dirs.unsqueeze(-1))[0, :, :, :, 0]
+        viewdirs = cam_raydir / cam_raydir.norm(dim=-1, keepdim=True)
+        nears = torch.tensor(0.01).view(1, 1, 1).expand(H, W, -1)
+        fars = sys.modules["nerfmatch.nerf.scene_utils"].rays_intersect_sphere(cam_centers.reshape(-1, 3), viewdirs.reshape(-1, 3), r=1).view(H, W, -1)
+        dx = torch.sqrt(torch.sum((viewdirs[:-1] - viewdirs[1:]) ** 2, -1))
+        dx = torch.cat([dx, dx[-2:-1]], 0)
+        radii = dx[..., None] * 2 / np.sqrt(12)
+        rays = torch.cat((cam_centers, viewdirs, nears, fars, viewdirs, radii), dim=-1)
+        rays = rays[ds // 2 :: ds, ds // 2 :: ds].reshape((-1, rays.shape[-1]))
+        n = rays.shape[0]
+        g = torch.Generator().manual_seed(seed)
+        img_ds = torch.rand(n, 3, generator=g)
+        # the two passes (nerfmatch_evaluator.py:345-420)
+        rays_d, viewd = rays[..., 3:6], rays[..., 8:11]
+        z_vals, weights = None, None
+        torch.manual_seed(7)
+        keep = {}
+        for key, model in (("coarse", ren.nerf_coarse), ("fine", ren.nerf_fine)):
+            pts, z_vals = r.sample_smth_along_rays(rays.detach(), num_pts=128, z_vals=z_vals, weights=weights, use_disp=False, perturb=False,
+                                                   embed_type="mip", model_type=key, scale_var=1)
+            vflat = viewd[..., None, :].expand(*pts[0].shape[:-1], 3)
+            mu = (z_vals[..., :-1] + z_vals[..., 1:]) / 2
+            hw = (z_vals[..., :-1] - z_vals[..., 1:]) / 2
+            eps = torch.tensor(torch.finfo(torch.float32).eps)
+            t_mean = mu + (2 * mu * hw**2) / torch.maximum(eps, 3 * mu**2 + hw**2)
+            var_flat = pts[1].contiguous().view(-1, 3)
+            pts_z = rays[:, None, :3].expand(*pts[0].shape[:-1], 3) + t_mean[:, :, None] * vflat
+            inputs = ren.xyz_encoder(pts_z.contiguous().view(-1, 3), y=var_flat)[0]
+            inputs = torch.cat((inputs, ren.dirs_encoder(vflat.contiguous().view(-1, 3))), dim=-1)
+            if key == "coarse":
+                with torch.no_grad():
+                    raw_outs, feats = model.forward(inputs, ret_pfeat=1, val=True)
+            else:
+                inputs.retain_grad()
+                raw_outs, feats = model.forward(inputs, ret_pfeat=1, val=True)
+                raw_outs.retain_grad()
+                keep.update(inputs=inputs, raw=raw_outs, z=z_vals.detach().clone(), var=pts[1].detach().clone())
+            raw_outs = raw_outs.view(-1, 128, raw_outs.shape[-1])
+            rgb_map, _, acc_map, weights, depth_map, _ = r.volume_render_radiance_field(
+                raw_outs, z_vals, rays_d, noise_std=0.0, white_bg=True, embed_type="mip", input_dim=4)
+        loss = torch.nn.MSELoss(reduction="mean")(rgb_map, img_ds)
+        loss.backward()
+        out.update({
+            f"{tag}.seed_gain_bias": np.array([seed, gain, bias], np.float64), f"{tag}.pose": cam_pose.detach()[0].numpy(),
+            f"{tag}.hwds": np.array([H, W, ds]), f"{tag}.K": K.numpy(), f"{tag}.img": img_ds.numpy(),
+            f"{tag}.z_fine": keep["z"].numpy(), f"{tag}.var_fine": keep["var"].numpy(), f"{tag}.rays": rays.detach().numpy(),
+            f"{tag}.rgb_map": rgb_map.detach().numpy(), f"{tag}.loss": np.array(loss.item(), np.float64),
+            f"{tag}.grad_pose": cam_pose.grad[0].numpy(), f"{tag}.grad_raw": keep["raw"].grad.numpy(),
+            f"{tag}.grad_inputs_head": keep["inputs"].grad.numpy()[:1024],     # first 8 rays' samples
+        })
+        print(tag, "loss", loss.item(), "|grad|", cam_pose.grad.abs().max().item(), "acc", acc_map.mean().item())
+    torch.set_grad_enabled(False)
+    return out
+
+
 def main():
     r = import_reference()
     gdir = os.path.join(os.path.dirname(HERE), "tests", "golden")
@@ -403,7 +484,7 @@ def main():
               "acc_c %.3f acc_f %.3f" % (out["weights_coarse"].sum(-1).mean(), out["weights_fine"].sum(-1).mean()),
               "wmax_f %.3f" % out["weights_fine"].max(-1).mean(), str(out["case"]))
     for fname, fn in (("raygen.npz", raygen_cases), ("stages.npz", stage_cases), ("match.npz", lambda _r: match_cases()),
-                      ("rayhelpers.npz", rayhelper_cases)):
+                      ("rayhelpers.npz", rayhelper_cases), ("inerf_grad.npz", inerf_cases)):
         if only and fname not in only:
             continue
         out = fn(r)
