@@ -98,7 +98,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": config_block(embed, "fp32-cpu"),
+        "config": dict(config_block(embed, "fp32-cpu", n_sample),
+                       sample=f"each step renders {n_sample} rays of the {H}x{W} view (bounded CPU sample of the same workload); the rate is per ray"),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": f"{n_sample} rays of the {H}x{W} view per step (numpy oracle port of nerfmatch/nerf, one thread per core)"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -107,10 +108,10 @@ def run_reference(args):
     emit(line)
 
 
-def config_block(embed, precision):
+def config_block(embed, precision, rays_per_step=H * W):
     return {"workload": f"7-Scenes {H}x{W} full-res feature render, {embed} embedding, 64 coarse + 128 fine samples "
                         f"({256 if embed == 'normal' else 128} MLP evals/ray), stop_layer=3, random-init weights",
-            "rays_per_step_per_gpu": H * W, "precision": precision, "parallelism": "rays sharded by view (one view per GPU per step), weights replicated, feat_fine + pt3d gathered to rank 0 (NCCL) when N > 1",
+            "rays_per_step_per_gpu": rays_per_step, "precision": precision, "parallelism": "rays sharded by view (one view per GPU per step), weights replicated, feat_fine + pt3d gathered to rank 0 (NCCL) when N > 1",
             "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set is also >> 126 MB"}
 
 

@@ -26,7 +26,9 @@ def _save(path: str, item: Dict[str, np.ndarray]):
 def cache_scene_pts(renderer, frames: Sequence[Dict], scene_dir: str, img_hw, unnorm_scene, downsample: int = 8,
                     feat_comb: str = "lin", views_per_batch: int = 8, device=None, writer_threads: int = 2,
                     rank: int = 0, world_size: int = 1) -> List[str]:
-    """Render and cache ``frames`` (each: dict(img_idx=str, K=[3,3], c2w=[4,4] world pose)).
+    """Render and cache ``frames`` (each: dict(img_idx=str, K=[3,3], c2w=[4,4] world pose[, ts=int])).  ``ts`` is the frame's
+    appearance-embedding id (the reference passes ``batch['ts']`` as ``ray_id``, nerf_evaluator.py:343-349); without it the
+    renderer's default id 1 is used, as ``render_novel_view`` does.
 
     With ``world_size`` > 1 the frames are dealt round-robin to the ranks (no collective: every rank writes its own
     files).  Returns the paths written by this rank."""
@@ -58,13 +60,15 @@ def cache_scene_pts(renderer, frames: Sequence[Dict], scene_dir: str, img_hw, un
 
     for b0 in range(0, len(mine), views_per_batch):
         batch = mine[b0:b0 + views_per_batch]
-        rays = []
+        rays, ids = [], []
         for f in batch:
             c2w_n = un_inv @ torch.as_tensor(np.asarray(f["c2w"])).float().cpu()
             r, (h, w), _ = eng.raygen(torch.as_tensor(np.asarray(f["K"])).float().cpu(), c2w_n, H, W, downsample)
             rays.append(r)
+            ids.append(torch.full((r.shape[0],), int(f.get("ts", 1)), dtype=torch.int64, device=device))
         per_view = rays[0].shape[0]
-        preds = renderer.render_rays(torch.cat(rays, 0), validation=True, _unnorm=un)
+        ray_id = torch.cat(ids, 0) if getattr(renderer, "appearance_embedding", False) else None
+        preds = renderer.render_rays(torch.cat(rays, 0), ray_id=ray_id, validation=True, _unnorm=un)
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(device))
         host = {}

@@ -50,7 +50,8 @@ struct nmr_handle {
   bool timing = false;
   bool auto_chunk = true;
   cudaStream_t copy_stream = nullptr;   // nmr_render_host: device->host copies overlap the next chunk's kernels
-  std::vector<StageEvent> events;
+  std::vector<StageEvent> events;       // recorded, not yet read by nmr_last_stage_ms
+  std::vector<StageEvent> event_pool;   // created once, re-used (no event creation inside a timed render after warm-up)
 };
 
 #define NMR_FAIL(h, code, ...)                                   \
@@ -155,6 +156,7 @@ extern "C" int nmr_create(const nmr_config* cfg, nmr_handle** out) {
 extern "C" void nmr_destroy(nmr_handle* h) {
   if (!h) return;
   for (auto& ev : h->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  for (auto& ev : h->event_pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[i]); }
   h->app.release(); h->X.release(); h->raw.release(); h->zc.release(); h->zf.release(); h->misc.release();
@@ -299,15 +301,28 @@ static int ensure_workspace(nmr_handle* h, int64_t rays, int64_t points) {
   return NMR_OK;
 }
 
+constexpr size_t kMaxPendingStageEvents = 4096;   // timing left on and never read: the oldest records are recycled
 static void stage_begin(nmr_handle* h, int stage, cudaStream_t s) {
   if (!h->timing) return;
-  StageEvent ev; ev.stage = stage;
-  cudaEventCreate(&ev.a); cudaEventCreate(&ev.b);
+  if (h->events.size() >= kMaxPendingStageEvents) {
+    h->event_pool.insert(h->event_pool.end(), h->events.begin(), h->events.begin() + kMaxPendingStageEvents / 2);
+    h->events.erase(h->events.begin(), h->events.begin() + kMaxPendingStageEvents / 2);
+  }
+  StageEvent ev;
+  if (!h->event_pool.empty()) {
+    ev = h->event_pool.back(); h->event_pool.pop_back();
+  } else if (cudaEventCreate(&ev.a) != cudaSuccess || cudaEventCreate(&ev.b) != cudaSuccess) {
+    cudaGetLastError();
+    return;                                        // no event, no sample: stage_end checks the marker below
+  }
+  ev.stage = stage;
   cudaEventRecord(ev.a, s);
   h->events.push_back(ev);
+  h->events.back().stage = stage | 0x100;          // open: stage_end closes it
 }
 static void stage_end(nmr_handle* h, cudaStream_t s) {
-  if (!h->timing) return;
+  if (!h->timing || h->events.empty() || !(h->events.back().stage & 0x100)) return;
+  h->events.back().stage &= 0xff;
   cudaEventRecord(h->events.back().b, s);
 }
 
@@ -336,14 +351,16 @@ extern "C" int nmr_set_timing(nmr_handle* h, int enable) {
 extern "C" int nmr_last_stage_ms(nmr_handle* h, float* sample_ms, float* mlp_ms, float* composite_ms) {
   if (!h) return NMR_ERR_INVALID;
   float acc[3] = {0, 0, 0};
+  cudaError_t first = cudaSuccess;
   for (auto& ev : h->events) {
-    NMR_CUDA(h, cudaEventSynchronize(ev.b));
     float ms = 0;
-    NMR_CUDA(h, cudaEventElapsedTime(&ms, ev.a, ev.b));
-    acc[ev.stage] += ms;
-    cudaEventDestroy(ev.a); cudaEventDestroy(ev.b);
+    cudaError_t e = (ev.stage & 0x100) ? cudaErrorNotReady : cudaEventSynchronize(ev.b);   // (an open record has no end event)
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev.a, ev.b);
+    if (e == cudaSuccess) acc[ev.stage & 3] += ms; else if (first == cudaSuccess && !(ev.stage & 0x100)) first = e;
+    h->event_pool.push_back(ev);
   }
   h->events.clear();
+  if (first != cudaSuccess) { cudaGetLastError(); NMR_FAIL(h, NMR_ERR_CUDA, "nmr_last_stage_ms: %s", cudaGetErrorString(first)); }
   if (sample_ms) *sample_ms = acc[0];
   if (mlp_ms) *mlp_ms = acc[1];
   if (composite_ms) *composite_ms = acc[2];
@@ -453,7 +470,6 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
   // fp32 path: ~3.7 KB of workspace per point; bf16 path: ~0.6 KB (raw, tiled features for the unfused tap, partials) -> larger chunks
   const int64_t max_points = (bf16 && h->auto_chunk) ? ((int64_t)1 << 22) : c.max_chunk_points;
   int64_t chunk_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, max_points / smax));
-  if (bf16) chunk_rays = tc_round_chunk_rays(d, chunk_rays, a->n);
   if ((r = ensure_workspace(h, chunk_rays, bf16 ? 0 : chunk_rays * smax)) != NMR_OK) return r;
   if (bf16) {
     std::string terr;
@@ -598,6 +614,11 @@ extern "C" int nmr_raygen(nmr_handle* h, const float* K, const float* c2w, int32
   NMR_CUDA(h, cudaMemsetAsync(p.miss_flag, 0, sizeof(int), s));
   launch_raygen(p, s);
   NMR_LAUNCHED(h, "raygen");
+  const float on = p.org[0] * p.org[0] + p.org[1] * p.org[1] + p.org[2] * p.org[2];
+  if (ds > 1 && !(1.0f - on >= 0.0f)) {          // camera outside the sphere: pixels the subsampling skips can miss too
+    launch_raygen_miss(p, s);
+    NMR_LAUNCHED(h, "raygen_miss");
+  }
   launch_far_fallback(rays_dev, (int64_t)p.h * p.w, h->d.mip ? 12 : 11, p.miss_flag, s);
   NMR_LAUNCHED(h, "far_fallback");
   if (far_fallback) {
@@ -683,43 +704,49 @@ extern "C" int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void*
   int slot = 0;
   if (!h->copy_stream) NMR_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   HostSink sink;
-  auto in = [&](const void* host, size_t bytes) -> void* {
+  cudaError_t stage_err = cudaSuccess;          // first staging failure (allocation or copy) of any buffer
+  const char* stage_what = "";
+  auto in = [&](const void* host, size_t bytes, const char* what) -> void* {
     DevBuf& b = h->stage[slot++];
     if (!host || bytes == 0) return nullptr;
-    if (b.reserve(bytes) != cudaSuccess) return nullptr;
-    cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, s);
+    cudaError_t e = b.reserve(bytes);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { if (stage_err == cudaSuccess) { stage_err = e; stage_what = what; } return nullptr; }
     return b.p;
   };
-  auto out = [&](void* host, size_t bytes) -> void* {
+  auto out = [&](void* host, size_t bytes, const char* what) -> void* {
     DevBuf& b = h->stage[slot++];
     if (!host || bytes == 0 || n == 0) return nullptr;
-    if (b.reserve(bytes) != cudaSuccess) return nullptr;
+    cudaError_t e = b.reserve(bytes);
+    if (e != cudaSuccess) { if (stage_err == cudaSuccess) { stage_err = e; stage_what = what; } return nullptr; }
     sink.items.push_back({(char*)host, (const char*)b.p, bytes / (size_t)n});
     return b.p;
   };
   const size_t f = sizeof(float);
-  a.rays = (const float*)in(args->rays, (size_t)n * args->ncols * f);
-  a.ray_id = (const int64_t*)in(args->ray_id, (size_t)n * sizeof(int64_t));
-  a.t_rand = (const float*)in(args->t_rand, (size_t)n * (d.sc + 1) * f);
-  a.u_jitter = (const float*)in(args->u_jitter, (size_t)n * (d.sc + 1) * f);
-  a.feat_coarse = (float*)out(args->feat_coarse, (size_t)n * kHid * f);
-  a.feat_fine = (float*)out(args->feat_fine, (size_t)n * kHid * f);
-  a.pts_coarse = (float*)out(args->pts_coarse, (size_t)n * 3 * f);
-  a.pts_fine = (float*)out(args->pts_fine, (size_t)n * 3 * f);
-  a.rgb_coarse = (float*)out(args->rgb_coarse, (size_t)n * 3 * f);
-  a.rgb_fine = (float*)out(args->rgb_fine, (size_t)n * 3 * f);
-  a.depth_coarse = (float*)out(args->depth_coarse, (size_t)n * f);
-  a.depth_fine = (float*)out(args->depth_fine, (size_t)n * f);
-  a.pt3d = (float*)out(args->pt3d, (size_t)n * 3 * f);
-  a.z_coarse = (float*)out(args->z_coarse, (size_t)n * d.zc * f);
-  a.z_fine = (float*)out(args->z_fine, (size_t)n * d.zf * f);
-  a.weights_coarse = (float*)out(args->weights_coarse, (size_t)n * d.sc * f);
-  a.weights_fine = (float*)out(args->weights_fine, (size_t)n * d.sf * f);
-  a.raw_coarse = (float*)out(args->raw_coarse, (size_t)n * d.sc * 4 * f);
-  a.raw_fine = (float*)out(args->raw_fine, (size_t)n * d.sf * 4 * f);
-  a.idx_fine = (int32_t*)out(args->idx_fine, (size_t)n * (d.mip ? d.sc + 1 : d.nf) * sizeof(int32_t));
-  NMR_CUDA(h, cudaGetLastError());
-  if (n > 0 && !a.rays) NMR_FAIL(h, NMR_ERR_CUDA, "nmr_render_host: staging allocation failed");
+  a.rays = (const float*)in(args->rays, (size_t)n * args->ncols * f, "rays");
+  a.ray_id = (const int64_t*)in(args->ray_id, (size_t)n * sizeof(int64_t), "ray_id");
+  a.t_rand = (const float*)in(args->t_rand, (size_t)n * (d.sc + 1) * f, "t_rand");
+  a.u_jitter = (const float*)in(args->u_jitter, (size_t)n * (d.sc + 1) * f, "u_jitter");
+  a.feat_coarse = (float*)out(args->feat_coarse, (size_t)n * kHid * f, "feat_coarse");
+  a.feat_fine = (float*)out(args->feat_fine, (size_t)n * kHid * f, "feat_fine");
+  a.pts_coarse = (float*)out(args->pts_coarse, (size_t)n * 3 * f, "pts_coarse");
+  a.pts_fine = (float*)out(args->pts_fine, (size_t)n * 3 * f, "pts_fine");
+  a.rgb_coarse = (float*)out(args->rgb_coarse, (size_t)n * 3 * f, "rgb_coarse");
+  a.rgb_fine = (float*)out(args->rgb_fine, (size_t)n * 3 * f, "rgb_fine");
+  a.depth_coarse = (float*)out(args->depth_coarse, (size_t)n * f, "depth_coarse");
+  a.depth_fine = (float*)out(args->depth_fine, (size_t)n * f, "depth_fine");
+  a.pt3d = (float*)out(args->pt3d, (size_t)n * 3 * f, "pt3d");
+  a.z_coarse = (float*)out(args->z_coarse, (size_t)n * d.zc * f, "z_coarse");
+  a.z_fine = (float*)out(args->z_fine, (size_t)n * d.zf * f, "z_fine");
+  a.weights_coarse = (float*)out(args->weights_coarse, (size_t)n * d.sc * f, "weights_coarse");
+  a.weights_fine = (float*)out(args->weights_fine, (size_t)n * d.sf * f, "weights_fine");
+  a.raw_coarse = (float*)out(args->raw_coarse, (size_t)n * d.sc * 4 * f, "raw_coarse");
+  a.raw_fine = (float*)out(args->raw_fine, (size_t)n * d.sf * 4 * f, "raw_fine");
+  a.idx_fine = (int32_t*)out(args->idx_fine, (size_t)n * (d.mip ? d.sc + 1 : d.nf) * sizeof(int32_t), "idx_fine");
+  if (stage_err != cudaSuccess) {
+    cudaGetLastError();
+    NMR_FAIL(h, NMR_ERR_CUDA, "nmr_render_host: staging %s failed: %s", stage_what, cudaGetErrorString(stage_err));
+  }
   int r = render_device(h, &a, s, &sink);
   cudaError_t e1 = cudaStreamSynchronize(s), e2 = cudaStreamSynchronize(h->copy_stream);
   for (auto ev : sink.events) cudaEventDestroy(ev);

@@ -56,6 +56,7 @@ struct RayGenParams {
   float* rays; int* miss_flag;
 };
 void launch_raygen(const RayGenParams& p, cudaStream_t s);
+void launch_raygen_miss(const RayGenParams& p, cudaStream_t s);   // full-grid sphere-miss test (camera outside the unit sphere)
 void launch_far_fallback(float* rays, int64_t n, int ncols, const int* miss_flag, cudaStream_t s);
 
 struct RayOpsParams {     // get_ray_dirs / get_rays_c2w / prepare_rays_data as separate ops

@@ -36,6 +36,8 @@ __device__ __forceinline__ float conf_value(const MatchParams& p, int i, int j) 
   return __fmul_rn(__fdiv_rn(expf(__fsub_rn(v, p.cmax[j])), p.csum[j]), __fdiv_rn(expf(__fsub_rn(v, p.rmax[i])), p.rsum[i]));
 }
 __device__ __forceinline__ void sm_merge(float& m, float& s, float m2, float s2) {
+  if (m2 == -INFINITY) return;                       // empty operand (a thread / slab that saw no element): -inf - -inf = NaN
+  if (m == -INFINITY) { m = m2; s = s2; return; }
   const float mm = fmaxf(m, m2);
   s = s * expf(m - mm) + s2 * expf(m2 - mm);
   m = mm;

@@ -989,9 +989,11 @@ struct VbParams {
 };
 constexpr int kVbRows = 64;   // rays (rows) per block: the transposed weight panel is staged once per block
 constexpr int kVbBatch = 8;   // rows per inner iteration: one weight load feeds eight independent FMA chains
+constexpr int kVbMaxK = 80;   // largest dirs + appearance width nmr_create accepts (dirs_num_freqs 8 -> 51, + 16), padded to 16
 __global__ void __launch_bounds__(128) view_bias_kernel(VbParams p) {
-  __shared__ float wt[48][129];
-  __shared__ __align__(16) float de[48][kVbBatch];   // [k][row of the batch]: encoded dirs | appearance
+  extern __shared__ __align__(16) float vb_smem[];   // sized by the launch: dap x (8 + 129) floats
+  float (*de)[kVbBatch] = reinterpret_cast<float (*)[kVbBatch]>(vb_smem);            // [k][row of the batch]: encoded dirs | appearance
+  float (*wt)[129] = reinterpret_cast<float (*)[129]>(vb_smem + p.dap * kVbBatch);   // [k][output], transposed weight panel
   const int t = threadIdx.x;
   const int nk = p.dirs + p.app;
   for (int i = t; i < kHalf * p.dap; i += 128) { int o = i / p.dap, k = i - o * p.dap; wt[k][o] = p.wview_d[i]; }
@@ -1037,6 +1039,9 @@ __global__ void __launch_bounds__(128) view_bias_kernel(VbParams p) {
     }
   }
 }
+
+inline size_t vb_smem_bytes(int dap) { return (size_t)dap * (kVbBatch + 129) * sizeof(float); }
+static_assert(kVbMaxK * (kVbBatch + 129) * sizeof(float) <= 48 * 1024, "view_bias_kernel: dynamic shared memory without opt-in");
 
 // tiled bf16 features -> fp32 [P,256] rows (stage API only)
 __global__ void detile_kernel(const uint8_t* tiles, int64_t P, float* out) {
@@ -1095,40 +1100,50 @@ size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep) {
   return off;
 }
 
-int* g_trap_host = nullptr;   // mapped pinned int: survives a trapped launch
+int* g_trap_host = nullptr;   // mapped pinned int: survives a trapped launch (portable: one flag for every device)
 int* g_trap_dev = nullptr;
 long long* g_timeline = nullptr;
 
 int g_cta_group = 0;           // 1 | 2 (CTA pairs); 0: not decided yet (NMR_TC_CG, default 1)
-int g_pair_ctas = 0;           // 2 x clusters of two that can be resident at once
+// One-time setup is per DEVICE: the opt-in shared-memory attribute of a kernel, the SM count and the number of
+// co-schedulable CTA pairs all belong to the device that is current at launch (one process may drive several).
+constexpr int kMaxDevices = 64;
+struct DevInit { bool done = false; int num_sms = 0; int pair_ctas = 0; };
+DevInit g_dev[kMaxDevices];
 
 int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std::string* err) {
-  static int num_sms = 0;
   if (p.P >= ((int64_t)1 << 31)) { *err = "more than 2^31 sample points in one launch: lower max_chunk_points"; return -1; }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { *err = "cudaGetDevice failed (or device ordinal >= 64)"; return -1; }
   if (!g_trap_host) {
-    if (cudaHostAlloc((void**)&g_trap_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc((void**)&g_trap_host, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&g_trap_dev, g_trap_host, 0) != cudaSuccess) {
       *err = "cudaHostAlloc(trap flag) failed"; return -1;
     }
     *g_trap_host = 0;
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
     if (g_cta_group == 0) {
       const char* ev = getenv("NMR_TC_CG");
       g_cta_group = (ev && atoi(ev) == 2) ? 2 : 1;
     }
+  }
+  DevInit& di = g_dev[dev];
+  if (!di.done) {
+    cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
     cudaLaunchConfig_t qc{};
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
-    qc.gridDim = dim3(num_sms & ~1); qc.blockDim = dim3(kThreads); qc.dynamicSmemBytes = kSmemBytes; qc.attrs = qa; qc.numAttrs = 1;
+    qc.gridDim = dim3(di.num_sms & ~1); qc.blockDim = dim3(kThreads); qc.dynamicSmemBytes = kSmemBytes; qc.attrs = qa; qc.numAttrs = 1;
     int ncl = 0;
     e = cudaOccupancyMaxActiveClusters(&ncl, nerf_mlp_tc_kernel<2>, &qc);
-    if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); g_cta_group = 1; }
-    g_pair_ctas = 2 * ncl;
+    if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); ncl = 0; }
+    di.pair_ctas = 2 * ncl;
+    di.done = true;
   }
+  const int num_sms = di.num_sms;
+  const int cta_group = (g_cta_group == 2 && di.pair_ctas >= 2) ? 2 : 1;   // a device that cannot co-schedule pairs runs single CTAs
   p.error_flag = g_trap_dev;
   if (!g_timeline && getenv("NMR_TC_TIMELINE")) { cudaMalloc((void**)&g_timeline, (kTlSlots) * sizeof(long long)); cudaMemset(g_timeline, 0, (kTlSlots) * sizeof(long long)); }
   p.timeline = g_timeline;
@@ -1136,8 +1151,8 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
   p.chunks = net.chunks; p.wrgb = net.wrgb;
   p.balpha = net.balpha; p.brgb0 = net.brgb[0]; p.brgb1 = net.brgb[1]; p.brgb2 = net.brgb[2];
   cudaError_t e;
-  if (g_cta_group == 2) {
-    int grid = (int)std::min<int64_t>(g_pair_ctas, (std::max<int64_t>(tiles, 1) + 1) / 2 * 2);
+  if (cta_group == 2) {
+    int grid = (int)std::min<int64_t>(di.pair_ctas, (std::max<int64_t>(tiles, 1) + 1) / 2 * 2);
     p.n_iters = (int)((tiles + grid - 1) / grid);
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute at[1];
@@ -1160,7 +1175,7 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
 int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err) {
   const int skipl = skip_layer + 1;
   out->set = false;
-  if (skipl != 5 || d.xyzp != 96 || d.fx != 15 || d.xyz > 94) {   // return 1: configuration valid for the fp32 path only
+  if (skipl != 5 || d.xyzp != 96 || d.fx != 15 || d.xyz > 94 || d.dap > kVbMaxK) {   // return 1: configuration valid for the fp32 path only
     *err = "the tcgen05 path is built for skips=[4] and a 96-wide padded xyz encoding (15 frequencies)";
     return 1;
   }
@@ -1260,7 +1275,9 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
 
 int tc_set_cluster(int cs) {   // 1: independent CTAs (default), 2: CTA pairs sharing every MMA (cta_group::2)
   if (cs != 1 && cs != 2) return -1;
-  if (cs == 2 && g_trap_host && g_pair_ctas < 2) return -1;   // pairs cannot be co-scheduled on this device
+  int dev = 0;
+  if (cs == 2 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices && g_dev[dev].done && g_dev[dev].pair_ctas < 2)
+    return -1;                                                 // pairs cannot be co-scheduled on the current device
   g_cta_group = cs;
   return 0;
 }
@@ -1278,8 +1295,6 @@ void tc_free_net(TcNet* n) {
   if (n->pool) cudaFree(n->pool);
   *n = TcNet{};
 }
-
-int64_t tc_round_chunk_rays(const Dims&, int64_t chunk_rays, int64_t) { return chunk_rays; }
 
 static int reserve(void** ws, size_t* cap, size_t need, std::string* err) {
   if (*cap >= need && *ws) return 0;
@@ -1308,7 +1323,7 @@ int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, con
   vp.mode = 0; vp.rays = r.rays; vp.ncols = r.ncols; vp.ray_id = r.ray_id; vp.app_table = r.app_table; vp.num_frames = r.num_frames;
   vp.mip = d.mip; vp.fd = d.fd; vp.dirs = d.dirs; vp.app = d.app; vp.dap = d.dap;
   vp.wview_d = net.wview_d; vp.bview = net.bview; vp.n = r.n; vp.out = w.vbias;
-  view_bias_kernel<<<(unsigned)((r.n + kVbRows - 1) / kVbRows), 128, 0, s>>>(vp);
+  view_bias_kernel<<<(unsigned)((r.n + kVbRows - 1) / kVbRows), 128, vb_smem_bytes(d.dap), s>>>(vp);
   *launches += 1;
   TcParams p{};
   p.vbias = w.vbias; p.vb_div = r.S;
@@ -1334,7 +1349,7 @@ int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int 
   vp.mode = 1; vp.X = X; vp.kx = d.kx; vp.xyzp = d.xyzp;
   vp.mip = d.mip; vp.fd = d.fd; vp.dirs = d.dirs; vp.app = d.app; vp.dap = d.dap;
   vp.wview_d = net.wview_d; vp.bview = net.bview; vp.n = P; vp.out = w.vbias;
-  view_bias_kernel<<<(unsigned)((P + kVbRows - 1) / kVbRows), 128, 0, s>>>(vp);
+  view_bias_kernel<<<(unsigned)((P + kVbRows - 1) / kVbRows), 128, vb_smem_bytes(d.dap), s>>>(vp);
   *launches += 1;
   TcParams p{};
   p.vbias = w.vbias; p.vb_div = 1;

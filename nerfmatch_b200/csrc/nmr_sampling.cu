@@ -62,6 +62,22 @@ __global__ void raygen_kernel(RayGenParams p) {
   }
 }
 
+// The reference tests rays_intersect_sphere on ALL H x W pixels before it subsamples (render_utils.py:60-68): with the
+// camera outside the unit sphere a pixel that the [ds/2::ds] grid skips can trigger the far = 1 fallback.  Launched only
+// in that case (inside the sphere no ray can miss).
+__global__ void raygen_miss_kernel(RayGenParams p) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.H * p.W) return;
+  int y = idx / p.W, x = idx - y * p.W;
+  float v[3];
+  pixel_viewdir(p, x, y, v);
+  float odotd = p.org[0] * v[0] + p.org[1] * v[1] + p.org[2] * v[2];
+  float dn = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  float on = p.org[0] * p.org[0] + p.org[1] * p.org[1] + p.org[2] * p.org[2];
+  float det = odotd * odotd + (1.0f - on) * dn;
+  if (!(det >= 0.0f)) atomicExch(p.miss_flag, 1);
+}
+
 __global__ void far_fallback_kernel(float* rays, int64_t n, int ncols, const int* miss_flag) {
   if (*miss_flag == 0) return;   // render_utils.py:62-68: any miss -> far = 1 for the whole view
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -71,6 +87,10 @@ __global__ void far_fallback_kernel(float* rays, int64_t n, int ncols, const int
 void launch_raygen(const RayGenParams& p, cudaStream_t s) {
   int n = p.h * p.w;
   raygen_kernel<<<(n + 255) / 256, 256, 0, s>>>(p);
+}
+void launch_raygen_miss(const RayGenParams& p, cudaStream_t s) {
+  int n = p.H * p.W;
+  raygen_miss_kernel<<<(n + 255) / 256, 256, 0, s>>>(p);
 }
 void launch_far_fallback(float* rays, int64_t n, int ncols, const int* miss_flag, cudaStream_t s) {
   far_fallback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(rays, n, ncols, miss_flag);

@@ -41,7 +41,6 @@ struct TcRun {
 
 int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err);
 void tc_free_net(TcNet* n);
-int64_t tc_round_chunk_rays(const Dims& d, int64_t chunk_rays, int64_t n);
 int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err);
 // Sample rows of one pass (encode + MLP fused): writes raw [n*S,4] fp32 and either tiled bf16 features or
 // (fuse_composite) per-tile, per-ray-segment partial composites [tiles][4][256] fp32 into the workspace and
@@ -59,6 +58,6 @@ int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int 
 // code recorded by a bounded barrier wait before trapping (mapped host memory), 0 = none
 int tc_trap_code();
 int tc_read_timeline(long long* host, int n);   // clock64 trace of CTA 0 (NMR_TC_TIMELINE=1)
-int tc_set_cluster(int cluster_size);   // 1, 2 or 4
+int tc_set_cluster(int cluster_size);   // 1 or 2
 
 }  // namespace nmr

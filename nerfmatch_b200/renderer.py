@@ -105,17 +105,19 @@ class NerfRenderer(nn.Module):
         """The nmr_handle for ``device``; (re)uploads weights when a parameter changed
         (load_state_dict, .to(), in-place edits bump the tensors' version counters)."""
         key = str(torch.device(device))
-        sig = (self.nerf_coarse.weights_signature(), self.nerf_fine.weights_signature(),
-               None if self.embedding_a is None else (self.embedding_a.weight.data_ptr(), self.embedding_a.weight._version),
-               self.embed_type, float(self.mip_var_scale))
+        cfg = self._engine_config()
+        # everything the nmr_handle fixes at creation (the reference reads these attributes live on every call)
+        static = tuple(sorted((k, v) for k, v in vars(cfg).items() if k != "precision"))
+        weights = (self.nerf_coarse.weights_signature(), self.nerf_fine.weights_signature(),
+                   None if self.embedding_a is None else (self.embedding_a.weight.data_ptr(), self.embedding_a.weight._version))
         ent = self._engines.get(key)
-        if ent is None or ent[1] != sig:
-            eng = Engine(self._engine_config(), device) if (ent is None or ent[1][3:] != sig[3:]) else ent[0]
+        if ent is None or ent[1] != (weights, static):
+            eng = Engine(cfg, device) if (ent is None or ent[1][1] != static) else ent[0]
             eng.set_weights(L.NMR_NET_COARSE, self.nerf_coarse.net_state())
             eng.set_weights(L.NMR_NET_FINE, self.nerf_fine.net_state())
             if self.embedding_a is not None:
                 eng.set_appearance(self.embedding_a.weight)
-            ent = (eng, sig)
+            ent = (eng, (weights, static))
             self._engines[key] = ent
         if ent[0].cfg.precision != self.precision:
             ent[0].set_precision(self.precision)
