@@ -23,6 +23,18 @@ def _save(path: str, item: Dict[str, np.ndarray]):
     np.save(path, item)   # a dict -> pickled 0-d object array, like the reference's np.save(scene_dir / f"{img_idx}.npy", scene_pts)
 
 
+def write_frame(scene_dir: str, img_idx: str, pt3d, unnorm_scene, pt_feat, pt_color, **extra) -> str:
+    """One frame of the scene cache in the reference's format (nerf_evaluator.py:358-372): ``{img_idx}.npy`` holding the
+    pickled dict(pt3d [n,3] f32, unnorm_scene [4,4] f32, pt_feat [n,C] f32, pt_color [n,3] f32 in [0,1]); ``extra`` carries
+    the optional keys the reference adds for some datasets (sky_mask, mask).  Pure numpy: no device involved."""
+    item = dict(pt3d=np.ascontiguousarray(pt3d, np.float32), unnorm_scene=np.ascontiguousarray(unnorm_scene, np.float32),
+                pt_feat=np.ascontiguousarray(pt_feat, np.float32), pt_color=np.clip(np.ascontiguousarray(pt_color, np.float32), 0.0, 1.0))
+    item.update(extra)
+    path = os.path.join(scene_dir, f"{img_idx}.npy")
+    _save(path, item)
+    return path
+
+
 def cache_scene_pts(renderer, frames: Sequence[Dict], scene_dir: str, img_hw, unnorm_scene, downsample: int = 8,
                     feat_comb: str = "lin", views_per_batch: int = 8, device=None, writer_threads: int = 2,
                     rank: int = 0, world_size: int = 1) -> List[str]:
@@ -52,11 +64,9 @@ def cache_scene_pts(renderer, frames: Sequence[Dict], scene_dir: str, img_hw, un
         ev.synchronize()
         for v, f in enumerate(batch):
             sl = slice(v * per_view, (v + 1) * per_view)
-            item = dict(pt3d=host["pt3d"][sl].numpy().copy(), unnorm_scene=un.numpy().copy(),
-                        pt_feat=host["feat_fine"][sl].numpy().copy(), pt_color=host["rgb_fine"][sl].clamp(0, 1).numpy().copy())
-            path = os.path.join(scene_dir, f"{f['img_idx']}.npy")
-            paths.append(path)
-            futures.append(pool.submit(_save, path, item))
+            paths.append(os.path.join(scene_dir, f"{f['img_idx']}.npy"))
+            futures.append(pool.submit(write_frame, scene_dir, f["img_idx"], host["pt3d"][sl].numpy().copy(), un.numpy().copy(),
+                                       host["feat_fine"][sl].numpy().copy(), host["rgb_fine"][sl].numpy().copy()))
 
     for b0 in range(0, len(mine), views_per_batch):
         batch = mine[b0:b0 + views_per_batch]
@@ -91,8 +101,22 @@ def cache_scene_pts(renderer, frames: Sequence[Dict], scene_dir: str, img_hw, un
     return paths
 
 
-def load_frame_3d(path: str):
-    """Reader with the reference's semantics (datasets/data_loading.py:36-80): -> pt3d, pt_feat, mask, unnorm_scene."""
-    scene_pts = np.load(path, allow_pickle=True).item()
+def frame_cache_name(file_path: str) -> str:
+    """File stem the reference derives from a frame's ``file_path`` (datasets/data_loading.py:39-40)."""
+    return file_path.replace("/", "_").replace(".color", "").replace(".png", "")
+
+
+def load_frame_3d(frame, scene_dir, use_msk=None, return_pose=False):
+    """Reader with the reference's signature and semantics (datasets/data_loading.py:36-80):
+    -> pt3d, pt_feat, mask, unnorm_scene[, c2w].  ``frame`` is the dataset's frame dict (``file_path`` names the cache file)."""
+    scene_pts = np.load(os.path.join(scene_dir, f"{frame_cache_name(frame['file_path'])}.npy"), allow_pickle=True).item()
     pt3d = scene_pts["pt3d"]
-    return pt3d, scene_pts["pt_feat"], np.ones(len(pt3d)).astype(np.bool_), scene_pts["unnorm_scene"]
+    unnorm_scene = scene_pts["unnorm_scene"]
+    c2w = torch.from_numpy(unnorm_scene @ scene_pts["cam2scene"]) if "cam2scene" in scene_pts else None
+    mask = np.ones(len(pt3d)).astype(np.bool_)
+    if "pt_mask" in scene_pts and use_msk:
+        src = {"sky": lambda: scene_pts["sky_mask"][0], "corr": lambda: scene_pts["corr_mask"]}.get(use_msk, lambda: scene_pts["pt_mask"][0])()
+        mask = (1 - src.reshape(-1)).astype(np.bool_)
+    if return_pose:
+        return pt3d, scene_pts["pt_feat"], mask, unnorm_scene, c2w
+    return pt3d, scene_pts["pt_feat"], mask, unnorm_scene

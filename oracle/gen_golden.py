@@ -469,6 +469,78 @@ def inerf_cases(r):
     return out
 
 
+def _stub_heavy_imports():
+    import importlib
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            m = _Any(self.__name__ + "." + name)
+            setattr(self, name, m)
+            return m
+
+        def __call__(self, *a, **k):
+            return self
+
+    for m in ("pytorch_lightning", "timm", "kornia", "transforms3d", "transforms3d.quaternions"):
+        if m not in sys.modules:
+            try:
+                importlib.import_module(m)
+            except Exception:
+                sys.modules[m] = _Any(m)
+
+
+def cache_cases(r):
+    """Scene-cache file format, both directions:
+      * a file written the way the reference writes it (nerf_evaluator.py:358-372: ``np.save(scene_dir / f"{img_idx}.npy",
+        scene_pts)``), committed as tests/golden/ref_cache/<img_idx>.npy, which the repo's reader must load;
+      * a file written by the repo's writer (nerfmatch_b200.cache.write_frame) read back with the reference's own
+        ``load_frame_3d`` (datasets/data_loading.py:36-80); what the reference returned is stored in the fixture."""
+    import importlib
+    import tempfile
+    from pathlib import Path
+
+    import torch
+
+    from nerfmatch_b200.cache import write_frame
+    from oracle.weights import make_unnorm_scene, uniform01
+
+    _stub_heavy_imports()
+    pkg = types.ModuleType("nerfmatch.datasets")            # the package __init__ pulls in the training datasets: load the one module only
+    pkg.__path__ = [os.path.join(REF, "nerfmatch", "datasets")]
+    sys.modules.setdefault("nerfmatch.datasets", pkg)
+    dl = importlib.import_module("nerfmatch.datasets.data_loading")
+
+    n = 24
+    pt3d = (uniform01(9, 1, n * 3).reshape(n, 3) * 4 - 2).astype(np.float32)
+    feat = uniform01(9, 2, n * 256).reshape(n, 256).astype(np.float32)
+    color = (uniform01(9, 3, n * 3).reshape(n, 3) * 1.2 - 0.1).astype(np.float32)
+    un = make_unnorm_scene()
+    out = {"pt3d": pt3d, "pt_feat": feat, "pt_color_raw": color, "unnorm_scene": un}
+    frame = {"file_path": "seq-01/frame-000007.color.png"}
+    img_idx = "seq-01_frame-000007"
+    # (1) reference-style writer -> committed file
+    ref_dir = Path(os.path.dirname(HERE)) / "tests" / "golden" / "ref_cache"
+    ref_dir.mkdir(parents=True, exist_ok=True)
+    scene_pts = dict(pt3d=torch.from_numpy(pt3d).numpy(), unnorm_scene=torch.from_numpy(un).numpy(), pt_feat=torch.from_numpy(feat).cpu().numpy(),
+                     pt_color=torch.from_numpy(color).reshape(-1, 3).clamp(0, 1).cpu().numpy())
+    np.save(ref_dir / f"{img_idx}.npy", scene_pts)
+    a = dl.load_frame_3d(frame, str(ref_dir))
+    assert np.array_equal(a[0], pt3d) and np.array_equal(a[1], feat) and a[2].all()
+    # (2) repo writer -> reference reader
+    with tempfile.TemporaryDirectory() as td:
+        write_frame(td, img_idx, pt3d, un, feat, color)
+        b = dl.load_frame_3d(frame, td, return_pose=True)
+        item = np.load(os.path.join(td, f"{img_idx}.npy"), allow_pickle=True).item()
+    out["ref_reads_ours.pt3d"], out["ref_reads_ours.pt_feat"], out["ref_reads_ours.mask"], out["ref_reads_ours.unnorm_scene"] = b[0], b[1], b[2], b[3]
+    out["ref_reads_ours.c2w_is_none"] = np.array(b[4] is None)
+    out["ref_reads_ours.keys"] = np.array(sorted(item))
+    out["ref_reads_ours.pt_color"] = item["pt_color"]
+    out["ref_written.keys"] = np.array(sorted(scene_pts))
+    return out
+
+
 def main():
     r = import_reference()
     gdir = os.path.join(os.path.dirname(HERE), "tests", "golden")
@@ -484,7 +556,7 @@ def main():
               "acc_c %.3f acc_f %.3f" % (out["weights_coarse"].sum(-1).mean(), out["weights_fine"].sum(-1).mean()),
               "wmax_f %.3f" % out["weights_fine"].max(-1).mean(), str(out["case"]))
     for fname, fn in (("raygen.npz", raygen_cases), ("stages.npz", stage_cases), ("match.npz", lambda _r: match_cases()),
-                      ("rayhelpers.npz", rayhelper_cases), ("inerf_grad.npz", inerf_cases)):
+                      ("rayhelpers.npz", rayhelper_cases), ("inerf_grad.npz", inerf_cases), ("cache_format.npz", cache_cases)):
         if only and fname not in only:
             continue
         out = fn(r)

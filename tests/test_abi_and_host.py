@@ -120,3 +120,36 @@ def test_unsupported_reference_options_fail_loudly():
     cfg.coarse_nerf.skips = [3]
     with pytest.raises(NotImplementedError):
         NerfRenderer(cfg)
+
+
+def test_scene_cache_format_both_directions(tmp_path):
+    """the repo's reader loads a file written the way the reference writes it
+    (tests/golden/ref_cache, produced by oracle/gen_golden.py::cache_cases with the reference's np.save line), and a file
+    written by the repo's writer was loaded by the REFERENCE's own load_frame_3d (what it returned is in the fixture)."""
+    from nerfmatch_b200.cache import frame_cache_name, load_frame_3d, write_frame
+    from nmr_helpers import GOLDEN, load_golden
+
+    g = load_golden("cache_format.npz")
+    frame = {"file_path": "seq-01/frame-000007.color.png"}
+    assert frame_cache_name(frame["file_path"]) == "seq-01_frame-000007"
+    # reference-written file -> our reader
+    pt3d, pt_feat, mask, un = load_frame_3d(frame, os.path.join(GOLDEN, "ref_cache"))
+    np.testing.assert_array_equal(pt3d, g["pt3d"])
+    np.testing.assert_array_equal(pt_feat, g["pt_feat"])
+    np.testing.assert_array_equal(un, g["unnorm_scene"])
+    assert mask.dtype == np.bool_ and mask.all() and len(mask) == len(pt3d)
+    ref_item = np.load(os.path.join(GOLDEN, "ref_cache", "seq-01_frame-000007.npy"), allow_pickle=True).item()
+    # our writer -> same keys / dtypes / values as the reference-written dict, and what the reference's reader returned
+    path = write_frame(str(tmp_path), "seq-01_frame-000007", g["pt3d"], g["unnorm_scene"], g["pt_feat"], g["pt_color_raw"])
+    item = np.load(path, allow_pickle=True).item()
+    assert sorted(item) == sorted(ref_item) == list(g["ref_written.keys"]) == list(g["ref_reads_ours.keys"])
+    for k in item:
+        assert item[k].dtype == ref_item[k].dtype and item[k].shape == ref_item[k].shape, k
+        np.testing.assert_array_equal(item[k], ref_item[k])
+    np.testing.assert_array_equal(g["ref_reads_ours.pt3d"], g["pt3d"])
+    np.testing.assert_array_equal(g["ref_reads_ours.pt_feat"], g["pt_feat"])
+    np.testing.assert_array_equal(g["ref_reads_ours.unnorm_scene"], g["unnorm_scene"])
+    assert g["ref_reads_ours.mask"].all() and bool(g["ref_reads_ours.c2w_is_none"])
+    a = load_frame_3d(frame, str(tmp_path), return_pose=True)
+    assert len(a) == 5 and a[4] is None
+    np.testing.assert_array_equal(a[1], g["pt_feat"])

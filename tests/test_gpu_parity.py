@@ -435,5 +435,6 @@ def test_cache_writer_matches_render_novel_view(tmp_path):
         view = ren.render_novel_view((480, 640), torch.from_numpy(K_7SCENES), torch.from_numpy(f["c2w"]), un, DEV, downsample=8)
         np.testing.assert_array_equal(item["pt_feat"], N(view["pt_feat"]))
         np.testing.assert_array_equal(item["pt3d"], N(view["pt3d"]))
-        pt3d, pt_feat, mask, un_r = load_frame_3d(p)
+        pt3d, pt_feat, mask, un_r = load_frame_3d(dict(file_path=f["img_idx"].replace("_", "/") + ".color.png"), str(tmp_path / "ds8lin"))
+        np.testing.assert_array_equal(pt_feat, item["pt_feat"])
         assert mask.all() and np.array_equal(un_r, un)
