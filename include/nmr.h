@@ -206,6 +206,31 @@ NMR_API int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z,
                         float* depth, float* acc, float* disp, float* weights, float* feat_out,
                         float* pts_out, void* stream);
 
+/* ---- next row: the differentiable render of the iNeRF pose refinement -----------------------------------------
+ * NeRFMatchEvaluator.inerf_refinement (nerfmatch_evaluator.py:288-500) optimises the camera pose with Adam through
+ *   gen_rays (:232-285, torch) -> xyz_encoder / dirs_encoder (:377-383) -> nerf_fine.forward (:395-404)
+ *   -> volume_render_radiance_field (:410-420) -> MSE (:424-426) -> loss.backward() (:450),
+ * with the sample positions and Gaussian variances constants (rays.detach(), :347).  These are the input gradients
+ * (vector-Jacobian products) of those three stages; the shim wraps each forward / backward pair in a
+ * torch.autograd.Function so the reference loop runs unchanged.  fp32 throughout.
+ *
+ * d enc -> d x for xyz_encoder (kind 0; IPE when var != NULL in mip mode, var is a constant) / dirs_encoder (kind 1).
+ * x [P,3], grad_out [P,dim] (dim as nmr_stage_encode), grad_x [P,3]. */
+NMR_API int nmr_stage_encode_backward(nmr_handle* h, int kind, const float* x, const float* var, int64_t P,
+                                      const float* grad_out, float* grad_x, void* stream);
+/* NeRF.forward backwards (models/nerf.py:94-144): x as in nmr_stage_mlp, grad_raw [P,4] w.r.t. (sigmoid rgb, raw sigma),
+ * grad_feat [P,256] w.r.t. the tapped activations (or NULL) -> grad_x [P, xyz+dirs+app].  The forward activations are
+ * recomputed chunk by chunk (nothing is kept between the forward and the backward call). */
+NMR_API int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer,
+                                   const float* grad_raw, const float* grad_feat, float* grad_x, void* stream);
+/* volume_render_radiance_field backwards (render_utils.py:176-230): inputs as nmr_stage_composite; incoming gradients of
+ * rgb_map [n,3], depth_map [n], acc_map [n], weights [n,S] (each optional) -> grad_raw [n,S,4] and, optionally,
+ * grad_rays_d [n,3] (through delta = dz * |rays_d|).  z is a constant. */
+NMR_API int nmr_stage_composite_backward(nmr_handle* h, const float* raw, const float* z, const float* rays_d, int64_t n,
+                                         int32_t S, uint32_t flags, const float* grad_rgb, const float* grad_depth,
+                                         const float* grad_acc, const float* grad_weights, float* grad_raw,
+                                         float* grad_rays_d, void* stream);
+
 /* ---- next row: NeRFMatch-Mini coarse matching on the rendered features, batch size 1 ------------
  * NeRFMatcherCoarse.coarse_matching (nerfmatch_coarse_trainer.py:223-234) + extract_mutual_matches
  * (modules/extract_matches.py:13-40, inference branch).  im_feat [m,d], pt_feat [n,d]: device fp32, d <= 512;

@@ -79,6 +79,9 @@ SYMBOLS = {
     "nmr_stage_encode": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp, _vp]),
     "nmr_stage_mlp": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp, _vp]),
     "nmr_stage_composite": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32] + [_vp] * 10),
+    "nmr_stage_encode_backward": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "nmr_stage_mlp_backward": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "nmr_stage_composite_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nmr_coarse_match": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, C.c_float, _i32, _i32, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nmr_stage_mlp_probe": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp]),
     "nmr_debug_trap_code": (C.c_int, []),

@@ -43,7 +43,7 @@ struct nmr_handle {
   int num_frames = 0;
   // workspace (per ray chunk)
   int64_t ws_points = 0, ws_rays = 0;
-  DevBuf X, B[4], raw, zc, zf, misc, rays_view, tcws, match;
+  DevBuf X, B[4], raw, zc, zf, misc, rays_view, tcws, match, bwd;
   DevBuf stage[24];     // nmr_render_host staging
   std::string err;
   int64_t launches = 0;
@@ -160,7 +160,7 @@ extern "C" void nmr_destroy(nmr_handle* h) {
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[i]); }
   h->app.release(); h->X.release(); h->raw.release(); h->zc.release(); h->zf.release(); h->misc.release();
-  h->rays_view.release(); h->tcws.release(); h->match.release();
+  h->rays_view.release(); h->tcws.release(); h->match.release(); h->bwd.release();
   for (auto& b : h->B) b.release();
   for (auto& b : h->stage) b.release();
   delete h;
@@ -251,6 +251,17 @@ extern "C" int nmr_set_weights(nmr_handle* h, int which, const nmr_weight_ptrs* 
   if ((r = fetch(h, tmp, w->rgb_b, 3, "rgb_b")) != NMR_OK) return r;
   hn.rgb_b = tmp;
   obr = alloc(4); memcpy(&pool[obr], tmp.data(), 3 * sizeof(float));
+  // transposed panels for the dgrad chain (nmr_stage_mlp_backward): src [rows, cols] -> [cols, rows]
+  auto transposed = [&](size_t src, int rows, int cols) {
+    size_t off = alloc((size_t)rows * cols);
+    for (int r2 = 0; r2 < rows; ++r2)
+      for (int c2 = 0; c2 < cols; ++c2) pool[off + (size_t)c2 * rows + r2] = pool[src + (size_t)r2 * cols + c2];
+    return off;
+  };
+  size_t oWt[kLayers];
+  for (int i = 0; i < kLayers; ++i) oWt[i] = transposed(oW[i], kHid, i == 0 ? d.xyzp : kHid);
+  const size_t oWtsx = transposed(oWsx, kHid, d.xyzp), oWtf = transposed(oWf, kHid, kHid),
+               oWtvf = transposed(oWvf, kHalf, kHid), oWtvd = transposed(oWvd, kHalf, d.dap);
 
   NMR_CUDA(h, h->wpool[which].reserve(pool.size() * sizeof(float)));
   float* base = (float*)h->wpool[which].p;
@@ -260,6 +271,8 @@ extern "C" int nmr_set_weights(nmr_handle* h, int which, const nmr_weight_ptrs* 
   n.Wskip_x = base + oWsx;
   n.Wfeat = base + oWf; n.bfeat = base + obf; n.Walpha = base + oWa; n.balpha = base + oba;
   n.Wview_f = base + oWvf; n.Wview_d = base + oWvd; n.bview = base + obv; n.Wrgb = base + oWr; n.brgb = base + obr;
+  for (int i = 0; i < kLayers; ++i) n.Wt[i] = base + oWt[i];
+  n.Wtskip_x = base + oWtsx; n.Wtfeat = base + oWtf; n.Wtview_f = base + oWtvf; n.Wtview_d = base + oWtvd;
   n.set = true;
   // bf16 UMMA-major tiles for the tcgen05 path
   std::string terr;
@@ -850,6 +863,148 @@ extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P
       NMR_CUDA(h, cudaMemcpyAsync(raw + p0 * 4, h->raw.p, (size_t)np * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
       if (feat) NMR_CUDA(h, cudaMemcpyAsync(feat + p0 * kHid, tap, (size_t)np * kHid * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
+  }
+  return NMR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// differentiable path: input gradients of the three stages the iNeRF refinement
+// (nerfmatch_evaluator.py:288-500) differentiates through
+// ------------------------------------------------------------------------------------------
+extern "C" int nmr_stage_encode_backward(nmr_handle* h, int kind, const float* x, const float* var, int64_t P,
+                                         const float* grad_out, float* grad_x, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (P < 0 || (P > 0 && (!x || !grad_out || !grad_x)) || (kind != 0 && kind != 1)) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_encode_backward: bad argument");
+  if (P == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  launch_encode_backward(kind, h->d, x, var, grad_out, P, grad_x, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "encode_backward");
+  return NMR_OK;
+}
+
+extern "C" int nmr_stage_composite_backward(nmr_handle* h, const float* raw, const float* z, const float* rays_d, int64_t n, int32_t S,
+                                            uint32_t flags, const float* grad_rgb, const float* grad_depth, const float* grad_acc,
+                                            const float* grad_weights, float* grad_raw, float* grad_rays_d, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (n < 0 || (n > 0 && (!raw || !z || !rays_d || !grad_raw))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_composite_backward: null argument");
+  if (S < 2 || S > kMaxSamples) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_composite_backward: S=%d (2..%d)", S, kMaxSamples);
+  if (n == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  CompositeBwdParams p{};
+  p.raw = raw; p.z = z; p.rays_d = rays_d; p.n = n; p.S = S; p.mip = h->d.mip; p.flags = flags;
+  p.grad_rgb = grad_rgb; p.grad_depth = grad_depth; p.grad_acc = grad_acc; p.grad_weights = grad_weights;
+  p.grad_raw = grad_raw; p.grad_rays_d = grad_rays_d;
+  launch_composite_backward(p, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "composite_backward");
+  return NMR_OK;
+}
+
+// NeRF.forward backwards (models/nerf.py:94-144): d raw [P,4] (+ d feat [P,256] at the tapped layer) -> d x [P,in_dim].
+// fp32 throughout.  Each chunk of points is re-evaluated forward with every activation kept (the ReLU masks), then the
+// dgrad chain runs on the same GEMM kernel with transposed panels: g_in = (g_out * W) [* mask of the layer below].
+extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, const float* grad_raw,
+                                      const float* grad_feat, float* grad_x, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (which != 0 && which != 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_backward: which=%d", which);
+  if (P < 0 || (P > 0 && (!x || !grad_raw || !grad_x))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_backward: null argument");
+  if (stop_layer >= kLayers) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_backward: stop_layer=%d", stop_layer);
+  if (!h->net[which].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_stage_mlp_backward: weights not set");
+  if (P == 0) return NMR_OK;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const Dims& d = h->d;
+  const NetF32& n = h->net[which];
+  const int skipl = h->cfg.skip_layer + 1;
+  const int tap = stop_layer < 0 ? kLayers - 1 : stop_layer;
+  const int64_t C = std::min<int64_t>(P, 65536);
+  // workspace layout (floats per point): X kx | H 8 x 256 | F 256 | V 128 | raw 4 | Gv 128 | Ga 256 | Gb 256 | Gxs xyzp | Gx0 xyzp | Gd dap
+  const size_t per_pt = (size_t)d.kx + 8 * kHid + kHid + kHalf + 4 + kHalf + 2 * kHid + 2 * d.xyzp + d.dap;
+  NMR_CUDA(h, h->bwd.reserve(per_pt * C * sizeof(float)));
+  float* wsp = (float*)h->bwd.p;
+  auto take = [&](size_t per) { float* q = wsp; wsp += per * C; return q; };
+  float* X = take(d.kx);
+  float* H[kLayers];
+  for (int i = 0; i < kLayers; ++i) H[i] = take(kHid);
+  float* F = take(kHid); float* V = take(kHalf); float* rawc = take(4);
+  float* Gv = take(kHalf); float* Ga = take(kHid); float* Gb = take(kHid);
+  float* Gxs = take(d.xyzp); float* Gx0 = take(d.xyzp); float* Gd = take(d.dap);
+  auto gemm = [&](const GemmParams& g, const char* what) -> int {
+    launch_sgemm(g, s);
+    return check_launch(h, what);
+  };
+  int r;
+  for (int64_t p0 = 0; p0 < P; p0 += C) {
+    const int64_t np = std::min<int64_t>(C, P - p0);
+    const float* gr = grad_raw + p0 * 4;
+    const float* gf = grad_feat ? grad_feat + p0 * kHid : nullptr;
+    // ---- forward, every activation kept ----
+    launch_repack_input(d, x + p0 * d.in_dim, np, X, s);
+    NMR_LAUNCHED(h, "repack_input");
+    const float* in = X; int lda = d.kx;
+    for (int i = 0; i < kLayers; ++i) {
+      GemmParams g{};
+      if (i == skipl) {
+        g.A1 = X; g.lda1 = d.kx; g.W1 = n.Wskip_x; g.K1 = d.xyzp;
+        g.A2 = in; g.lda2 = lda; g.W2 = n.W[i]; g.K2 = kHid;
+      } else {
+        g.A1 = in; g.lda1 = lda; g.W1 = n.W[i]; g.K1 = (i == 0) ? d.xyzp : kHid;
+      }
+      g.bias = n.b[i]; g.C = H[i]; g.ldc = kHid; g.M = np; g.N = kHid; g.act = 1;
+      if ((r = gemm(g, "bwd: trunk forward")) != NMR_OK) return r;
+      in = H[i]; lda = kHid;
+    }
+    {
+      GemmParams g{};
+      g.A1 = H[7]; g.lda1 = kHid; g.W1 = n.Wfeat; g.K1 = kHid; g.bias = n.bfeat; g.C = F; g.ldc = kHid; g.M = np; g.N = kHid; g.act = 0;
+      if ((r = gemm(g, "bwd: feature_linear forward")) != NMR_OK) return r;
+      GemmParams v{};
+      v.A1 = F; v.lda1 = kHid; v.W1 = n.Wview_f; v.K1 = kHid; v.A2 = X + d.xyzp; v.lda2 = d.kx; v.W2 = n.Wview_d; v.K2 = d.dap;
+      v.bias = n.bview; v.C = V; v.ldc = kHalf; v.M = np; v.N = kHalf; v.act = 1;
+      if ((r = gemm(v, "bwd: views forward")) != NMR_OK) return r;
+      GemmParams c{};
+      c.A1 = V; c.lda1 = kHalf; c.W1 = n.Wrgb; c.K1 = kHalf; c.bias = n.brgb; c.C = rawc; c.ldc = 4; c.M = np; c.N = 3; c.act = 2;
+      if ((r = gemm(c, "bwd: rgb forward")) != NMR_OK) return r;
+    }
+    // ---- backward ----
+    launch_rgb_head_backward(gr, rawc, V, n.Wrgb, np, Gv, s);
+    NMR_LAUNCHED(h, "rgb_head_backward");
+    {
+      GemmParams g{};   // d feature = d views_pre * Wview[:, :256]
+      g.A1 = Gv; g.lda1 = kHalf; g.W1 = n.Wtview_f; g.K1 = kHalf; g.C = Ga; g.ldc = kHid; g.M = np; g.N = kHid;
+      if ((r = gemm(g, "bwd: d feature")) != NMR_OK) return r;
+      GemmParams q{};   // d [dirs | app] = d views_pre * Wview[:, 256:]
+      q.A1 = Gv; q.lda1 = kHalf; q.W1 = n.Wtview_d; q.K1 = kHalf; q.C = Gd; q.ldc = d.dap; q.M = np; q.N = d.dap;
+      if ((r = gemm(q, "bwd: d dirs")) != NMR_OK) return r;
+      GemmParams t{};   // d h7 = d feature * Wfeat + d sigma (x) w_alpha (+ d feat if h7 is the tapped layer), masked by h7 > 0
+      t.A1 = Ga; t.lda1 = kHid; t.W1 = n.Wtfeat; t.K1 = kHid; t.C = Gb; t.ldc = kHid; t.M = np; t.N = kHid;
+      t.r1a = gr + 3; t.ldr1 = 4; t.r1b = n.Walpha;
+      if (gf && tap == kLayers - 1) { t.add = gf; t.ldadd = kHid; }
+      t.mask = H[7]; t.ldm = kHid;
+      if ((r = gemm(t, "bwd: d h7")) != NMR_OK) return r;
+    }
+    float* gin = Gb; float* gout = Ga;
+    for (int i = kLayers - 1; i >= 1; --i) {
+      if (i == skipl) {   // the skip connection's xyz part: d x += d pre_5 * W5[:, :xyz]
+        GemmParams g{};
+        g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wtskip_x; g.K1 = kHid; g.C = Gxs; g.ldc = d.xyzp; g.M = np; g.N = d.xyzp;
+        if ((r = gemm(g, "bwd: d x (skip)")) != NMR_OK) return r;
+      }
+      GemmParams g{};
+      g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wt[i]; g.K1 = kHid; g.C = gout; g.ldc = kHid; g.M = np; g.N = kHid;
+      if (gf && tap == i - 1) { g.add = gf; g.ldadd = kHid; }
+      g.mask = H[i - 1]; g.ldm = kHid;
+      if ((r = gemm(g, "bwd: d h")) != NMR_OK) return r;
+      std::swap(gin, gout);
+    }
+    {
+      GemmParams g{};
+      g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wt[0]; g.K1 = kHid; g.C = Gx0; g.ldc = d.xyzp; g.M = np; g.N = d.xyzp;
+      g.add = Gxs; g.ldadd = d.xyzp;
+      if ((r = gemm(g, "bwd: d x")) != NMR_OK) return r;
+    }
+    launch_unpack_grad(d, Gx0, Gd, d.dap, np, grad_x + p0 * d.in_dim, s);
+    NMR_LAUNCHED(h, "unpack_grad");
   }
   return NMR_OK;
 }

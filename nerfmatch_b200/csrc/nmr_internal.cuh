@@ -46,6 +46,12 @@ struct NetF32 {
   float* Wview_d;                   // [128,dap] dirs+app part
   float* bview;
   float* Wrgb; float* brgb;         // [3,128]
+  // transposed panels for the input-gradient (dgrad) chain: g_in = g_out * W is the same "A * W'^T" GEMM with W' = W^T
+  float* Wt[kLayers];  // [Kp, 256] (layer 0: [xyzp, 256], zero rows beyond xyz; layer skip+1: the h-part)
+  float* Wtskip_x;     // [xyzp, 256]
+  float* Wtfeat;       // [256, 256]
+  float* Wtview_f;     // [256, 128]
+  float* Wtview_d;     // [dap, 128]
   bool set;
 };
 
@@ -114,12 +120,32 @@ struct CompositeParams {
 };
 void launch_composite(const CompositeParams& p, cudaStream_t s);
 
-struct GemmParams {        // C = act(A1*W1^T + A2*W2^T + bias)
+struct GemmParams {        // C = act(A1*W1^T + A2*W2^T + bias [+ r1a (x) r1b] [+ add]) [* (mask > 0)]
   const float* A1; int lda1; const float* W1; int K1;
   const float* A2; int lda2; const float* W2; int K2;   // optional second segment
   const float* bias; float* C; int ldc; int64_t M; int N; int act;  // 0 none, 1 relu, 2 sigmoid
+  // backward-pass epilogue terms (all optional): rank-1 update r1a[row * ldr1] * r1b[col] (the sigma head's input gradient),
+  // an added matrix (gradient arriving at a tapped layer / a second gradient path), and the ReLU mask of the forward
+  // activation the result is the gradient of
+  const float* r1a; int ldr1; const float* r1b;
+  const float* add; int ldadd;
+  const float* mask; int ldm;
 };
 void launch_sgemm(const GemmParams& p, cudaStream_t s);
+
+// ---- backward pieces of the differentiable render (nmr_backward.cu) ----
+struct CompositeBwdParams {
+  const float* raw; const float* z; const float* rays_d; int64_t n; int S; int mip; uint32_t flags;
+  const float* grad_rgb; const float* grad_depth; const float* grad_acc; const float* grad_weights;   // any may be null
+  float* grad_raw;        // [n,S,4]
+  float* grad_rays_d;     // [n,3] or null
+};
+void launch_composite_backward(const CompositeBwdParams& p, cudaStream_t s);
+void launch_encode_backward(int kind, const Dims& d, const float* x, const float* var, const float* gout, int64_t P, float* gx,
+                            cudaStream_t s);
+void launch_rgb_head_backward(const float* grad_raw, const float* raw, const float* V, const float* wrgb, int64_t P, float* Gv,
+                              cudaStream_t s);
+void launch_unpack_grad(const Dims& d, const float* Gx, const float* Gd, int ldgd, int64_t P, float* out, cudaStream_t s);
 
 // coarse matching (nmr_match.cu)
 struct MatchParams {

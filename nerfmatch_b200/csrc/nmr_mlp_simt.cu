@@ -99,7 +99,14 @@ __global__ void __launch_bounds__(kThreads) sgemm_kernel(GemmParams p) {
       for (int j = 0; j < 4; ++j) {
         int cc = c + j;
         float b = (p.bias && cc < p.N) ? p.bias[cc] : 0.f;
-        v[j] = apply_act(acc[i][jh * 4 + j] + b, p.act);
+        float x = acc[i][jh * 4 + j] + b;
+        if (cc < p.N) {
+          if (p.r1a) x = fmaf(p.r1a[r * p.ldr1], p.r1b[cc], x);
+          if (p.add) x += p.add[r * p.ldadd + cc];
+        }
+        x = apply_act(x, p.act);
+        if (p.mask && cc < p.N && !(p.mask[r * p.ldm + cc] > 0.f)) x = 0.f;
+        v[j] = x;
       }
       float* out = p.C + r * p.ldc + c;
       if (c + 3 < p.N && (p.ldc % 4 == 0)) {

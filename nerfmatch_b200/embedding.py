@@ -6,6 +6,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .autograd import EncodeFn, wants_grad
 from .engine import Engine, EngineConfig
 
 
@@ -33,11 +34,15 @@ class _EncoderBase(nn.Module):
         if x.device.type != "cuda":
             raise RuntimeError("nerfmatch_b200 encoders run on CUDA tensors only (no CPU fallback)")
         shape = x.shape[:-1]
-        xf = x.detach().reshape(-1, 3).float().contiguous()
         vf = None if var is None else var.detach().reshape(-1, 3).float().contiguous()
         eng = self._engine(x.device)
+        # the C ABI encodes with the handle's xyz slot (kind 0: up to 16 frequencies, IPE when a variance is given) or its
+        # dirs slot (kind 1: up to 8); this private handle has both slots set to our frequency count
         kind = 0 if self.num_freqs > 8 or vf is not None else 1
-        out = eng.stage_encode(kind, xf, vf)
+        if wants_grad(x):           # iNeRF refinement: d enc / d x (the variances are constants there)
+            out = EncodeFn.apply(x.reshape(-1, 3), vf, eng, kind)
+        else:
+            out = eng.stage_encode(kind, x.detach().reshape(-1, 3).float().contiguous(), vf)
         return out.reshape(*shape, out.shape[-1])
 
 

@@ -348,3 +348,31 @@ class Engine:
                                               _ptr(pts_out), self.stream())
         self.check(st, "nmr_stage_composite")
         return dict(rgb=rgb, depth=depth, acc=acc, disp=disp, weights=weights, feat=feat_out, pts=pts_out)
+
+    # -- backward stages (iNeRF refinement) ----------------------------
+    def stage_encode_backward(self, kind: int, x, var, grad_out):
+        P = x.shape[0]
+        gx = torch.empty(P, 3, device=self.device)
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_stage_encode_backward(self.h, kind, _ptr(x), _ptr(var), P, _ptr(grad_out), _ptr(gx), self.stream())
+        self.check(st, "nmr_stage_encode_backward")
+        return gx
+
+    def stage_mlp_backward(self, which: int, x, stop_layer: int, grad_raw, grad_feat=None):
+        P = x.shape[0]
+        gx = torch.empty(P, x.shape[1], device=self.device)
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_stage_mlp_backward(self.h, which, _ptr(x), P, stop_layer, _ptr(grad_raw), _ptr(grad_feat), _ptr(gx), self.stream())
+        self.check(st, "nmr_stage_mlp_backward")
+        return gx
+
+    def stage_composite_backward(self, raw, z, rays_d, flags=0, grad_rgb=None, grad_depth=None, grad_acc=None, grad_weights=None,
+                                 want_rays_d=True):
+        n, S = raw.shape[0], raw.shape[1]
+        g_raw = torch.empty(n, S, 4, device=self.device)
+        g_d = torch.empty(n, 3, device=self.device) if want_rays_d else None
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_stage_composite_backward(self.h, _ptr(raw), _ptr(z), _ptr(rays_d), n, S, flags, _ptr(grad_rgb), _ptr(grad_depth),
+                                                       _ptr(grad_acc), _ptr(grad_weights), _ptr(g_raw), _ptr(g_d), self.stream())
+        self.check(st, "nmr_stage_composite_backward")
+        return g_raw, g_d

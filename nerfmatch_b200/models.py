@@ -8,6 +8,7 @@ from argparse import Namespace
 import torch
 import torch.nn as nn
 
+from .autograd import MlpFn, wants_grad
 from .engine import Engine, EngineConfig
 
 _DEFAULTS = dict(layer_num=8, hid_dim=256, xyz_dim=3, dirs_dim=3, app_dim=0, output_dim=4, skips=[4],
@@ -48,7 +49,7 @@ class NeRF(nn.Module):
 
     def forward(self, x, ret_pfeat=0, pfeat_mask=None, val=False):
         """x: [P, xyz+dirs+app] in the reference column order -> [P,4] (rgb, raw sigma) and, if
-        ``ret_pfeat``, the tapped [P,256] activations.  Inference only (no autograd)."""
+        ``ret_pfeat``, the tapped [P,256] activations.  Differentiable w.r.t. ``x`` (not the weights)."""
         if pfeat_mask is not None:
             raise NotImplementedError("pfeat_mask is a training-validation feature (out of scope)")
         if x.device.type != "cuda":
@@ -66,8 +67,11 @@ class NeRF(nn.Module):
             eng.set_weights(1, self.net_state())
             ent = (eng, sig)
             self._engines[key] = ent
-        xf = x.detach().reshape(-1, x.shape[-1]).float().contiguous()
-        raw, feat = ent[0].stage_mlp(0, xf, self.stop_layer, want_feat=ret_pfeat > 0)
+        if wants_grad(x):           # iNeRF refinement (nerfmatch_evaluator.py:395-404): d (raw, feat) / d x
+            raw, feat = MlpFn.apply(x.reshape(-1, x.shape[-1]), ent[0], 0, self.stop_layer)
+        else:
+            xf = x.detach().reshape(-1, x.shape[-1]).float().contiguous()
+            raw, feat = ent[0].stage_mlp(0, xf, self.stop_layer, want_feat=ret_pfeat > 0)
         raw = raw.reshape(*x.shape[:-1], 4)
         if ret_pfeat > 0:
             return raw, feat.reshape(*x.shape[:-1], 256)

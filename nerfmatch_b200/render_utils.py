@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .autograd import CompositeFn, wants_grad
 from .engine import Engine, EngineConfig
 
 _engines = {}
@@ -128,9 +129,12 @@ def volume_render_radiance_field(radiance_field, z_vals, rays_d, noise_std=0.0, 
         raise NotImplementedError("sigma noise / out_last heads (training) are outside the built hot path")
     mip = str(embed_type)[:3] == "mip"
     eng = _engine(radiance_field.device, embed_type="mip" if mip else "normal")
+    flags = L.NMR_FLAG_WHITE_BG if white_bg else 0
+    if wants_grad(radiance_field, rays_d):      # iNeRF refinement (nerfmatch_evaluator.py:410-420); z_vals is a constant there
+        rgb, disp, acc, weights, depth = CompositeFn.apply(radiance_field[..., :4], rays_d, z_vals, eng, flags)
+        return rgb, disp, acc, weights, depth, None
     raw = radiance_field[..., :4].detach().float().contiguous()
-    out = eng.stage_composite(raw, z_vals.detach().float().contiguous(), rays_d.detach().float().contiguous(),
-                              flags=L.NMR_FLAG_WHITE_BG if white_bg else 0)
+    out = eng.stage_composite(raw, z_vals.detach().float().contiguous(), rays_d.detach().float().contiguous(), flags=flags)
     return out["rgb"], out["disp"], out["acc"], out["weights"], out["depth"], None
 
 
