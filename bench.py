@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the scene-feature render hot path (BASELINE.json: rays/sec, feature render, 64+128 samples).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp16|fp32]
 
 A "step" renders one full 480x640 view (307 200 rays, classic 64 coarse + 128 fine samples = 256 MLP
 evaluations per ray, feature tap at layer 3, all reference outputs incl. feat_coarse) per GPU with
@@ -258,7 +258,7 @@ def run_ours(args):
     # ---- kernel (c) standalone: the same step with the tile-local feature compositing of the bf16 MLP kernel switched off,
     #      i.e. the compositor streams the per-sample bf16 features from HBM (what the fp32 path and feat_comb="max" always do) ----
     stage_unfused = None
-    if args.precision == "bf16":
+    if args.precision in ("bf16", "fp16"):
         eng.set_fuse_composite(False)
         eng.render(dargs)
         eng.last_stage_ms()
@@ -287,7 +287,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
         "config": config_block(embed, args.precision),
         "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -300,7 +300,7 @@ def run_ours(args):
     # compositing kernel: HBM-bound side of the path (SURVEY.md 8d byte counts, bf16 | fp32 features), measured with the
     # per-sample features streamed from HBM (kernel (c) standalone); the bf16 product path composites the features tile by
     # tile inside the MLP kernel, its (small, latency-bound) compositor is reported as composite_fused.
-    bf = 2 if args.precision == "bf16" else 4
+    bf = 2 if args.precision in ("bf16", "fp16") else 4
     by = 0
     by_fused = 0
     for S in ((64, 192) if embed == "normal" else (64, 64)):
@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("NMR_PRECISION", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("NMR_PRECISION", "bf16"), choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--embed", default="normal", choices=["normal", "mip"])
     ap.add_argument("--cpu-rays", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true")

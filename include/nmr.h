@@ -43,7 +43,9 @@ typedef enum nmr_status {
 
 enum { NMR_EMBED_NORMAL = 0, NMR_EMBED_MIP = 1 };          /* config.embedding.type, renderer.py:40 */
 enum { NMR_NET_COARSE = 0, NMR_NET_FINE = 1 };             /* nerf_coarse / nerf_fine               */
-enum { NMR_PREC_FP32 = 0, NMR_PREC_BF16 = 1 };             /* SIMT fp32 (parity) | tcgen05 bf16     */
+enum { NMR_PREC_FP32 = 0, NMR_PREC_BF16 = 1, NMR_PREC_FP16 = 2 };  /* SIMT fp32 (parity) | tcgen05 with bf16 | fp16 operands
+                                                              (same kernel and rate; fp16: 8x smaller operand rounding,
+                                                              activations saturate at 65504, weights must fit fp16)   */
 enum { NMR_RNG_NONE = 0, NMR_RNG_PHILOX = 1 };             /* draws when t_rand/u_jitter are NULL   */
 
 /* per-call flags: the attributes callers poke on the reference object */
@@ -139,7 +141,7 @@ NMR_API int nmr_abi_version(void);
 NMR_API int nmr_set_weights(nmr_handle* h, int which, const nmr_weight_ptrs* w);
 /* embedding_a.weight [num_frames, app_dim] (renderer.py:104-107); host or device pointer. */
 NMR_API int nmr_set_appearance(nmr_handle* h, const float* table, int32_t num_frames);
-/* Switch NMR_PREC_FP32 <-> NMR_PREC_BF16 on a live handle (weights are kept in both forms). */
+/* Switch between NMR_PREC_FP32 / NMR_PREC_BF16 / NMR_PREC_FP16 on a live handle (weights are kept in all forms). */
 NMR_API int nmr_set_precision(nmr_handle* h, int precision);
 
 /* ---- the hot path --------------------------------------------------------------------- */

@@ -17,7 +17,8 @@ ABI_VERSION = 1
 
 NMR_EMBED_NORMAL, NMR_EMBED_MIP = 0, 1
 NMR_NET_COARSE, NMR_NET_FINE = 0, 1
-NMR_PREC_FP32, NMR_PREC_BF16 = 0, 1
+NMR_PREC_FP32, NMR_PREC_BF16, NMR_PREC_FP16 = 0, 1, 2
+PRECISIONS = {"fp32": NMR_PREC_FP32, "bf16": NMR_PREC_BF16, "fp16": NMR_PREC_FP16}
 NMR_RNG_NONE, NMR_RNG_PHILOX = 0, 1
 NMR_FLAG_RET_PFEAT, NMR_FLAG_FEAT_MAX, NMR_FLAG_WHITE_BG, NMR_FLAG_SKIP_COARSE_FEAT = 1, 2, 4, 8
 

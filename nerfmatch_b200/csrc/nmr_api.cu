@@ -38,7 +38,7 @@ struct nmr_handle {
   bool fuse_composite = true;   // bf16 path: composite the tapped features tile-locally inside the MLP kernel (NMR_TC_FUSE=0: off)
   NetF32 net[2];
   DevBuf wpool[2];
-  TcNet tc[2];
+  TcNet tc[2][2];               // [operand format: 0 bf16, 1 fp16][coarse, fine]
   DevBuf app;
   int num_frames = 0;
   // workspace (per ray chunk)
@@ -126,7 +126,7 @@ extern "C" int nmr_create(const nmr_config* cfg, nmr_handle** out) {
     return NMR_ERR_UNSUPPORTED;
   }
   if (c.stop_layer_coarse >= kLayers || c.stop_layer_fine >= kLayers) { g_create_error = "nmr_create: stop_layer >= layer_num"; return NMR_ERR_INVALID; }
-  if (c.precision != NMR_PREC_FP32 && c.precision != NMR_PREC_BF16) { g_create_error = "nmr_create: precision"; return NMR_ERR_INVALID; }
+  if (c.precision != NMR_PREC_FP32 && c.precision != NMR_PREC_BF16 && c.precision != NMR_PREC_FP16) { g_create_error = "nmr_create: precision"; return NMR_ERR_INVALID; }
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) {
@@ -148,7 +148,7 @@ extern "C" int nmr_create(const nmr_config* cfg, nmr_handle** out) {
   h->d = d;
   h->device = dev;
   if (const char* fv = getenv("NMR_TC_FUSE")) h->fuse_composite = atoi(fv) != 0;
-  for (int i = 0; i < 2; ++i) { memset(&h->net[i], 0, sizeof(NetF32)); h->tc[i] = TcNet{}; }
+  for (int i = 0; i < 2; ++i) { memset(&h->net[i], 0, sizeof(NetF32)); h->tc[0][i] = TcNet{}; h->tc[1][i] = TcNet{}; }
   *out = h;
   return NMR_OK;
 }
@@ -158,7 +158,7 @@ extern "C" void nmr_destroy(nmr_handle* h) {
   for (auto& ev : h->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto& ev : h->event_pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[i]); }
+  for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[0][i]); tc_free_net(&h->tc[1][i]); }
   h->app.release(); h->X.release(); h->raw.release(); h->zc.release(); h->zf.release(); h->misc.release();
   h->rays_view.release(); h->tcws.release(); h->match.release(); h->bwd.release();
   for (auto& b : h->B) b.release();
@@ -170,7 +170,7 @@ extern "C" int64_t nmr_launch_count(const nmr_handle* h) { return h ? h->launche
 
 extern "C" int nmr_set_precision(nmr_handle* h, int precision) {
   if (!h) return NMR_ERR_INVALID;
-  if (precision != NMR_PREC_FP32 && precision != NMR_PREC_BF16) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_set_precision: %d", precision);
+  if (precision != NMR_PREC_FP32 && precision != NMR_PREC_BF16 && precision != NMR_PREC_FP16) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_set_precision: %d", precision);
   h->cfg.precision = precision;
   return NMR_OK;
 }
@@ -274,11 +274,13 @@ extern "C" int nmr_set_weights(nmr_handle* h, int which, const nmr_weight_ptrs* 
   for (int i = 0; i < kLayers; ++i) n.Wt[i] = base + oWt[i];
   n.Wtskip_x = base + oWtsx; n.Wtfeat = base + oWtf; n.Wtview_f = base + oWtvf; n.Wtview_d = base + oWtvd;
   n.set = true;
-  // bf16 UMMA-major tiles for the tcgen05 path
-  std::string terr;
-  int tr = tc_pack_net(h->d, h->cfg.skip_layer, hn, &h->tc[which], &terr);
-  if (tr < 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_pack_net: %s", terr.c_str());
-  if (tr > 0 && h->cfg.precision == NMR_PREC_BF16) NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_set_weights: %s", terr.c_str());
+  // 16-bit UMMA-major tiles for the tcgen05 path, in both operand formats (nmr_set_precision switches on a live handle)
+  for (int fmt = 0; fmt < 2; ++fmt) {
+    std::string terr;
+    int tr = tc_pack_net(h->d, h->cfg.skip_layer, hn, &h->tc[fmt][which], &terr, fmt);
+    if (tr < 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_pack_net: %s", terr.c_str());
+    if (tr > 0 && h->cfg.precision == (fmt ? NMR_PREC_FP16 : NMR_PREC_BF16)) NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_set_weights: %s", terr.c_str());
+  }
   return NMR_OK;
 }
 
@@ -457,8 +459,11 @@ static int validate_render(nmr_handle* h, const nmr_render_args* a) {
   if (a->ncols < 8) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: rays need at least 8 columns (o, d, near, far), got %d", a->ncols);
   if (h->d.mip && a->ncols < 12) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: mip rays need 12 columns (radius in column 11), got %d", a->ncols);
   if (!h->net[0].set || !h->net[1].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_render: weights of both nets must be set first");
-  if (h->cfg.precision == NMR_PREC_BF16 && (!h->tc[0].set || !h->tc[1].set))
-    NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_render: this configuration is not built for the tcgen05 path; use NMR_PREC_FP32");
+  if (h->cfg.precision != NMR_PREC_FP32) {
+    const int fmt = h->cfg.precision == NMR_PREC_FP16;
+    if (!h->tc[fmt][0].set || !h->tc[fmt][1].set)
+      NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_render: this configuration / these weights are not built for the tcgen05 path in this operand format; use NMR_PREC_FP32");
+  }
   if (h->d.app > 0 && h->num_frames == 0) NMR_FAIL(h, NMR_ERR_STATE, "nmr_render: appearance table not set");
   if (a->pt3d && !a->unnorm) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_render: pt3d requested without unnorm");
   return NMR_OK;
@@ -478,7 +483,8 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
   NMR_CUDA(h, cudaSetDevice(h->device));
   const Dims& d = h->d;
   const nmr_config& c = h->cfg;
-  const bool bf16 = c.precision == NMR_PREC_BF16;
+  const bool bf16 = c.precision != NMR_PREC_FP32;      // the tcgen05 path (bf16 or fp16 operands)
+  const int tcfmt = c.precision == NMR_PREC_FP16;
   const int smax = std::max(d.sc, d.sf);
   // fp32 path: ~3.7 KB of workspace per point; bf16 path: ~0.6 KB (raw, tiled features for the unfused tap, partials) -> larger chunks
   const int64_t max_points = (bf16 && h->auto_chunk) ? ((int64_t)1 << 22) : c.max_chunk_points;
@@ -539,9 +545,9 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
         tr.stop_layer = stop; tr.want_feat = want_feat; tr.ws = h->tcws.p;
         tr.fuse_composite = h->fuse_composite && !(a->flags & NMR_FLAG_FEAT_MAX);
         std::string terr; int nl = 0;
-        if (tc_run(d, h->tc[pass], tr, &raw_pass, (const void**)&feat, &partials, &nl, s, &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_run: %s", terr.c_str());
+        if (tc_run(d, h->tc[tcfmt][pass], tr, &raw_pass, (const void**)&feat, &partials, &nl, s, &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_run: %s", terr.c_str());
         NMR_LAUNCHED(h, "tcgen05 mlp", nl);
-        feat_bf16 = 1;
+        feat_bf16 = 1 + tcfmt;
         stage_end(h, s);
       }
       // ---- volume rendering + compositing (+ fused re-sampling after the coarse pass) (kernel c) ----
@@ -852,9 +858,11 @@ extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P
     launch_repack_input(d, x + p0 * d.in_dim, np, (float*)h->X.p, s);
     NMR_LAUNCHED(h, "repack_input");
     const float* tap = nullptr;
-    if (h->cfg.precision == NMR_PREC_BF16) {
+    if (h->cfg.precision != NMR_PREC_FP32) {
+      const TcNet& tcn = h->tc[h->cfg.precision == NMR_PREC_FP16][which];
+      if (!tcn.set) NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_stage_mlp: this configuration / these weights are not built for the tcgen05 path");
       std::string terr; int nl = 0;
-      if (tc_run_rows(d, h->tc[which], (const float*)h->X.p, np, stop_layer, raw + p0 * 4, feat ? feat + p0 * kHid : nullptr,
+      if (tc_run_rows(d, tcn, (const float*)h->X.p, np, stop_layer, raw + p0 * 4, feat ? feat + p0 * kHid : nullptr,
                       &h->tcws.p, &h->tcws.cap, &nl, s, &terr) != 0)
         NMR_FAIL(h, NMR_ERR_CUDA, "tc_run_rows: %s", terr.c_str());
       NMR_LAUNCHED(h, "tcgen05 mlp rows", nl);
@@ -1052,7 +1060,7 @@ extern "C" int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int
                                    void* stream) {
   if (!h) return NMR_ERR_INVALID;
   if (which != 0 && which != 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: which=%d", which);
-  if (h->cfg.precision != NMR_PREC_BF16) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: bf16 path only");
+  if (h->cfg.precision == NMR_PREC_FP32) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: tcgen05 path only (NMR_PREC_BF16 / NMR_PREC_FP16)");
   if (step < 0 || step > 8 || P <= 0 || !x || !out) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_probe: bad argument");
   if (!h->net[which].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_stage_mlp_probe: weights not set");
   NMR_CUDA(h, cudaSetDevice(h->device));
@@ -1063,7 +1071,7 @@ extern "C" int nmr_stage_mlp_probe(nmr_handle* h, int which, const float* x, int
   launch_repack_input(d, x, P, (float*)h->X.p, s);
   NMR_LAUNCHED(h, "repack_input");
   std::string terr; int nl = 0;
-  if (tc_run_rows(d, h->tc[which], (const float*)h->X.p, P, 3, (float*)h->raw.p, nullptr, &h->tcws.p, &h->tcws.cap, &nl, s,
+  if (tc_run_rows(d, h->tc[h->cfg.precision == NMR_PREC_FP16][which], (const float*)h->X.p, P, 3, (float*)h->raw.p, nullptr, &h->tcws.p, &h->tcws.cap, &nl, s,
                   &terr, step + 1, out) != 0)
     NMR_FAIL(h, NMR_ERR_CUDA, "tc_run_rows: %s", terr.c_str());
   NMR_LAUNCHED(h, "tcgen05 mlp probe", nl);

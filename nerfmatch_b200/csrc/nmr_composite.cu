@@ -43,11 +43,13 @@ __device__ __forceinline__ int upper_bound(const float* a, int n, float u) {
   return lo;
 }
 
-__device__ __forceinline__ void accum8_bf16(float acc[8], uint4 v, float w) {
+// eight packed 16-bit features (fmt 1: bf16, 2: fp16 - the tcgen05 kernel's operand format) times w
+__device__ __forceinline__ void accum8_16(float acc[8], uint4 v, float w, int fmt) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const __half2* hh = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
+    float2 f = fmt == 2 ? __half22float2(hh[i]) : __bfloat1622float2(h[i]);
     acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
     acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
   }
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
                                                 ((cc ^ ((rr & 7) >> 1)) << 4));
         };
         if (fmax) {
-          accum8_bf16(a, __ldg(addr(besti)), 1.0f);
+          accum8_16(a, __ldg(addr(besti)), 1.0f, p.feats_bf16);
         } else {
           int s = 0;
           for (; s + 8 <= S; s += 8) {
@@ -230,9 +232,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = __ldcs(addr(s + k));
 #pragma unroll
-            for (int k = 0; k < 8; ++k) accum8_bf16(a, v[k], sw[s + k]);
+            for (int k = 0; k < 8; ++k) accum8_16(a, v[k], sw[s + k], p.feats_bf16);
           }
-          for (; s < S; ++s) accum8_bf16(a, __ldcs(addr(s)), sw[s]);
+          for (; s < S; ++s) accum8_16(a, __ldcs(addr(s)), sw[s], p.feats_bf16);
         }
       } else {
         // lane owns channels [4*lane, +4) and [128 + 4*lane, +4): every load instruction is a

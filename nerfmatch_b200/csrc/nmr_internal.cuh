@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 
@@ -107,7 +108,7 @@ struct CompositeParams {
   const float* rays; int ncols;   // when rays == null: rays_d given separately, no point recompute
   const float* rays_d;     // [n,3] (stage API)
   int64_t n; int S; int mip; uint32_t flags;
-  const void* feats; int feats_bf16;   // [n,S,256] fp32 | bf16, or null
+  const void* feats; int feats_bf16;   // [n,S,256] fp32 rows (0) | tiled 16-bit features of the tcgen05 kernel (1: bf16, 2: fp16), or null
   const float* partials;               // or: per 128-point tile and ray segment, locally composited features [tiles][4][256] (nmr_tc.cuh)
   const float* pts_in;     // [n,S,3] explicit points (stage API) or null -> recomputed from rays/z
   float* rgb; float* depth; float* acc; float* disp; float* weights;

@@ -198,9 +198,11 @@ __device__ __forceinline__ uint64_t mk_desc(uint32_t lo) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
-// instruction descriptor: kind::f16, A = B = bf16 (K-major), D = fp32, M = 128
+// instruction descriptor: kind::f16, A = B = bf16 (format 1) or fp16 (format 0), K-major, D = fp32, M = 128.  Both formats run
+// at the same tensor-core rate; fp16 carries 11 significand bits instead of 8 (8x smaller operand rounding, range +-65504).
+template <int F16>
 __device__ __forceinline__ uint32_t umma_idesc(int N, int M) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+  return (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -269,10 +271,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* w) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+// two fp32 -> packed 16-bit operands (a in the low half), round to nearest even; fp16 saturates at +-65504
+template <int F16>
+__device__ __forceinline__ uint32_t pack16(float a, float b) {
+  uint32_t r;
+  if (F16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
 }
+// low / high half of a packed pair of NON-NEGATIVE 16-bit values as fp32 bit patterns that a following multiply turns into
+// the value: bf16 is the upper half of an fp32 (scale 1); an fp16 bit pattern shifted into the fp32 exponent / mantissa
+// fields is the value times 2^-112, exactly, subnormals included (scale 2^112 - folded into the weight by the caller)
+template <int F16> __device__ __forceinline__ float unpack_lo(uint32_t v) { return __uint_as_float(F16 ? ((v & 0xffffu) << 13) : (v << 16)); }
+template <int F16> __device__ __forceinline__ float unpack_hi(uint32_t v) { return __uint_as_float(F16 ? ((v >> 16) << 13) : (v & 0xffff0000u)); }
+constexpr float kF16Scale = 5.192296858534828e33f;   // 2^112
 // byte offset of 16-byte chunk c (0..3) of row r inside a [128 x 32 bf16] 64B-swizzled block
 __device__ __forceinline__ uint32_t sw64_off(int r, int c) {
   return (uint32_t)(((r >> 3) << 9) + ((r & 7) << 6) + ((c ^ ((r & 7) >> 1)) << 4));
@@ -286,16 +298,17 @@ __device__ __forceinline__ uint32_t sw64_off(int r, int c) {
 // cos(x) - they differ by at most half an ulp of the ARGUMENT (2^-11 at the top octave), below bf16
 // resolution.  (The fp32 parity path, nmr_sampling.cu, evaluates the reference expressions literally.)
 // One thread encodes one row: columns are produced in output order, 8 at a time -> one 16-byte chunk.
+template <int F16>
 struct RowWriter {
   uint32_t e_base; int r;
   __device__ __forceinline__ void store(int chunk, const float* f) const {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(e_base + (chunk >> 2) * kBlk + sw64_off(r, chunk & 3)),
-                 "r"(pack_bf16(f[0], f[1])), "r"(pack_bf16(f[2], f[3])), "r"(pack_bf16(f[4], f[5])), "r"(pack_bf16(f[6], f[7])) : "memory");
+                 "r"(pack16<F16>(f[0], f[1])), "r"(pack16<F16>(f[2], f[3])), "r"(pack16<F16>(f[4], f[5])), "r"(pack16<F16>(f[6], f[7])) : "memory");
   }
 };
 
-template <int F>
-__device__ __forceinline__ void encode_row_fourier(const float m[3], const RowWriter& w) {
+template <int F, class Writer>
+__device__ __forceinline__ void encode_row_fourier(const float m[3], const Writer& w) {
   float f[8];
   float sn[3], cs[3];
 #pragma unroll
@@ -323,8 +336,8 @@ __device__ __forceinline__ void encode_row_fourier(const float m[3], const RowWr
   }
 }
 
-template <int F>
-__device__ __forceinline__ void encode_row_ipe(const float m[3], const float var[3], const RowWriter& w) {
+template <int F, class Writer>
+__device__ __forceinline__ void encode_row_ipe(const float m[3], const float var[3], const Writer& w) {
   // The output order is [all sin columns | all cos columns]: the octave chain is walked once, the cos half is kept in
   // registers (3F values, compile-time indexed) and written when its columns come up.
   float f[8];
@@ -394,12 +407,15 @@ __device__ __forceinline__ void tap_chunk(EpiCtx& e, uint32_t t_chunk) {
   ++e.tap_n;
 }
 
+template <int F16>
 __device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, uint32_t t_chunk, int j, const TcParams& p, bool valid,
                                           int64_t pt) {
   uint32_t w[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
+  for (int i = 0; i < 16; ++i) {
+    if (F16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
+  }
   tmem_st16(t_chunk, w);
   if (p.debug_out && e.s == p.debug_step && valid) {
 #pragma unroll
@@ -446,7 +462,7 @@ __device__ __forceinline__ void epi_view_slice(const float* tab, const float* vb
 // CG = 1: every CTA is on its own.  CG = 2: CTA pairs (cluster of 2) share every MMA (cta_group::2): each CTA keeps its own
 // 128-point tile, encoder, epilogues and TMEM, but streams only HALF of every weight chunk (its half of the output
 // columns) - the per-SM weight delivery from L2, which bounds the single-CTA kernel, is halved.
-template <int CG>
+template <int CG, int F16>
 __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int kStages = CG == 2 ? kMaxStages : kMaxStages / 2;
   constexpr int kStageB = kRingBytes / kStages;      // 8 KB half chunks | 16 KB chunks
@@ -558,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
 #pragma unroll
       for (int s = 0; s < kSteps; ++s, ++gstep) {
         const int ne = step_chunks_e(s), nh = step_chunks_h(s);
-        const uint32_t idesc = umma_idesc((s == kViewStep) ? kViewN : 256, kTileM * CG);
+        const uint32_t idesc = umma_idesc<F16>((s == kViewStep) ? kViewN : 256, kTileM * CG);
         const int ab = gstep & 1;
         const uint32_t d_tmem = tmem_base + ab * 256;            // accumulator ping-pong by layer
         const uint32_t a_tmem = tmem_base + (ab ^ 1) * 256;      // previous layer's activations, packed in place of its accumulator
@@ -672,11 +688,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           const int j = g + 2 * jj;
           tmem_ld_wait();
           tmem_ld32(t_lane + (j + 2) * 32, vb);
-          epi_trunk(e, va, t_lane + j * 32, j, p, valid, pt);
+          epi_trunk<F16>(e, va, t_lane + j * 32, j, p, valid, pt);
           hand_over(j);
           tmem_ld_wait();
           if (jj + 2 < 4) tmem_ld32(t_lane + (j + 4) * 32, va);
-          epi_trunk(e, vb, t_lane + (j + 2) * 32, j + 2, p, valid, pt);
+          epi_trunk<F16>(e, vb, t_lane + (j + 2) * 32, j + 2, p, valid, pt);
           hand_over(j + 2);
         }
         tc_fence_before();
@@ -806,7 +822,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         if (ray * p.vb_div < p.P) t = __ldg(reinterpret_cast<const float4*>(p.vbias + ray * kHalf) + (r & 31));
         reinterpret_cast<float4*>(vbs + (eb * kVbRays + (r >> 5)) * kHalf)[r & 31] = t;
       }
-      const RowWriter rw{base + OFF_E + eb * kEBytes, r};
+      const RowWriter<F16> rw{base + OFF_E + eb * kEBytes, r};
       if (p.mode == 1 || !valid) {
         for (int ch = 0; ch < 12; ++ch) {
           float f[8];
@@ -839,12 +855,12 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       for (int j = 0; j < 8; j += 2) {
         tmem_ld_wait();
         tmem_ld32(t_lane + (j + 1) * 32, vb);
-        epi_trunk(e0, va, t_lane + j * 32, j, p, pt < p.P, pt);
+        epi_trunk<F16>(e0, va, t_lane + j * 32, j, p, pt < p.P, pt);
         tmem_st_wait(); tc_fence_before();
         warp_arrive_leader<CG>(bars + 8 * (BAR_HREADY + j), rank, lane);
         tmem_ld_wait();
         if (j + 2 < 8) tmem_ld32(t_lane + (j + 2) * 32, va);
-        epi_trunk(e0, vb, t_lane + (j + 1) * 32, j + 1, p, pt < p.P, pt);
+        epi_trunk<F16>(e0, vb, t_lane + (j + 1) * 32, j + 1, p, pt < p.P, pt);
         tmem_st_wait(); tc_fence_before();
         warp_arrive_leader<CG>(bars + 8 * (BAR_HREADY + j + 1), rank, lane);
       }
@@ -929,17 +945,17 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int rr = 8 * i + rsub, row = qq * 32 + rr;
-                const float w = (row >= ra && row < rb) ? wl[row] : 0.f;
+                const float w = (row >= ra && row < rb) ? (F16 ? wl[row] * kF16Scale : wl[row]) : 0.f;
                 const uint32_t src = unit + rr * 64 + ((pc ^ ((rr & 7) >> 1)) << 4);
 #pragma unroll
                 for (int gg = 0; gg < 2; ++gg) {
                   uint32_t v0, v1, v2, v3;
                   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
                                : "r"(src + gg * 4 * kTapBufs * kTapBytes));
-                  acc[gg][0] = fmaf(w, __uint_as_float(v0 << 16), acc[gg][0]); acc[gg][1] = fmaf(w, __uint_as_float(v0 & 0xffff0000u), acc[gg][1]);
-                  acc[gg][2] = fmaf(w, __uint_as_float(v1 << 16), acc[gg][2]); acc[gg][3] = fmaf(w, __uint_as_float(v1 & 0xffff0000u), acc[gg][3]);
-                  acc[gg][4] = fmaf(w, __uint_as_float(v2 << 16), acc[gg][4]); acc[gg][5] = fmaf(w, __uint_as_float(v2 & 0xffff0000u), acc[gg][5]);
-                  acc[gg][6] = fmaf(w, __uint_as_float(v3 << 16), acc[gg][6]); acc[gg][7] = fmaf(w, __uint_as_float(v3 & 0xffff0000u), acc[gg][7]);
+                  acc[gg][0] = fmaf(w, unpack_lo<F16>(v0), acc[gg][0]); acc[gg][1] = fmaf(w, unpack_hi<F16>(v0), acc[gg][1]);
+                  acc[gg][2] = fmaf(w, unpack_lo<F16>(v1), acc[gg][2]); acc[gg][3] = fmaf(w, unpack_hi<F16>(v1), acc[gg][3]);
+                  acc[gg][4] = fmaf(w, unpack_lo<F16>(v2), acc[gg][4]); acc[gg][5] = fmaf(w, unpack_hi<F16>(v2), acc[gg][5]);
+                  acc[gg][6] = fmaf(w, unpack_lo<F16>(v3), acc[gg][6]); acc[gg][7] = fmaf(w, unpack_hi<F16>(v3), acc[gg][7]);
                 }
               }
             }
@@ -1044,7 +1060,7 @@ inline size_t vb_smem_bytes(int dap) { return (size_t)dap * (kVbBatch + 129) * s
 static_assert(kVbMaxK * (kVbBatch + 129) * sizeof(float) <= 48 * 1024, "view_bias_kernel: dynamic shared memory without opt-in");
 
 // tiled bf16 features -> fp32 [P,256] rows (stage API only)
-__global__ void detile_kernel(const uint8_t* tiles, int64_t P, float* out) {
+__global__ void detile_kernel(const uint8_t* tiles, int64_t P, float* out, int f16) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte chunk (8 channels) per thread
   if (i >= P * 32) return;
   int64_t pt = i >> 5;
@@ -1054,9 +1070,10 @@ __global__ void detile_kernel(const uint8_t* tiles, int64_t P, float* out) {
   const uint8_t* src = tiles + (pt >> 7) * kFeatTileBytes + j * kBlk + sw64_off(r, c);
   uint4 v = *reinterpret_cast<const uint4*>(src);
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const __half2* hh = reinterpret_cast<const __half2*>(&v);
   float* o = out + pt * kHid + j * 32 + c * 8;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) { float2 f = __bfloat1622float2(h[k]); o[2 * k] = f.x; o[2 * k + 1] = f.y; }
+  for (int k = 0; k < 4; ++k) { float2 f = f16 ? __half22float2(hh[k]) : __bfloat1622float2(h[k]); o[2 * k] = f.x; o[2 * k + 1] = f.y; }
 }
 
 // ---- host side -----------------------------------------------------------------------------
@@ -1066,16 +1083,46 @@ uint16_t f2bf(float f) {
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
+// fp32 -> fp16 bits, round to nearest even, subnormals kept, finite overflow saturates at 65504 (like cvt.rn.satfinite)
+uint16_t f2h(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  const uint32_t a = u & 0x7fffffffu;
+  if (a > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);            // NaN
+  if (a >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);           // >= 65520 rounds beyond the largest finite value: saturate
+  if (a < 0x33000001u) return sign;                                  // <= 2^-25: rounds to zero
+  const int e = (int)(a >> 23) - 127;
+  uint32_t m = (a & 0x7fffffu) | 0x800000u;                          // 24-bit significand
+  int shift = e < -14 ? (13 + (-14 - e)) : 13;                       // bits dropped (subnormal results drop more)
+  uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+  if (rem > half || (rem == half && (q & 1u))) ++q;
+  const uint32_t base = e < -14 ? 0u : ((uint32_t)(e + 15) << 10) - 0x400u;   // q carries the implicit bit for normals
+  return (uint16_t)(sign | (uint16_t)(base + q));
+}
+float h2f(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+  float v;
+  if (e == 0) v = ldexpf((float)m, -24);
+  else if (e == 31) v = m ? NAN : INFINITY;
+  else v = ldexpf((float)(m | 0x400u), (int)e - 25);
+  return sign ? -v : v;
+}
+// the 16-bit operand format of one packed net: 0 = bf16, 1 = fp16
+inline uint16_t to16(float f, int fmt) { return fmt ? f2h(f) : f2bf(f); }
+inline float from16(uint16_t h, int fmt) {
+  if (fmt) return h2f(h);
+  uint32_t u = (uint32_t)h << 16; float f; memcpy(&f, &u, 4); return f;
+}
 
 // pack W[rows, ldw] columns [k0, k0+32) (zero beyond kmax) as one swizzled chunk
-void pack_chunk(std::vector<uint8_t>& out, const float* W, int rows, int ldw, int k0, int kmax) {
+void pack_chunk(std::vector<uint8_t>& out, const float* W, int rows, int ldw, int k0, int kmax, int fmt) {
   size_t off = out.size();
   out.resize(off + (size_t)rows * 64, 0);
   for (int n = 0; n < rows; ++n)
     for (int k = 0; k < 32; ++k) {
       int kk = k0 + k;
       float v = (kk < kmax) ? W[(size_t)n * ldw + kk] : 0.f;
-      uint16_t h = f2bf(v);
+      uint16_t h = to16(v, fmt);
       size_t b = off + (size_t)(n >> 3) * 512 + (n & 7) * 64 + (((k >> 3) ^ ((n & 7) >> 1)) << 4) + (k & 7) * 2;
       memcpy(&out[b], &h, 2);
     }
@@ -1129,15 +1176,17 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
   DevInit& di = g_dev[dev];
   if (!di.done) {
     cudaDeviceGetAttribute(&di.num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nerf_mlp_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -1; }
     cudaLaunchConfig_t qc{};
     cudaLaunchAttribute qa[1];
     qa[0].id = cudaLaunchAttributeClusterDimension; qa[0].val.clusterDim.x = 2; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
     qc.gridDim = dim3(di.num_sms & ~1); qc.blockDim = dim3(kThreads); qc.dynamicSmemBytes = kSmemBytes; qc.attrs = qa; qc.numAttrs = 1;
     int ncl = 0;
-    e = cudaOccupancyMaxActiveClusters(&ncl, nerf_mlp_tc_kernel<2>, &qc);
+    e = cudaOccupancyMaxActiveClusters(&ncl, nerf_mlp_tc_kernel<2, 0>, &qc);
     if (e != cudaSuccess || ncl < 1) { cudaGetLastError(); ncl = 0; }
     di.pair_ctas = 2 * ncl;
     di.done = true;
@@ -1158,11 +1207,12 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = kSmemBytes; cfg.stream = s; cfg.attrs = at; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, nerf_mlp_tc_kernel<2>, p);
+    e = net.fmt ? cudaLaunchKernelEx(&cfg, nerf_mlp_tc_kernel<2, 1>, p) : cudaLaunchKernelEx(&cfg, nerf_mlp_tc_kernel<2, 0>, p);
   } else {
     int grid = (int)std::min<int64_t>(num_sms, std::max<int64_t>(tiles, 1));
     p.n_iters = (int)((tiles + grid - 1) / grid);
-    nerf_mlp_tc_kernel<1><<<grid, kThreads, kSmemBytes, s>>>(p);
+    if (net.fmt) nerf_mlp_tc_kernel<1, 1><<<grid, kThreads, kSmemBytes, s>>>(p);
+    else nerf_mlp_tc_kernel<1, 0><<<grid, kThreads, kSmemBytes, s>>>(p);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) { *err = std::string("nerf_mlp_tc_kernel launch: ") + cudaGetErrorString(e); return -1; }
@@ -1172,9 +1222,16 @@ int launch_tc(const TcNet& net, TcParams& p, int* launches, cudaStream_t s, std:
 
 }  // namespace
 
-int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err) {
+int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err, int fmt) {
   const int skipl = skip_layer + 1;
   out->set = false;
+  out->fmt = fmt;
+  if (fmt) {   // fp16 operands: every weight must be representable (|w| <= 65504); return 1 -> this net stays on bf16 / fp32
+    auto too_big = [](const std::vector<float>& v) { for (float x : v) if (!(fabsf(x) <= 65504.f)) return true; return false; };
+    bool bad = too_big(hn.feature_w) || too_big(hn.views_w) || too_big(hn.alpha_w) || too_big(hn.rgb_w);
+    for (int i = 0; i < kLayers; ++i) bad = bad || too_big(hn.pts_w[i]) || too_big(hn.pts_b[i]);
+    if (bad) { *err = "a weight exceeds the fp16 range (65504): use bf16 or fp32 for this network"; return 1; }
+  }
   if (skipl != 5 || d.xyzp != 96 || d.fx != 15 || d.xyz > 94 || d.dap > kVbMaxK) {   // return 1: configuration valid for the fp32 path only
     *err = "the tcgen05 path is built for skips=[4] and a 96-wide padded xyz encoding (15 frequencies)";
     return 1;
@@ -1202,9 +1259,9 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
       const float* bs = hn.pts_b[s].data();
       auto put_bias = [&](size_t chunk_off) {      // k = 30 (column 94): lo part, k = 31 (column 95): hi part
         for (int n = 0; n < kHid; ++n) {
-          uint16_t hi = f2bf(bs[n]);
-          uint32_t hu = (uint32_t)hi << 16; float hf; memcpy(&hf, &hu, 4);
-          uint16_t lo = f2bf(bs[n] - hf);
+          uint16_t hi = to16(bs[n], fmt);
+          const float hf = from16(hi, fmt);
+          uint16_t lo = to16(bs[n] - hf, fmt);
           for (int k = 30; k < 32; ++k) {
             size_t b = chunk_off + (size_t)(n >> 3) * 512 + (n & 7) * 64 + (((k >> 3) ^ ((n & 7) >> 1)) << 4) + (k & 7) * 2;
             uint16_t v = (k == 30) ? lo : hi;
@@ -1212,7 +1269,7 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
           }
         }
       };
-      auto both = [&](const float* Wp, int k0, int kmax) { pack_chunk(chunks, Wp, kHid, kin, k0, kmax); };
+      auto both = [&](const float* Wp, int k0, int kmax) { pack_chunk(chunks, Wp, kHid, kin, k0, kmax, fmt); };
       if (s == 0) {
         for (int c = 0; c < 3; ++c) both(W, 32 * c, d.xyz);
         put_bias(chunks.size() - kStageBytes);
@@ -1230,11 +1287,11 @@ int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, st
       std::vector<float> wv((size_t)kViewN * kHid, 0.f);
       memcpy(wv.data(), wfold.data(), wfold.size() * sizeof(float));
       for (int i = 0; i < kHid; ++i) {
-        uint32_t hu = (uint32_t)f2bf(hn.alpha_w[i]) << 16; float hf; memcpy(&hf, &hu, 4);
+        const float hf = from16(to16(hn.alpha_w[i], fmt), fmt);
         wv[(size_t)kHalf * kHid + i] = hf;
         wv[(size_t)(kHalf + 1) * kHid + i] = hn.alpha_w[i] - hf;
       }
-      for (int c = 0; c < 8; ++c) pack_chunk(chunks, wv.data(), kViewN, kHid, 32 * c, kHid);
+      for (int c = 0; c < 8; ++c) pack_chunk(chunks, wv.data(), kViewN, kHid, 32 * c, kHid, fmt);
     }
   }
   if ((int64_t)chunks.size() != step_offset(kSteps)) { *err = "internal: chunk stream size mismatch"; return -1; }
@@ -1362,7 +1419,7 @@ int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int 
   cudaError_t e = cudaMemcpyAsync(raw, w.raw, (size_t)P * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);
   if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
   if (feat) {
-    detile_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, s>>>(w.feat, P, feat);
+    detile_kernel<<<(unsigned)((P * 32 + 255) / 256), 256, 0, s>>>(w.feat, P, feat, net.fmt);
     *launches += 1;
   }
   return 0;

@@ -19,6 +19,7 @@ struct TcNet {
   void* pool = nullptr;
   size_t bytes = 0;
   bool set = false;
+  int fmt = 0;                       // operand format of the chunk stream and of the tapped features: 0 = bf16, 1 = fp16
   const uint8_t* chunks = nullptr;   // weight chunk stream (device)
   const float* bias = nullptr;       // [8][256] pts_linears bias (fp32, device)
   const float* walpha = nullptr;     // [256]
@@ -39,7 +40,7 @@ struct TcRun {
   void* ws;
 };
 
-int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err);
+int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err, int fmt = 0);
 void tc_free_net(TcNet* n);
 int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err);
 // Sample rows of one pass (encode + MLP fused): writes raw [n*S,4] fp32 and either tiled bf16 features or

@@ -92,7 +92,7 @@ class Engine:
             num_pts_coarse=cfg.num_pts_coarse, num_pts_fine=cfg.num_pts_fine,
             hid_dim=cfg.hid_dim, layer_num=cfg.layer_num, skip_layer=int(tuple(cfg.skips)[0]),
             app_dim=cfg.app_dim, stop_layer_coarse=cfg.stop_layer_coarse, stop_layer_fine=cfg.stop_layer_fine,
-            use_disp=int(cfg.use_disp), precision=L.NMR_PREC_BF16 if cfg.precision == "bf16" else L.NMR_PREC_FP32,
+            use_disp=int(cfg.use_disp), precision=self._prec(cfg.precision),
             mip_var_scale=float(cfg.mip_var_scale), resample_padding=float(cfg.resample_padding),
             max_chunk_points=int(cfg.max_chunk_points),
         )
@@ -112,6 +112,12 @@ class Engine:
             pass
 
     # -- plumbing -------------------------------------------------------------------------
+    @staticmethod
+    def _prec(name: str) -> int:
+        if name not in L.PRECISIONS:
+            raise L.NmrError(f"precision must be one of {sorted(L.PRECISIONS)}, got {name!r}")
+        return L.PRECISIONS[name]
+
     def stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -119,7 +125,7 @@ class Engine:
         L.check(self.h, st, what)
 
     def set_precision(self, precision: str):
-        self.check(self.lib.nmr_set_precision(self.h, L.NMR_PREC_BF16 if precision == "bf16" else L.NMR_PREC_FP32), "nmr_set_precision")
+        self.check(self.lib.nmr_set_precision(self.h, self._prec(precision)), "nmr_set_precision")
         self.cfg.precision = precision
 
     def set_weights(self, which: int, sd: Dict[str, torch.Tensor]):

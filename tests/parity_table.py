@@ -90,7 +90,7 @@ def render_cuda(ren, rays, t_rand=None, u_jitter=None, ray_id=None, unnorm=None)
     return {k: v.detach().cpu().numpy() for k, v in outs.items()}
 
 
-def golden_rows(precisions=("fp32", "bf16")):
+def golden_rows(precisions=("fp32", "bf16", "fp16")):
     rows = {}
     for name in RENDER_CASES:
         g = load_golden(f"render_{name}.npz")
@@ -142,7 +142,7 @@ def oracle_render(cfg, sd, rays, tr, uj, unnorm):
     return ref
 
 
-def view_rows(precisions=("fp32", "bf16"), quick=False):
+def view_rows(precisions=("fp32", "bf16", "fp16"), quick=False):
     rows = {}
     un = make_unnorm_scene()
     specs = {

@@ -28,8 +28,14 @@ def bf16(x):
     return u.astype(np.uint32).view(np.float32)
 
 
-def emulate_steps(wts, x, cfg):
-    """Outputs of the 9 MLP steps with bf16 operands / fp32 accumulation, as the kernel computes them."""
+def fp16(x):
+    """round-to-nearest-even to IEEE half (saturating at 65504, as the kernel's cvt.rn.satfinite does), returned as float32"""
+    return np.clip(np.ascontiguousarray(x, np.float32), -65504, 65504).astype(np.float16).astype(np.float32)
+
+
+def emulate_steps(wts, x, cfg, bf16=bf16):
+    """Outputs of the 9 MLP steps with 16-bit operands (``bf16``: the rounding function) / fp32 accumulation, as the kernel
+    computes them."""
     xd, dd = cfg.xyz_dim, cfg.dirs_dim
     enc = bf16(x[:, :xd])
     side = x[:, xd:]
@@ -80,32 +86,57 @@ def test_tc_mlp_is_deterministic():
         assert torch.equal(r1, r2) and torch.equal(f1, f2), stop
 
 
-@pytest.mark.parametrize("embed,app", [("mip", False), ("normal", True)])
-def test_tc_mlp_step_by_step(embed, app):
+@pytest.mark.parametrize("embed,app,prec", [("mip", False, "bf16"), ("normal", True, "bf16"), ("mip", False, "fp16"), ("normal", True, "fp16")])
+def test_tc_mlp_step_by_step(embed, app, prec):
     from nerfmatch_b200 import _lib as L
 
+    bf16 = globals()["fp16" if prec == "fp16" else "bf16"]      # the operand rounding of this precision mode
     cfg = O.RenderConfig(embed_type=embed, app_dim=16 if app else 0)
     sd = make_state_dict(61, embed_type=embed, app_dim=cfg.app_dim, num_frames=5 if app else 0, sigma_gain=30.0, sigma_bias=1.0)
     wts = O.split_state_dict(sd, "nerf_fine.")
-    eng = engine(embed_type=embed, app_dim=cfg.app_dim, precision="bf16")
+    eng = engine(embed_type=embed, app_dim=cfg.app_dim, precision=prec)
     eng.set_weights(0, {k: torch.from_numpy(v) for k, v in wts.items()})
     P = 128 * 5 + 37        # several tiles over few CTAs + a ragged tail
     in_dim = cfg.xyz_dim + cfg.dirs_dim + cfg.app_dim
     x = (uniform01(62, 1, P * in_dim).reshape(P, in_dim) * 2 - 1).astype(np.float32)
-    outs, raw_ref = emulate_steps(wts, x, cfg)
+    outs, raw_ref = emulate_steps(wts, x, cfg, bf16)
+    tol = 2e-3 if prec == "bf16" else 3e-4
     for step in range(9):
         got = N(eng.stage_mlp_probe(0, T(x), step))
         torch.cuda.synchronize()
         assert L.load().nmr_debug_trap_code() == 0
         ncol = 128 if step == 8 else 256
         err = rel_l2(got[:, :ncol], outs[step])
-        assert err < 2e-3, (step, err)
+        assert err < tol, (step, err)
     raw, feat = eng.stage_mlp(0, T(x), 3)
-    np.testing.assert_allclose(N(raw), raw_ref, rtol=2e-3, atol=2e-3)
-    assert rel_l2(N(feat), bf16(outs[3])) < 2e-3
+    np.testing.assert_allclose(N(raw), raw_ref, rtol=tol, atol=tol)
+    assert rel_l2(N(feat), bf16(outs[3])) < tol
     for stop in (-1, 0, 5, 6, 7):
         _, f = eng.stage_mlp(0, T(x), stop)
-        assert rel_l2(N(f), bf16(outs[7 if stop < 0 else stop])) < 2e-3, stop
+        assert rel_l2(N(f), bf16(outs[7 if stop < 0 else stop])) < tol, stop
+
+
+def test_fp16_operands_saturate_and_reject_out_of_range_weights():
+    """NMR_PREC_FP16: activations beyond the half range saturate at 65504 instead of becoming inf, and a network whose
+    weights do not fit fp16 is refused for this mode (it still runs in bf16 / fp32)."""
+    from nerfmatch_b200 import NmrError
+
+    cfg = O.RenderConfig(embed_type="normal")
+    sd = make_state_dict(66, embed_type="normal", sigma_gain=30.0, sigma_bias=1.0)
+    wts = {k: torch.from_numpy(v.copy()) for k, v in O.split_state_dict(sd, "nerf_fine.").items()}
+    wts["pts_linears.0.weight"] *= 3e4                               # layer-0 outputs ~1e5: beyond 65504
+    x = (torch.rand(256, cfg.xyz_dim + cfg.dirs_dim, device=DEV, generator=torch.Generator(DEV).manual_seed(4)) * 2 - 1)
+    eng = engine(embed_type="normal", precision="fp16"); eng.set_weights(0, wts)
+    h0 = eng.stage_mlp_probe(0, x, 0)
+    assert h0.max() > 65504                                          # the probe reports the fp32 accumulator after ReLU
+    raw, feat = eng.stage_mlp(0, x, 0)
+    assert torch.isfinite(raw).all() and torch.isfinite(feat).all() and feat.max() == 65504
+    wts["pts_linears.3.weight"][0, 0] = 1e5
+    bad = engine(embed_type="normal", precision="fp16")
+    with pytest.raises(NmrError):
+        bad.set_weights(0, wts)
+    ok = engine(embed_type="normal", precision="bf16"); ok.set_weights(0, wts)
+    assert torch.isfinite(ok.stage_mlp(0, x, 3)[0]).all()
 
 
 def test_tc_mlp_many_tiles_matches_fp32_path():
