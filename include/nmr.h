@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define NMR_ABI_VERSION 1
+#define NMR_ABI_VERSION 2
 #if defined(__GNUC__)
 #define NMR_API __attribute__((visibility("default")))
 #else
@@ -53,6 +53,8 @@ enum { NMR_RNG_NONE = 0, NMR_RNG_PHILOX = 1 };             /* draws when t_rand/
 #define NMR_FLAG_FEAT_MAX    (1u << 1)  /* NerfRenderer.feat_comb == "max" (renderer.py:257-260)     */
 #define NMR_FLAG_WHITE_BG    (1u << 2)  /* config.render.white_bg (renderer.py:36, render_utils:224) */
 #define NMR_FLAG_SKIP_COARSE_FEAT (1u << 3) /* do not composite feat_coarse (no caller reads it)     */
+#define NMR_FLAG_PERTURB     (1u << 4)  /* classic mode, rng_mode = PHILOX: draw the training-mode sample perturbation
+                                           in the kernels (render_utils.py:118-126, 246-247)        */
 
 /* Static configuration; mirrors what NerfRenderer.__init__ reads (renderer.py:27-114). */
 typedef struct nmr_config {
@@ -100,8 +102,10 @@ typedef struct nmr_render_args {
   int32_t ncols;            /* 12 mip, 11 normal; 8..10 -> viewdirs = rays_d (renderer.py:188) */
   uint32_t flags;           /* NMR_FLAG_*                                                      */
   const int64_t* ray_id;    /* [n] appearance ids or NULL (-> 1 for every ray, renderer.py:299) */
-  const float* t_rand;      /* mip coarse jitter  [n, Sc+1] in [0,1)   (render_utils.py:444)   */
-  const float* u_jitter;    /* mip fine jitter    [n, Sc+1] in [0, 1/(Sc+1)-eps) (:483-485)    */
+  const float* t_rand;      /* mip: coarse jitter [n, Sc+1] in [0,1) (render_utils.py:444), drawn at inference too;
+                               classic: training-mode perturbation [n, Sc] (perturb=True, :118-126) or NULL */
+  const float* u_jitter;    /* mip: fine jitter [n, Sc+1] in [0, 1/(Sc+1)-eps) (:483-485);
+                               classic: the u draws of sample_pdf(det=False) [n, Nf] in [0,1) (:246-247), NULL = det */
   int32_t rng_mode;         /* NMR_RNG_* used when the two pointers above are NULL             */
   uint64_t seed;            /* Philox seed for NMR_RNG_PHILOX                                  */
   const float* unnorm;      /* HOST 3x4 row-major affine (top rows of unnorm_scene) or NULL    */
@@ -123,6 +127,10 @@ typedef struct nmr_render_args {
   float* raw_coarse;        /* [n,Sc,4]  (rgb after sigmoid, raw sigma)                        */
   float* raw_fine;
   int32_t* idx_fine;        /* mip [n,Sc+1] interval index | normal [n,Nf] searchsorted result */
+  /* training-mode forward (renderer.py:217, 242, 283-286; nerf_trainer.py:140-147) - all optional, NULL at inference */
+  const float* sigma_noise_coarse; /* [n,Sc]  randn * noise_std, added to the raw density before the ReLU (render_utils.py:191-195) */
+  const float* sigma_noise_fine;   /* [n,Sf]                                                    */
+  float* s_fine;            /* [n,zf]  preds["s_fine"] = t_to_s(z_fine, min z_fine, max z_fine) over this call's rays (:283-285) */
 } nmr_render_args;
 
 typedef struct nmr_handle nmr_handle;

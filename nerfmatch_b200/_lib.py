@@ -13,14 +13,14 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnmr.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 NMR_EMBED_NORMAL, NMR_EMBED_MIP = 0, 1
 NMR_NET_COARSE, NMR_NET_FINE = 0, 1
 NMR_PREC_FP32, NMR_PREC_BF16, NMR_PREC_FP16 = 0, 1, 2
 PRECISIONS = {"fp32": NMR_PREC_FP32, "bf16": NMR_PREC_BF16, "fp16": NMR_PREC_FP16}
 NMR_RNG_NONE, NMR_RNG_PHILOX = 0, 1
-NMR_FLAG_RET_PFEAT, NMR_FLAG_FEAT_MAX, NMR_FLAG_WHITE_BG, NMR_FLAG_SKIP_COARSE_FEAT = 1, 2, 4, 8
+NMR_FLAG_RET_PFEAT, NMR_FLAG_FEAT_MAX, NMR_FLAG_WHITE_BG, NMR_FLAG_SKIP_COARSE_FEAT, NMR_FLAG_PERTURB = 1, 2, 4, 8, 16
 
 _fp = C.POINTER(C.c_float)
 
@@ -58,6 +58,7 @@ class NmrRenderArgs(C.Structure):
         ("pt3d", C.c_void_p),
         ("z_coarse", C.c_void_p), ("z_fine", C.c_void_p), ("weights_coarse", C.c_void_p), ("weights_fine", C.c_void_p),
         ("raw_coarse", C.c_void_p), ("raw_fine", C.c_void_p), ("idx_fine", C.c_void_p),
+        ("sigma_noise_coarse", C.c_void_p), ("sigma_noise_fine", C.c_void_p), ("s_fine", C.c_void_p),
     ]
 
 

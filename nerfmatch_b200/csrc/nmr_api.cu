@@ -44,7 +44,7 @@ struct nmr_handle {
   // workspace (per ray chunk)
   int64_t ws_points = 0, ws_rays = 0;
   DevBuf X, B[4], raw, zc, zf, misc, rays_view, tcws, match, bwd;
-  DevBuf stage[24];     // nmr_render_host staging
+  DevBuf stage[28];     // nmr_render_host staging
   std::string err;
   int64_t launches = 0;
   bool timing = false;
@@ -343,8 +343,8 @@ static void stage_end(nmr_handle* h, cudaStream_t s) {
 
 extern "C" int nmr_copy_host_staging(nmr_handle* h, int32_t output_index, void* dst_dev, size_t bytes, void* stream) {
   if (!h) return NMR_ERR_INVALID;
-  if (output_index < 0 || output_index >= 16 || !dst_dev) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_copy_host_staging: bad argument");
-  DevBuf& b = h->stage[4 + output_index];            // slots 0..3 are the inputs of nmr_render_host
+  if (output_index < 0 || output_index >= 17 || !dst_dev) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_copy_host_staging: bad argument");
+  DevBuf& b = h->stage[6 + output_index];            // slots 0..5 are the inputs of nmr_render_host
   if (!b.p || b.cap < bytes) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_copy_host_staging: output %d was not produced by the last nmr_render_host (or is smaller)", output_index);
   NMR_CUDA(h, cudaSetDevice(h->device));
   NMR_CUDA(h, cudaMemcpyAsync(dst_dev, b.p, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
@@ -474,6 +474,7 @@ struct HostSink {
   struct Item { char* host; const char* dev; size_t bytes_per_ray; };
   std::vector<Item> items;
   std::vector<cudaEvent_t> events;
+  float* s_fine_host = nullptr;   // s_fine needs the whole call's min / max: copied home after the last chunk
 };
 
 static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s, HostSink* sink = nullptr) {
@@ -515,7 +516,8 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
       if (pass == 0) {
         SampleParams sp{};
         sp.rays = rays; sp.n = nr; sp.ncols = a->ncols; sp.ray0 = r0; sp.S = d.sc; sp.mip = d.mip; sp.use_disp = c.use_disp;
-        sp.t_rand = a->t_rand ? a->t_rand + r0 * (d.sc + 1) : nullptr;
+        sp.perturb = !d.mip && (a->t_rand != nullptr || (a->flags & NMR_FLAG_PERTURB));     // classic mode: training only
+        sp.t_rand = a->t_rand ? a->t_rand + r0 * d.zc : nullptr;
         sp.rng_mode = a->rng_mode; sp.seed = a->seed; sp.z = zc;
         launch_sample_coarse(sp, s);
         NMR_LAUNCHED(h, "sample_coarse");
@@ -543,7 +545,8 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
         tr.rays = rays; tr.n = nr; tr.ncols = a->ncols; tr.S = S; tr.z = z; tr.ray_id = rid;
         tr.app_table = app_table; tr.num_frames = h->num_frames; tr.var_scale = c.mip_var_scale;
         tr.stop_layer = stop; tr.want_feat = want_feat; tr.ws = h->tcws.p;
-        tr.fuse_composite = h->fuse_composite && !(a->flags & NMR_FLAG_FEAT_MAX);
+        // (the in-kernel tile compositing recomputes alpha from the raw density: not with injected sigma noise)
+        tr.fuse_composite = h->fuse_composite && !(a->flags & NMR_FLAG_FEAT_MAX) && !(pass == 0 ? a->sigma_noise_coarse : a->sigma_noise_fine);
         std::string terr; int nl = 0;
         if (tc_run(d, h->tc[tcfmt][pass], tr, &raw_pass, (const void**)&feat, &partials, &nl, s, &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc_run: %s", terr.c_str());
         NMR_LAUNCHED(h, "tcgen05 mlp", nl);
@@ -555,6 +558,8 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
       CompositeParams cp{};
       cp.raw = raw_pass; cp.z = z; cp.rays = rays; cp.ncols = a->ncols; cp.n = nr; cp.S = S; cp.mip = d.mip;
       cp.flags = a->flags;
+      const float* noise = pass == 0 ? a->sigma_noise_coarse : a->sigma_noise_fine;
+      cp.sigma_noise = noise ? noise + r0 * S : nullptr;
       cp.feats = want_feat ? feat : nullptr; cp.feats_bf16 = feat_bf16;
       cp.partials = want_feat ? partials : nullptr;
       float* fo = pass == 0 ? a->feat_coarse : a->feat_fine;
@@ -574,7 +579,8 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
       if (pass == 0) {
         cp.z_next = zf; cp.nf = d.nf; cp.resample_padding = c.resample_padding;
         cp.idx_out = a->idx_fine ? a->idx_fine + r0 * (d.mip ? d.sc + 1 : d.nf) : nullptr;
-        cp.u_jitter = a->u_jitter ? a->u_jitter + r0 * (d.sc + 1) : nullptr;
+        cp.u_jitter = a->u_jitter ? a->u_jitter + r0 * (d.mip ? d.sc + 1 : d.nf) : nullptr;
+        cp.perturb = !d.mip && (a->u_jitter != nullptr || (a->flags & NMR_FLAG_PERTURB));
         cp.rng_mode = a->rng_mode; cp.seed = a->seed; cp.ray0 = r0;
       }
       launch_composite(cp, s);
@@ -583,6 +589,8 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
       // ---- optional intermediates for the parity tests ----
       float* zo = pass == 0 ? a->z_coarse : a->z_fine;
       if (zo) NMR_CUDA(h, cudaMemcpyAsync(zo + r0 * nz, z, (size_t)nr * nz * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      if (pass == 1 && a->s_fine)   // z_fine of every chunk first; mapped to s once the whole call's min / max are known
+        NMR_CUDA(h, cudaMemcpyAsync(a->s_fine + r0 * nz, z, (size_t)nr * nz * sizeof(float), cudaMemcpyDeviceToDevice, s));
       float* rawo = pass == 0 ? a->raw_coarse : a->raw_fine;
       if (rawo) NMR_CUDA(h, cudaMemcpyAsync(rawo + r0 * S * 4, raw_pass, (size_t)nr * S * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
@@ -595,6 +603,13 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
       for (auto& it : sink->items)
         NMR_CUDA(h, cudaMemcpyAsync(it.host + (size_t)r0 * it.bytes_per_ray, it.dev + (size_t)r0 * it.bytes_per_ray,
                                     (size_t)nr * it.bytes_per_ray, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+  }
+  if (a->s_fine) {   // preds["s_fine"] = t_to_s(z_fine, z_fine.min(), z_fine.max()) (renderer.py:283-285)
+    launch_t_to_s(a->s_fine, a->n * d.zf, (uint32_t*)((char*)h->misc.p + 64), s);
+    NMR_LAUNCHED(h, "t_to_s", 3);
+    if (sink && sink->s_fine_host) {
+      NMR_CUDA(h, cudaMemcpyAsync(sink->s_fine_host, a->s_fine, (size_t)a->n * d.zf * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
   }
   return NMR_OK;
@@ -744,8 +759,10 @@ extern "C" int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void*
   const size_t f = sizeof(float);
   a.rays = (const float*)in(args->rays, (size_t)n * args->ncols * f, "rays");
   a.ray_id = (const int64_t*)in(args->ray_id, (size_t)n * sizeof(int64_t), "ray_id");
-  a.t_rand = (const float*)in(args->t_rand, (size_t)n * (d.sc + 1) * f, "t_rand");
-  a.u_jitter = (const float*)in(args->u_jitter, (size_t)n * (d.sc + 1) * f, "u_jitter");
+  a.t_rand = (const float*)in(args->t_rand, (size_t)n * d.zc * f, "t_rand");
+  a.u_jitter = (const float*)in(args->u_jitter, (size_t)n * (d.mip ? d.sc + 1 : d.nf) * f, "u_jitter");
+  a.sigma_noise_coarse = (const float*)in(args->sigma_noise_coarse, (size_t)n * d.sc * f, "sigma_noise_coarse");
+  a.sigma_noise_fine = (const float*)in(args->sigma_noise_fine, (size_t)n * d.sf * f, "sigma_noise_fine");
   a.feat_coarse = (float*)out(args->feat_coarse, (size_t)n * kHid * f, "feat_coarse");
   a.feat_fine = (float*)out(args->feat_fine, (size_t)n * kHid * f, "feat_fine");
   a.pts_coarse = (float*)out(args->pts_coarse, (size_t)n * 3 * f, "pts_coarse");
@@ -762,6 +779,8 @@ extern "C" int nmr_render_host(nmr_handle* h, const nmr_render_args* args, void*
   a.raw_coarse = (float*)out(args->raw_coarse, (size_t)n * d.sc * 4 * f, "raw_coarse");
   a.raw_fine = (float*)out(args->raw_fine, (size_t)n * d.sf * 4 * f, "raw_fine");
   a.idx_fine = (int32_t*)out(args->idx_fine, (size_t)n * (d.mip ? d.sc + 1 : d.nf) * sizeof(int32_t), "idx_fine");
+  a.s_fine = (float*)out(args->s_fine, (size_t)n * d.zf * f, "s_fine");
+  if (a.s_fine) { sink.items.pop_back(); sink.s_fine_host = args->s_fine; }      // not per chunk: see HostSink
   if (stage_err != cudaSuccess) {
     cudaGetLastError();
     NMR_FAIL(h, NMR_ERR_CUDA, "nmr_render_host: staging %s failed: %s", stage_what, cudaGetErrorString(stage_err));

@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     // ---- alpha and the exclusive transmittance product ------------------------------------
     const float dnorm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
     for (int s = lane; s < S; s += 32) {
-      float sigma = fmaxf(p.raw[(ray * S + s) * 4 + 3], 0.0f);
+      float sraw = p.raw[(ray * S + s) * 4 + 3];
+      if (p.sigma_noise) sraw = sraw + p.sigma_noise[ray * S + s];   // training mode: relu(raw + noise) (render_utils.py:191-195)
+      float sigma = fmaxf(sraw, 0.0f);
       float dist = (p.mip || s < S - 1) ? (sz[s + 1] - sz[s]) : 1e10f;
       dist = dist * dnorm;
       float alpha = 1.0f - expf(-sigma * dist);
@@ -357,7 +359,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     float* comb = st;   // S + N <= kMaxSamples floats (checked in nmr_create)
     for (int j = lane; j < S; j += 32) comb[j] = sz[j];
     for (int j = lane; j < N; j += 32) {
-      float u = torch_linspace(1.0f, N, j);
+      float u;
+      if (p.perturb && (p.u_jitter != nullptr || p.rng_mode == NMR_RNG_PHILOX))       // sample_pdf(det=False): u = torch.rand (:246-247)
+        u = p.u_jitter ? p.u_jitter[ray * N + j] : philox_uniform(p.seed, (uint64_t)(p.ray0 + ray) * 1024u + j, 1u);
+      else
+        u = torch_linspace(1.0f, N, j);
       int inds = upper_bound(sa, nb, u);
       int below = max(0, inds - 1), above = min(nb - 1, inds);
       float cb = sa[below], ca = sa[above];

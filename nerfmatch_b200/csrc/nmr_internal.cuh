@@ -63,6 +63,8 @@ struct RayGenParams {
   float* rays; int* miss_flag;
 };
 void launch_raygen(const RayGenParams& p, cudaStream_t s);
+// preds["s_fine"] (renderer.py:283-285): s = t_to_s(z, min z, max z) in place over count values; scratch: 2 uint32 on the device
+void launch_t_to_s(float* z, int64_t count, uint32_t* scratch, cudaStream_t s);
 void launch_raygen_miss(const RayGenParams& p, cudaStream_t s);   // full-grid sphere-miss test (camera outside the unit sphere)
 void launch_far_fallback(float* rays, int64_t n, int ncols, const int* miss_flag, cudaStream_t s);
 
@@ -78,7 +80,8 @@ void launch_ray_op(int op, const RayOpsParams& p, cudaStream_t s);   // 0 dirs, 
 struct SampleParams {
   const float* rays; int64_t n; int ncols; int64_t ray0;  // ray0: global index of first ray (Philox)
   int S; int mip; int use_disp;
-  const float* t_rand;   // [n, S+1] or null
+  int perturb;           // classic mode: training-mode perturbation (from t_rand [n,S], or Philox when rng_mode says so)
+  const float* t_rand;   // mip [n, S+1] | classic [n, S], or null
   int rng_mode; uint64_t seed;
   float* z;              // mip [n,S+1] | normal [n,S]
 };
@@ -118,6 +121,8 @@ struct CompositeParams {
   float* z_next; int32_t* idx_out; int nf;
   const float* u_jitter; int rng_mode; uint64_t seed; int64_t ray0; float resample_padding;
   const float* weights_in; // stage API: resample from given weights instead of computing them
+  const float* sigma_noise; // [n,S] added to the raw density before the ReLU (training mode), or null
+  int perturb;             // classic mode: u_jitter [n,nf] holds the u draws of sample_pdf(det=False) (or Philox)
 };
 void launch_composite(const CompositeParams& p, cudaStream_t s);
 

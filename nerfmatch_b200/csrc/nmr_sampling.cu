@@ -9,6 +9,8 @@
 //   nerfmatch/nerf/render_utils.py:326-402         conical frustum -> diagonal Gaussian
 //   nerfmatch/nerf/embedding.py:35-46, 66-84       Fourier / IPE / PE encodings
 #include "nmr_internal.cuh"
+#include <algorithm>
+
 #include "nmr_encode.cuh"
 
 namespace nmr {
@@ -88,6 +90,36 @@ void launch_raygen(const RayGenParams& p, cudaStream_t s) {
   int n = p.h * p.w;
   raygen_kernel<<<(n + 255) / 256, 256, 0, s>>>(p);
 }
+// ---- t_to_s (render_utils.py:618-636) over a whole call's z_fine: s = (g(t) - g(near)) / (g(far) - g(near)), g(x) = 1 / (x + 1e-6),
+// near / far = min / max of ALL values (z_vals.min() / .max() over the batch).  g adds its epsilon IN PLACE (:634) and near goes
+// through it twice, so the denominator's g(near) is 1 / (near + 1e-6 + 1e-6) - reproduced here -------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__device__ __forceinline__ float ord2f(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+__global__ void minmax_kernel(const float* __restrict__ z, int64_t count, uint32_t* scratch) {
+  uint32_t lo = 0xffffffffu, hi = 0u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = f2ord(z[i]);
+    lo = min(lo, v); hi = max(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+  if ((threadIdx.x & 31) == 0) { atomicMin(scratch, lo); atomicMax(scratch + 1, hi); }
+}
+__global__ void t_to_s_kernel(float* z, int64_t count, const uint32_t* scratch) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const float eps = 1e-6f;
+  const float near1 = ord2f(scratch[0]) + eps, near2 = near1 + eps;
+  z[i] = (1.0f / (z[i] + eps) - 1.0f / near1) / (1.0f / (ord2f(scratch[1]) + eps) - 1.0f / near2);
+}
+__global__ void minmax_init_kernel(uint32_t* scratch) { scratch[0] = 0xffffffffu; scratch[1] = 0u; }
+void launch_t_to_s(float* z, int64_t count, uint32_t* scratch, cudaStream_t s) {
+  if (count == 0) return;
+  minmax_init_kernel<<<1, 1, 0, s>>>(scratch);
+  minmax_kernel<<<(unsigned)std::min<int64_t>((count + 255) / 256, 1184), 256, 0, s>>>(z, count, scratch);
+  t_to_s_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(z, count, scratch);
+}
+
 void launch_raygen_miss(const RayGenParams& p, cudaStream_t s) {
   int n = p.H * p.W;
   raygen_miss_kernel<<<(n + 255) / 256, 256, 0, s>>>(p);
@@ -163,11 +195,12 @@ __global__ void sample_coarse_kernel(SampleParams p) {
   int j = (int)(i - ray * nz);
   const float* r = p.rays + ray * p.ncols;
   float near = r[6], far = r[7];
-  float t = lerp_nf(near, far, torch_linspace(1.0f, nz, j), p.mip ? 0 : p.use_disp);
-  if (p.mip && (p.t_rand != nullptr || p.rng_mode == NMR_RNG_PHILOX)) {
-    // stratified jitter inside half-bins (render_utils.py:440-445)
-    float tp = (j > 0) ? lerp_nf(near, far, torch_linspace(1.0f, nz, j - 1), 0) : t;
-    float tn = (j < nz - 1) ? lerp_nf(near, far, torch_linspace(1.0f, nz, j + 1), 0) : t;
+  const int ud = p.mip ? 0 : p.use_disp;
+  float t = lerp_nf(near, far, torch_linspace(1.0f, nz, j), ud);
+  if ((p.mip || p.perturb) && (p.t_rand != nullptr || p.rng_mode == NMR_RNG_PHILOX)) {
+    // stratified jitter inside half-bins: mip always (render_utils.py:440-445), classic in training mode (:118-126)
+    float tp = (j > 0) ? lerp_nf(near, far, torch_linspace(1.0f, nz, j - 1), ud) : t;
+    float tn = (j < nz - 1) ? lerp_nf(near, far, torch_linspace(1.0f, nz, j + 1), ud) : t;
     float upper = (j < nz - 1) ? 0.5f * (tn + t) : t;
     float lower = (j > 0) ? 0.5f * (t + tp) : t;
     float u = p.t_rand ? p.t_rand[i] : philox_uniform(p.seed, (uint64_t)(p.ray0 + ray) * 1024u + j, 0u);

@@ -232,12 +232,14 @@ class Engine:
         return out
 
     def make_args(self, n: int, ncols: int, rays=None, ray_id=None, t_rand=None, u_jitter=None, flags=0,
-                  rng_mode=L.NMR_RNG_NONE, seed=0, unnorm=None, outs: Optional[Dict[str, torch.Tensor]] = None):
+                  rng_mode=L.NMR_RNG_NONE, seed=0, unnorm=None, outs: Optional[Dict[str, torch.Tensor]] = None,
+                  sigma_noise_coarse=None, sigma_noise_fine=None):
         a = L.NmrRenderArgs()
         a.rays, a.n, a.ncols, a.flags = _ptr(rays), n, ncols, flags
         a.ray_id, a.t_rand, a.u_jitter = _ptr(ray_id), _ptr(t_rand), _ptr(u_jitter)
+        a.sigma_noise_coarse, a.sigma_noise_fine = _ptr(sigma_noise_coarse), _ptr(sigma_noise_fine)
         a.rng_mode, a.seed = rng_mode, seed
-        keep = [rays, ray_id, t_rand, u_jitter]
+        keep = [rays, ray_id, t_rand, u_jitter, sigma_noise_coarse, sigma_noise_fine]
         if unnorm is not None:
             un = (C.c_float * 12)(*[float(v) for v in torch.as_tensor(unnorm, dtype=torch.float32)[:3, :4].reshape(-1).tolist()])
             a.unnorm = C.cast(un, C.c_void_p)
@@ -247,7 +249,8 @@ class Engine:
             keep.append(t)
         return a, keep
 
-    def alloc_outputs(self, n: int, want_feat: bool, want_pt3d: bool, intermediates: bool = False, device=None, pin=False):
+    def alloc_outputs(self, n: int, want_feat: bool, want_pt3d: bool, intermediates: bool = False, device=None, pin=False,
+                      training: bool = False):
         cfg = self.cfg
         dev = self.device if device is None else device
 
@@ -264,6 +267,8 @@ class Engine:
             o[f"depth_{key}"] = e(n)
         if want_pt3d:
             o["pt3d"] = e(n, 3)
+        if training:         # forward(validation=False): s_fine / weights_fine (renderer.py:283-286)
+            o["s_fine"], o["weights_fine"] = e(n, cfg.z_fine), e(n, cfg.s_fine)
         if intermediates:
             o["z_coarse"], o["z_fine"] = e(n, cfg.z_coarse), e(n, cfg.z_fine)
             o["weights_coarse"], o["weights_fine"] = e(n, cfg.num_pts_coarse), e(n, cfg.s_fine)

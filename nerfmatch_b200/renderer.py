@@ -4,10 +4,11 @@ Same constructor, attributes, ``state_dict`` keys and return dictionaries; the w
 libnmr.so (hand-written sm_100a CUDA) through the C ABI in include/nmr.h.  PyTorch is used for
 device memory, the current stream, random draws and ``torch.distributed`` only.
 
-What is built is the inference path the evaluators use (``predict`` / ``forward(validation=True)``
-/ ``render_novel_view``).  Training-mode forward (perturb, sigma noise, ``s_fine`` /
-``weights_fine`` outputs; renderer.py:217, 242, 283-286), ``out_scr`` heads, ``single_model`` and
-``pfeat_mask`` are outside the hot-path scope and raise ``NotImplementedError``.
+Built: the inference path the evaluators use (``predict`` / ``forward(validation=True)`` /
+``render_novel_view``) and the training-mode FORWARD (``forward(validation=False)``: perturbed
+sampling, sigma noise, ``s_fine`` / ``weights_fine`` outputs; renderer.py:217, 242, 283-286) -
+outputs carry no autograd graph w.r.t. the network weights (optimising the NeRF itself is outside the
+hot-path scope).  ``out_scr`` heads, ``single_model`` and ``pfeat_mask`` raise ``NotImplementedError``.
 """
 from __future__ import annotations
 
@@ -133,6 +134,26 @@ class NerfRenderer(nn.Module):
             f |= L.NMR_FLAG_WHITE_BG
         return f
 
+    def _train_draws(self, n, device):
+        """Training-mode randomness (``self.training``): the reference's draws, made with the same calls, shapes, devices and
+        ORDER so that a seeded run consumes the generators identically (coarse sampling draw, coarse sigma noise, fine
+        sampling draw, fine sigma noise):
+          mip      torch.rand [n,Sc+1] (render_utils.py:444) . randn [n,Sc] (:191) . uniform_ [n,Sc+1] (:483-485) . randn [n,Sc]
+          classic  torch.rand_like [n,Sc] (:122) . randn [n,Sc] . torch.rand [n,Nf] ON THE CPU (:247, then .to(device)) . randn [n,Sc+Nf]
+        ``perturb`` gates the classic sampling draws only (mip jitters regardless); ``noise_std`` <= 0 skips the noise."""
+        mip = self.embed_type == "mip"
+        Sc, Nf = self.num_pts_coarse, self.num_pts_fine
+        noise = lambda S: (torch.randn(n, S, device=device) * self.noise_std) if self.noise_std > 0.0 else None
+        if mip:
+            t_rand = torch.rand(n, Sc + 1, device=device)
+            nc = noise(Sc)
+            u = torch.empty(n, Sc + 1, device=device).uniform_(to=(1 / (Sc + 1) - _EPS32))
+            return t_rand, u, nc, noise(Sc)
+        t_rand = torch.rand(n, Sc, device=device) if self.perturb else None
+        nc = noise(Sc)
+        u = torch.rand(n, Nf).to(device) if self.perturb else None
+        return t_rand, u, nc, noise(Sc + Nf)
+
     def _draws(self, n, device):
         """mip mode jitters samples even at inference (``randomized`` is never overridden,
         renderer.py:211-221).  With rng='torch' the two draws are made with the same calls, shapes
@@ -173,12 +194,7 @@ class NerfRenderer(nn.Module):
 
     def render_rays(self, rays, ray_id=None, validation=False, _intermediates=False, _unnorm=None):
         """Hierarchical coarse->fine render of a ray batch (reference renderer.py:182-295)."""
-        if not validation:
-            raise NotImplementedError(
-                "training-mode forward (perturb / sigma noise / s_fine / weights_fine) is outside the built hot path; "
-                "call predict() or forward(validation=True)"
-            )
-        if self.pfeat_mask is not None:
+        if self.pfeat_mask is not None and self.ret_pfeat:
             raise NotImplementedError("pfeat_mask is a training-validation feature (out of scope)")
         if rays.device.type != "cuda":
             raise RuntimeError("NerfRenderer (nerfmatch_b200) renders CUDA ray tensors only: there is no CPU fallback")
@@ -189,16 +205,25 @@ class NerfRenderer(nn.Module):
             ray_id = ray_id.detach().to(device=rays.device, dtype=torch.int64).contiguous()
         else:
             ray_id = None if not self.appearance_embedding else torch.ones(n, dtype=torch.int64, device=rays.device)
-        t_rand, u_jit, rng_mode, seed = self._draws(n, rays.device)
-        outs = eng.alloc_outputs(n, self.ret_pfeat, _unnorm is not None, intermediates=_intermediates)
+        noise_c = noise_f = None
+        if self.training:                   # perturb / noise_std act in training mode only (renderer.py:217, 242)
+            t_rand, u_jit, noise_c, noise_f = self._train_draws(n, rays.device)
+            rng_mode, seed = L.NMR_RNG_NONE, 0
+        else:
+            t_rand, u_jit, rng_mode, seed = self._draws(n, rays.device)
+        outs = eng.alloc_outputs(n, self.ret_pfeat, _unnorm is not None, intermediates=_intermediates, training=not validation)
         args, keep = eng.make_args(n, ncols, rays=rays, ray_id=ray_id, t_rand=t_rand, u_jitter=u_jit, flags=self._flags(),
-                                   rng_mode=rng_mode, seed=seed, unnorm=_unnorm, outs=outs)
+                                   rng_mode=rng_mode, seed=seed, unnorm=_unnorm, outs=outs, sigma_noise_coarse=noise_c, sigma_noise_fine=noise_f)
         eng.render(args)
         preds = {}
         for key in ("coarse", "fine"):      # key order of the reference dict
             if self.ret_pfeat:
                 preds[f"feat_{key}"] = outs[f"feat_{key}"]
-            preds[f"pts_{key}"] = outs[f"pts_{key}"]
+            if validation:                  # pts_* only under validation (renderer.py:276-281) ...
+                preds[f"pts_{key}"] = outs[f"pts_{key}"]
+            elif key == "fine":             # ... s_fine / weights_fine only without it (:283-286)
+                preds["s_fine"] = outs["s_fine"]
+                preds["weights_fine"] = outs["weights_fine"]
             preds[f"rgb_{key}"] = outs[f"rgb_{key}"]
             preds[f"depth_{key}"] = outs[f"depth_{key}"]
         for k, v in outs.items():

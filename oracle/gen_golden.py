@@ -541,6 +541,51 @@ def cache_cases(r):
     return out
 
 
+def train_cases(r):
+    """Training-mode forward: the reference's NerfRenderer.forward(validation=False) with
+    set_training_mode(True) - perturbed sampling, sigma noise, s_fine / weights_fine outputs (renderer.py:217, 242, 283-286;
+    nerf_trainer.py:140-147) - on CPU, with the random draws it consumed replayed in the same order from the same seed."""
+    import torch
+
+    from oracle.weights import K_7SCENES, make_pose, make_state_dict
+
+    torch.set_grad_enabled(False)
+    out = {}
+    for tag, embed, pfeat, seed in (("mip", "mip", False, 31), ("normal", "normal", True, 32)):
+        c = dict(embed=embed, nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False, sigma_target=(2.0, 1.0), ds=60, seed=seed)
+        rays0 = r.sample_nerf_rays(480, 640, torch.from_numpy(K_7SCENES), torch.from_numpy(make_pose(seed)), ds=c["ds"], embed_type=embed)
+        c["sigma_gain"], c["sigma_bias"] = calibrate_sigma(c, rays0.numpy())
+        torch.manual_seed(0)
+        ren = r.NerfRenderer(ref_config(embed, 64, 128, False, False), num_frames=None, training=True, stop_layer=3)
+        sd = make_state_dict(seed, embed_type=embed, sigma_gain=c["sigma_gain"], sigma_bias=c["sigma_bias"])
+        ren.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
+        ren.ret_pfeat = pfeat
+        ren.set_training_mode(True)
+        rays = rays0
+        n = rays.shape[0]
+        torch.manual_seed(13)
+        preds = ren.forward(rays, step=0, ray_id=None, validation=False)
+        assert "pts_fine" not in preds and "s_fine" in preds and "weights_fine" in preds
+        # replay the draws in the order the reference consumed them (all on the CPU generator here)
+        torch.manual_seed(13)
+        if embed == "mip":
+            t_rand = torch.rand(n, 65)
+            noise_c = torch.randn(n, 64) * 1.0
+            u = torch.empty(n, 65).uniform_(to=(1 / 65 - torch.finfo(torch.float32).eps))
+            noise_f = torch.randn(n, 64) * 1.0
+        else:
+            t_rand = torch.rand(n, 64)
+            noise_c = torch.randn(n, 64) * 1.0
+            u = torch.rand(n, 128)
+            noise_f = torch.randn(n, 192) * 1.0
+        out.update({f"{tag}.rays": rays.numpy(), f"{tag}.t_rand": t_rand.numpy(), f"{tag}.u": u.numpy(), f"{tag}.noise_coarse": noise_c.numpy(),
+                    f"{tag}.noise_fine": noise_f.numpy(), f"{tag}.case": np.array(repr(c)), f"{tag}.keys": np.array(list(preds.keys()))})
+        for k, v in preds.items():
+            out[f"{tag}.{k}"] = v.numpy()
+        print(tag, "keys", list(preds.keys()), "acc_f", preds["weights_fine"].sum(-1).mean().item())
+    return out
+
+
 def main():
     r = import_reference()
     gdir = os.path.join(os.path.dirname(HERE), "tests", "golden")
@@ -556,7 +601,7 @@ def main():
               "acc_c %.3f acc_f %.3f" % (out["weights_coarse"].sum(-1).mean(), out["weights_fine"].sum(-1).mean()),
               "wmax_f %.3f" % out["weights_fine"].max(-1).mean(), str(out["case"]))
     for fname, fn in (("raygen.npz", raygen_cases), ("stages.npz", stage_cases), ("match.npz", lambda _r: match_cases()),
-                      ("rayhelpers.npz", rayhelper_cases), ("inerf_grad.npz", inerf_cases), ("cache_format.npz", cache_cases)):
+                      ("rayhelpers.npz", rayhelper_cases), ("inerf_grad.npz", inerf_cases), ("cache_format.npz", cache_cases), ("train_forward.npz", train_cases)):
         if only and fname not in only:
             continue
         out = fn(r)

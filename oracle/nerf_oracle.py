@@ -315,28 +315,35 @@ def resample_gaus_along_rays(rays, t_vals, weights, u_jitter, resample_padding=0
 # ----------------------------------------------------------------------------------
 # classic NeRF sampling   (render_utils.py:107-148, 233-264)
 # ----------------------------------------------------------------------------------
-def sample_pts_init(rays, S: int, use_disp: bool = False):
-    """render_utils.py:107-129 with perturb=False (inference)."""
+def sample_pts_init(rays, S: int, use_disp: bool = False, t_rand: Optional[np.ndarray] = None):
+    """render_utils.py:107-129; ``t_rand`` [n,S] is the torch.rand_like draw of the perturb=True (training) branch
+    (:118-126), None -> perturb=False (inference)."""
     o, d, near, far = rays[:, 0:3], rays[:, 3:6], rays[:, 6:7], rays[:, 7:8]
     tau = torch_linspace01(S)[None, :]
     if use_disp:
         z = F32(1.0) / (F32(1.0) / near * (F32(1) - tau) + F32(1.0) / far * tau)
     else:
         z = near * (F32(1) - tau) + far * tau
+    z = np.broadcast_to(z.astype(F32), (rays.shape[0], S))
+    if t_rand is not None:
+        mids = F32(0.5) * (z[:, :-1] + z[:, 1:])
+        upper = np.concatenate([mids, z[:, -1:]], -1)
+        lower = np.concatenate([z[:, :1], mids], -1)
+        z = lower + (upper - lower) * t_rand.astype(F32)
     z = np.ascontiguousarray(z.astype(F32))
     pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
     return pts.astype(F32), z
 
 
-def sample_pdf_det(bins, weights, N: int):
-    """render_utils.py:233-264 with det=True.  bins [n,B], weights [n,B-1] ->
-    samples [n,N], inds int32 [n,N] (the raw searchsorted result of :251)."""
+def sample_pdf_det(bins, weights, N: int, u: Optional[np.ndarray] = None):
+    """render_utils.py:233-264.  bins [n,B], weights [n,B-1] -> samples [n,N], inds int32 [n,N] (the raw searchsorted
+    result of :251).  ``u`` [n,N]: the torch.rand draw of det=False (training); None -> det=True (linspace)."""
     w = (weights + F32(1e-5)).astype(F32)
     pdf = (w / rowsum_f64(w)).astype(F32)
     cdf = cumsum_f64acc(pdf)
     n = w.shape[0]
     cdf = np.concatenate([np.zeros((n, 1), F32), cdf], -1)
-    u = np.broadcast_to(torch_linspace01(N), (n, N))
+    u = np.broadcast_to(torch_linspace01(N), (n, N)) if u is None else np.ascontiguousarray(u, F32)
     inds = np.empty((n, N), np.int64)
     for r in range(n):
         inds[r] = np.searchsorted(cdf[r], u[r], side="right")
@@ -350,11 +357,11 @@ def sample_pdf_det(bins, weights, N: int):
     return (bb + t * (ba - bb)).astype(F32), inds.astype(np.int32)
 
 
-def sample_pts_fine(rays, z_vals, weights, N: int):
+def sample_pts_fine(rays, z_vals, weights, N: int, u: Optional[np.ndarray] = None):
     """render_utils.py:132-148: 63 mid-point bins, weights[1:-1], sort(cat(z, samples))."""
     o, d = rays[:, 0:3], rays[:, 3:6]
     z_mid = F32(0.5) * (z_vals[:, 1:] + z_vals[:, :-1])
-    samples, inds = sample_pdf_det(z_mid, weights[:, 1:-1], N)
+    samples, inds = sample_pdf_det(z_mid, weights[:, 1:-1], N, u)
     z = np.sort(np.concatenate([z_vals, samples], -1), axis=-1).astype(F32)
     pts = o[:, None, :] + d[:, None, :] * z[:, :, None]
     return pts.astype(F32), z, inds
@@ -451,10 +458,20 @@ def encode_points(cfg: RenderConfig, pts, var, viewdirs, app_emb, S: int) -> np.
 # ----------------------------------------------------------------------------------
 # volume rendering + compositing   (render_utils.py:176-230, renderer.py:250-281)
 # ----------------------------------------------------------------------------------
-def volume_render(raw: np.ndarray, z_vals: np.ndarray, rays_d: np.ndarray, mip: bool, white_bg=False):
-    """volume_render_radiance_field at inference (noise_std=0).  raw [n,S,4]."""
+def t_to_s(z: np.ndarray) -> np.ndarray:
+    """render_utils.py:618-636 as renderer.py:283-285 calls it: near / far are the min / max over the WHOLE batch, and
+    g(x) = 1 / (x + 1e-6) adds its epsilon IN PLACE (:634) - ``near`` is passed to g twice, so the second call (in the
+    denominator) sees near + 2e-6: s = (1/(t+e) - 1/(near+e)) / (1/(far+e) - 1/(near+e+e))."""
+    eps = F32(1e-6)
+    near1 = z.min() + eps
+    near2 = near1 + eps
+    return ((F32(1) / (z + eps) - F32(1) / near1) / (F32(1) / (z.max() + eps) - F32(1) / near2)).astype(F32)
+
+
+def volume_render(raw: np.ndarray, z_vals: np.ndarray, rays_d: np.ndarray, mip: bool, white_bg=False, noise: Optional[np.ndarray] = None):
+    """volume_render_radiance_field; ``noise`` [n,S] = randn * noise_std of the training mode (None: inference).  raw [n,S,4]."""
     rgb = raw[..., :3]
-    density = np.maximum(raw[..., 3] + F32(0), F32(0))
+    density = np.maximum(raw[..., 3] + (F32(0) if noise is None else noise.astype(F32)), F32(0))
     dists = z_vals[:, 1:] - z_vals[:, :-1]
     if mip:
         z_mids = F32(0.5) * (z_vals[:, :-1] + z_vals[:, 1:])
@@ -510,11 +527,18 @@ def render_rays(
     ray_id: Optional[np.ndarray] = None,
     keep_intermediates: bool = False,
     chunk: int = 4096,
+    validation: bool = True,
+    noise_coarse: Optional[np.ndarray] = None,
+    noise_fine: Optional[np.ndarray] = None,
 ) -> Dict[str, np.ndarray]:
-    """NerfRenderer.render_rays with validation=True (renderer.py:182-295), chunked over
-    rays only to bound memory (rays are independent)."""
+    """NerfRenderer.render_rays (renderer.py:182-295), chunked over rays only to bound memory (rays are independent).
+    Training mode (validation=False, one chunk only because s_fine normalises over the batch): ``t_rand`` / ``u_jitter``
+    are then also the classic mode's perturbation [n,Sc] and sample_pdf draws [n,Nf]; ``noise_*`` the scaled sigma noise;
+    outputs drop pts_* and gain s_fine / weights_fine (:276-286)."""
     rays = np.ascontiguousarray(rays, F32)
     n = rays.shape[0]
+    if not validation:
+        chunk = max(chunk, n)
     if n > chunk:
         parts = []
         for s in range(0, n, chunk):
@@ -556,9 +580,9 @@ def render_rays(
             S = z_vals.shape[1] - 1
         else:
             if key == "coarse":
-                pts, z_vals = sample_pts_init(rays, cfg.num_pts_coarse, cfg.use_disp)
+                pts, z_vals = sample_pts_init(rays, cfg.num_pts_coarse, cfg.use_disp, t_rand)
             else:
-                pts, z_vals, idx = sample_pts_fine(rays, z_vals, weights, cfg.num_pts_fine)
+                pts, z_vals, idx = sample_pts_fine(rays, z_vals, weights, cfg.num_pts_fine, u_jitter)
                 if keep_intermediates:
                     out["idx_fine"] = idx
             var = None
@@ -567,11 +591,15 @@ def render_rays(
         raw, feat = mlp_forward(w, x, cfg, cfg.stop_layer if key == "fine" else cfg.stop_layer_coarse)
         raw = raw.reshape(n, S, 4)
         feat = feat.reshape(n, S, -1)
-        rgb_map, disp, acc, weights, depth = volume_render(raw, z_vals, rays_d, mip, cfg.white_bg)
+        rgb_map, disp, acc, weights, depth = volume_render(raw, z_vals, rays_d, mip, cfg.white_bg, noise_coarse if key == "coarse" else noise_fine)
         f, p = composite(weights, feat, pts, cfg.feat_comb)
         if cfg.ret_pfeat:
             out[f"feat_{key}"] = f
-        out[f"pts_{key}"] = p
+        if validation:
+            out[f"pts_{key}"] = p
+        elif key == "fine":
+            out["s_fine"] = t_to_s(z_vals)
+            out["weights_fine"] = weights
         out[f"rgb_{key}"] = rgb_map
         out[f"depth_{key}"] = depth
         if keep_intermediates:

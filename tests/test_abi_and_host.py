@@ -64,7 +64,7 @@ def test_no_cpu_fallback_without_gpu():
     from nerfmatch_b200 import _lib as L
 
     lib = L.load()
-    cfg = L.NmrConfig(abi_version=1, embed_type=1, xyz_num_freqs=15, dirs_num_freqs=4, num_pts_coarse=64, num_pts_fine=128,
+    cfg = L.NmrConfig(abi_version=L.ABI_VERSION, embed_type=1, xyz_num_freqs=15, dirs_num_freqs=4, num_pts_coarse=64, num_pts_fine=128,
                       hid_dim=256, layer_num=8, skip_layer=4, app_dim=0, stop_layer_coarse=-1, stop_layer_fine=3)
     h = C.c_void_p()
     assert lib.nmr_create(C.byref(cfg), C.byref(h)) == -2 and not h.value  # NMR_ERR_CUDA
@@ -81,10 +81,10 @@ def test_create_rejects_bad_configs():
     h = C.c_void_p()
     bad_abi = L.NmrConfig(abi_version=99)
     assert lib.nmr_create(C.byref(bad_abi), C.byref(h)) == -1
-    wide = L.NmrConfig(abi_version=1, embed_type=1, xyz_num_freqs=15, dirs_num_freqs=4, num_pts_coarse=64, num_pts_fine=128,
+    wide = L.NmrConfig(abi_version=L.ABI_VERSION, embed_type=1, xyz_num_freqs=15, dirs_num_freqs=4, num_pts_coarse=64, num_pts_fine=128,
                        hid_dim=512, layer_num=8, skip_layer=4)
     assert lib.nmr_create(C.byref(wide), C.byref(h)) == -4  # NMR_ERR_UNSUPPORTED
-    many = L.NmrConfig(abi_version=1, embed_type=0, xyz_num_freqs=15, dirs_num_freqs=4, num_pts_coarse=192, num_pts_fine=128,
+    many = L.NmrConfig(abi_version=L.ABI_VERSION, embed_type=0, xyz_num_freqs=15, dirs_num_freqs=4, num_pts_coarse=192, num_pts_fine=128,
                        hid_dim=256, layer_num=8, skip_layer=4)
     assert lib.nmr_create(C.byref(many), C.byref(h)) == -4
     assert lib.nmr_create(None, C.byref(h)) == -1

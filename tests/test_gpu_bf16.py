@@ -124,7 +124,7 @@ def test_fp16_operands_saturate_and_reject_out_of_range_weights():
     cfg = O.RenderConfig(embed_type="normal")
     sd = make_state_dict(66, embed_type="normal", sigma_gain=30.0, sigma_bias=1.0)
     wts = {k: torch.from_numpy(v.copy()) for k, v in O.split_state_dict(sd, "nerf_fine.").items()}
-    wts["pts_linears.0.weight"] *= 3e4                               # layer-0 outputs ~1e5: beyond 65504
+    wts["pts_linears.0.weight"] *= 2e5                               # layer-0 outputs ~3e5: beyond 65504 (weights ~2e4 still fit)
     x = (torch.rand(256, cfg.xyz_dim + cfg.dirs_dim, device=DEV, generator=torch.Generator(DEV).manual_seed(4)) * 2 - 1)
     eng = engine(embed_type="normal", precision="fp16"); eng.set_weights(0, wts)
     h0 = eng.stage_mlp_probe(0, x, 0)
