@@ -111,7 +111,7 @@ def run_reference(args):
 def config_block(embed, precision, rays_per_step=H * W):
     return {"workload": f"7-Scenes {H}x{W} full-res feature render, {embed} embedding, 64 coarse + 128 fine samples "
                         f"({256 if embed == 'normal' else 128} MLP evals/ray), stop_layer=3, random-init weights",
-            "rays_per_step_per_gpu": rays_per_step, "precision": precision, "parallelism": "rays sharded by view (one view per GPU per step), weights replicated, feat_fine + pt3d gathered to rank 0 (NCCL) when N > 1",
+            "rays_per_step_per_gpu": rays_per_step, "precision": precision, "parallelism": "rays sharded by view (one view per GPU per step), weights replicated; when N > 1 feat_fine + pt3d are delivered to rank 0 inside the timed step (peer-memory stores over NVLink, NCCL for setup / barriers)",
             "l2": "256 MiB buffer written between timed steps (L2 flush); per-step working set is also >> 126 MB"}
 
 
@@ -195,28 +195,45 @@ def run_ours(args):
     h2d = rays_h.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in outs_h.values())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    # N > 1: the one real exchange of the path - rendered features + 3D points gathered to the matcher's rank 0
-    gbuf = None
+    # N > 1: the one real exchange of the path - rendered features + 3D points delivered to the matcher's rank 0.  Product
+    # form (dist.PeerBuffers): rank 0 owns the gathered maps, every rank's render kernels store their rows straight into
+    # them over NVLink (the output pointers of the render ARE peer addresses); a flag per producer orders rank 0's stream
+    # behind the stores.  The NCCL gather after the render (the round-1 form) is kept below as comparison + verification.
+    EX = ("feat_fine", "pt3d")
+    pb = None
     if world > 1:
-        gbuf = {k: ([torch.empty_like(outs[k]) for _ in range(world)] if rank == 0 else None) for k in ("feat_fine", "pt3d")}
-
-    def gather_to_matcher(o):
-        if world > 1:
-            for k in ("feat_fine", "pt3d"):
-                dist.gather(o[k], gbuf[k], dst=0)
+        from nerfmatch_b200.dist import PeerBuffers
+        pb = PeerBuffers(eng, {"feat_fine": (world * n, 256), "pt3d": (world * n, 3)}, dst=0)
+        peer_outs = dict(outs)
+        peer_outs.update(pb.out_ptrs(rank * n))
+        dargs, keep = eng.make_args(n, rays.shape[1], rays=rays, flags=flags, rng_mode=rng_mode, seed=1234, unnorm=un, outs=peer_outs)
+        gbuf = {k: ([torch.empty_like(outs[k]) for _ in range(world)] if rank == 0 else None) for k in EX}
+        nargs, keep_n = eng.make_args(n, rays.shape[1], rays=rays, flags=flags, rng_mode=rng_mode, seed=1234, unnorm=un, outs=outs)
 
     def step_dev():
+        if pb is not None:
+            pb.begin()
         eng.render(dargs)
-        gather_to_matcher(outs)
+        if pb is not None:
+            pb.publish()
+            if rank == 0:
+                pb.wait()
 
-    outs_back = {k: torch.empty_like(outs[k]) for k in ("feat_fine", "pt3d")} if world > 1 else None
+    def step_nccl():                         # comparison leg: render into local tensors, then dist.gather (NCCL send / recv)
+        eng.render(nargs)
+        for k in EX:
+            dist.gather(outs[k], gbuf[k], dst=0)
 
     def step_host():
+        if pb is not None:
+            pb.begin()
         eng.render_host(hargs)
-        if world > 1:   # the matcher's rank also needs the other ranks' feature maps: gather the device-side staging copies
-            for k in ("feat_fine", "pt3d"):
-                eng.copy_host_staging(k, outs_back[k])
-            gather_to_matcher(outs_back)
+        if pb is not None:   # the matcher's rank also needs the other ranks' maps: device-side staging copies -> peer memory
+            for k, p_ in pb.out_ptrs(rank * n).items():
+                eng.copy_host_staging(k, p_, outs[k].numel() * 4)
+            pb.publish()
+            if rank == 0:
+                pb.wait()
 
     def barrier():
         if world > 1:
@@ -270,6 +287,45 @@ def run_ours(args):
     eng.set_timing(False)
     # ---- end-to-end arm ----
     ms_e2e, _, _ = timed(step_host, args.steps, max(3, args.warmup))
+    exchange = None
+    if world > 1:
+        # same step with the NCCL gather after the render; its result also verifies the peer-delivered maps bit for bit
+        step_dev()
+        ms_nccl, _, _ = timed(step_nccl, args.steps, 2)
+        ok = True
+        if rank == 0:
+            torch.cuda.synchronize(dev)
+            pb.check()
+            for k in EX:
+                ok = ok and torch.equal(pb.tensor(k), torch.cat(gbuf[k], 0))
+        exchange = {"form": "peer stores from the compositing kernel into rank 0's memory (CUDA IPC over NVLink), flag per producer",
+                    "bytes_into_rank0_per_step": (world - 1) * n * (256 + 3) * 4, "verified_equal_to_nccl_gather": bool(ok),
+                    "ms_per_step_peer": ms_dev / args.steps, "ms_per_step_nccl_gather": ms_nccl / args.steps}
+        if rank == 0 and not ok:
+            raise SystemExit("peer-delivered maps differ from the NCCL gather")
+
+    # ---- BASELINE config 4: a batch of 64 query poses at matcher resolution (ds=8: 60 x 80 rays each), the rays of all views
+    #      flattened and sharded across the ranks (STRONG scaling: 307 200 rays in total at every N), maps delivered to rank 0 ----
+    from nerfmatch_b200.dist import render_views_sharded
+    un4 = np.eye(4, dtype=np.float32); un4[:3, :3] *= 3.0
+    c2ws = torch.stack([torch.from_numpy(un4 @ make_pose(200 + v)) for v in range(64)])
+    Kt = torch.from_numpy(K_7SCENES)
+
+    def step_cfg4():
+        return render_views_sharded(ren, (H, W), Kt, c2ws, un4, downsample=8, dst=0)
+
+    ms_cfg4, _, _ = timed(step_cfg4, args.steps, 2)
+    # ---- same tcgen05 kernel with fp16 operands (NMR_PREC_FP16): informational second measurement of the headline step ----
+    other = None
+    if args.precision in ("bf16", "fp16") and world == 1:
+        alt = "fp16" if args.precision == "bf16" else "bf16"
+        ren.precision = alt
+        ren.engine(dev)
+        ms_alt, _, _ = timed(step_dev, args.steps, 2)
+        ren.precision = args.precision
+        ren.engine(dev)
+        other = {"precision": alt, "value": n * args.steps / (ms_alt / 1e3), "unit": "rays/s", "ms_per_step": ms_alt / args.steps,
+                 "note": "same kernel, other 16-bit operand format; parity of both in profiles/r02_parity.json"}
 
     total_rays = n * world
     value = total_rays * args.steps / (ms_dev / 1e3)
@@ -297,6 +353,12 @@ def run_ours(args):
                      "flops_per_launch_set": flops_step, "ms_per_step": mlp_s * 1e3},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
     }
+    if exchange is not None:
+        line["exchange"] = exchange
+    line["config4"] = {"workload": "64 query poses x 4800 rays (480x640, ds=8), rays of all views sharded across the ranks, pt_feat / pt3d / im_pred delivered to rank 0",
+                       "scaling": "strong", "rays": 64 * 4800, "ms_per_batch": ms_cfg4 / args.steps, "value": 64 * 4800 * args.steps / (ms_cfg4 / 1e3), "unit": "rays/s"}
+    if other is not None:
+        line["other_operand_format"] = other
     # compositing kernel: HBM-bound side of the path (SURVEY.md 8d byte counts, bf16 | fp32 features), measured with the
     # per-sample features streamed from HBM (kernel (c) standalone); the bf16 product path composites the features tile by
     # tile inside the MLP kernel, its (small, latency-bound) compositor is reported as composite_fused.

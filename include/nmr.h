@@ -216,6 +216,30 @@ NMR_API int nmr_stage_composite(nmr_handle* h, const float* raw, const float* z,
                         float* depth, float* acc, float* disp, float* weights, float* feat_out,
                         float* pts_out, void* stream);
 
+/* ---- multi-GPU exchange: peer-memory outputs ----------------------------------------------------------------
+ * The one exchange of the path is "rendered feature map + 3D points -> the matcher's rank" (dist.gather in the reference's
+ * terms, BASELINE config 4).  Every output pointer of nmr_render_args may be a PEER pointer - memory of another GPU of the
+ * same box mapped over NVLink / NVSwitch - so the compositing kernel's own stores deliver the rows while later chunks are
+ * still rendering.  nmr_peer_alloc / nmr_peer_open create and map such buffers across processes (CUDA IPC; one process per
+ * GPU), nmr_peer_signal / nmr_peer_wait order a consumer stream on the matcher rank behind the producers' stores.
+ *
+ * Allocate `bytes` of zeroed device memory on this handle's device and export it (64-byte IPC handle, to be sent to the other
+ * ranks with any byte transport, e.g. torch.distributed.broadcast). */
+typedef struct nmr_peer_handle { unsigned char bytes[64]; } nmr_peer_handle;
+NMR_API int nmr_peer_alloc(nmr_handle* h, size_t bytes, void** dev_ptr, nmr_peer_handle* out);
+NMR_API int nmr_peer_free(nmr_handle* h, void* dev_ptr);
+/* Map a buffer exported by ANOTHER process into this process; the returned pointer is valid in kernels and copies on this
+ * handle's device (peer access is enabled on first use). */
+NMR_API int nmr_peer_open(nmr_handle* h, const nmr_peer_handle* in, void** peer_ptr);
+NMR_API int nmr_peer_close(nmr_handle* h, void* peer_ptr);
+/* Producer: after all work enqueued on `stream` so far, publish `value` (a step counter) in the uint32 at `flag` (normally a
+ * slot of a peer buffer on the matcher's rank).  Consumer: make `stream` wait until each of the `count` uint32 flags at
+ * `flags` (local memory) has reached `value`; a producer that does not arrive within ~2 s sets *late (host, optional, read
+ * after synchronising the stream) to 1 + its index instead of hanging the device. */
+NMR_API int nmr_peer_signal(nmr_handle* h, uint32_t* flag, uint32_t value, void* stream);
+NMR_API int nmr_peer_wait(nmr_handle* h, const uint32_t* flags, int32_t count, uint32_t value, void* stream);
+NMR_API int nmr_peer_wait_status(nmr_handle* h);   /* 0, or 1 + index of the first late producer since the last call */
+
 /* ---- next row: the differentiable render of the iNeRF pose refinement -----------------------------------------
  * NeRFMatchEvaluator.inerf_refinement (nerfmatch_evaluator.py:288-500) optimises the camera pose with Adam through
  *   gen_rays (:232-285, torch) -> xyz_encoder / dirs_encoder (:377-383) -> nerf_fine.forward (:395-404)

@@ -84,6 +84,13 @@ SYMBOLS = {
     "nmr_stage_encode_backward": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp, _vp, _vp]),
     "nmr_stage_mlp_backward": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "nmr_stage_composite_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nmr_peer_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp), _vp]),
+    "nmr_peer_free": (C.c_int, [_vp, _vp]),
+    "nmr_peer_open": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "nmr_peer_close": (C.c_int, [_vp, _vp]),
+    "nmr_peer_signal": (C.c_int, [_vp, _vp, _u32, _vp]),
+    "nmr_peer_wait": (C.c_int, [_vp, _vp, _i32, _u32, _vp]),
+    "nmr_peer_wait_status": (C.c_int, [_vp]),
     "nmr_coarse_match": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, C.c_float, _i32, _i32, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nmr_stage_mlp_probe": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp]),
     "nmr_debug_trap_code": (C.c_int, []),

@@ -49,6 +49,7 @@ struct nmr_handle {
   int64_t launches = 0;
   bool timing = false;
   bool auto_chunk = true;
+  int* peer_status = nullptr; int* peer_status_dev = nullptr;   // mapped host int: late-producer report of nmr_peer_wait
   cudaStream_t copy_stream = nullptr;   // nmr_render_host: device->host copies overlap the next chunk's kernels
   std::vector<StageEvent> events;       // recorded, not yet read by nmr_last_stage_ms
   std::vector<StageEvent> event_pool;   // created once, re-used (no event creation inside a timed render after warm-up)
@@ -158,6 +159,7 @@ extern "C" void nmr_destroy(nmr_handle* h) {
   for (auto& ev : h->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto& ev : h->event_pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->peer_status) cudaFreeHost(h->peer_status);
   for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[0][i]); tc_free_net(&h->tc[1][i]); }
   h->app.release(); h->X.release(); h->raw.release(); h->zc.release(); h->zf.release(); h->misc.release();
   h->rays_view.release(); h->tcws.release(); h->match.release(); h->bwd.release();
@@ -894,6 +896,73 @@ extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P
   return NMR_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// peer-memory exchange
+// ------------------------------------------------------------------------------------------
+extern "C" int nmr_peer_alloc(nmr_handle* h, size_t bytes, void** dev_ptr, nmr_peer_handle* out) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!dev_ptr || !out || bytes == 0) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(nmr_peer_handle), "IPC handle size");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  void* p = nullptr;
+  NMR_CUDA(h, cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t ih;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&ih, p);
+  if (e != cudaSuccess) { cudaFree(p); cudaGetLastError(); NMR_FAIL(h, NMR_ERR_CUDA, "nmr_peer_alloc: %s", cudaGetErrorString(e)); }
+  memcpy(out->bytes, &ih, sizeof(ih));
+  *dev_ptr = p;
+  return NMR_OK;
+}
+extern "C" int nmr_peer_free(nmr_handle* h, void* dev_ptr) {
+  if (!h) return NMR_ERR_INVALID;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  NMR_CUDA(h, cudaFree(dev_ptr));
+  return NMR_OK;
+}
+extern "C" int nmr_peer_open(nmr_handle* h, const nmr_peer_handle* in, void** peer_ptr) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!in || !peer_ptr) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_peer_open: null argument");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  cudaIpcMemHandle_t ih;
+  memcpy(&ih, in->bytes, sizeof(ih));
+  NMR_CUDA(h, cudaIpcOpenMemHandle(peer_ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+  return NMR_OK;
+}
+extern "C" int nmr_peer_close(nmr_handle* h, void* peer_ptr) {
+  if (!h) return NMR_ERR_INVALID;
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  NMR_CUDA(h, cudaIpcCloseMemHandle(peer_ptr));
+  return NMR_OK;
+}
+extern "C" int nmr_peer_signal(nmr_handle* h, uint32_t* flag, uint32_t value, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!flag) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_peer_signal: null flag");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  launch_peer_signal(flag, value, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "peer_signal");
+  return NMR_OK;
+}
+extern "C" int nmr_peer_wait(nmr_handle* h, const uint32_t* flags, int32_t count, uint32_t value, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!flags || count < 1 || count > 64) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_peer_wait: need 1..64 flags");
+  NMR_CUDA(h, cudaSetDevice(h->device));
+  if (!h->peer_status) {
+    NMR_CUDA(h, cudaHostAlloc((void**)&h->peer_status, sizeof(int), cudaHostAllocMapped));
+    *h->peer_status = 0;
+    NMR_CUDA(h, cudaHostGetDevicePointer((void**)&h->peer_status_dev, h->peer_status, 0));
+  }
+  launch_peer_wait(flags, count, value, h->peer_status_dev, (cudaStream_t)stream);
+  NMR_LAUNCHED(h, "peer_wait");
+  return NMR_OK;
+}
+extern "C" int nmr_peer_wait_status(nmr_handle* h) {
+  if (!h || !h->peer_status) return 0;
+  const int v = *(volatile int*)h->peer_status;
+  *(volatile int*)h->peer_status = 0;
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------
 // differentiable path: input gradients of the three stages the iNeRF refinement

@@ -153,6 +153,10 @@ void launch_rgb_head_backward(const float* grad_raw, const float* raw, const flo
                               cudaStream_t s);
 void launch_unpack_grad(const Dims& d, const float* Gx, const float* Gd, int ldgd, int64_t P, float* out, cudaStream_t s);
 
+// peer-memory exchange (nmr_peer.cu)
+void launch_peer_signal(uint32_t* flag, uint32_t value, cudaStream_t s);
+void launch_peer_wait(const uint32_t* flags, int count, uint32_t value, int* status, cudaStream_t s);
+
 // coarse matching (nmr_match.cu)
 struct MatchParams {
   const float* sim; int m, n;

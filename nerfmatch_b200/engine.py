@@ -63,8 +63,11 @@ class EngineConfig:
         return self.num_pts_coarse + 1 if self.mip else self.num_pts_fine
 
 
-def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else C.c_void_p(t.data_ptr())
+def _ptr(t):
+    """device pointer of a tensor, or a raw address (int: e.g. a peer-memory pointer from ``Engine.peer_open``)"""
+    if t is None:
+        return None
+    return C.c_void_p(int(t)) if isinstance(t, int) else C.c_void_p(t.data_ptr())
 
 
 def _f32c(t: torch.Tensor, device) -> torch.Tensor:
@@ -167,10 +170,12 @@ class Engine:
 
     HOST_OUTPUTS = ("feat_coarse", "feat_fine", "pts_coarse", "pts_fine", "rgb_coarse", "rgb_fine", "depth_coarse", "depth_fine", "pt3d")
 
-    def copy_host_staging(self, name: str, dst: torch.Tensor):
-        """Device copy of output ``name`` of the last render_host call -> ``dst`` (device tensor), device to device."""
+    def copy_host_staging(self, name: str, dst, nbytes: Optional[int] = None):
+        """Device copy of output ``name`` of the last render_host call -> ``dst`` (device tensor, or a raw / peer address with
+        ``nbytes``), device to device."""
+        nbytes = dst.numel() * dst.element_size() if nbytes is None else nbytes
         with torch.cuda.device(self.device):
-            st = self.lib.nmr_copy_host_staging(self.h, self.HOST_OUTPUTS.index(name), _ptr(dst), dst.numel() * dst.element_size(), self.stream())
+            st = self.lib.nmr_copy_host_staging(self.h, self.HOST_OUTPUTS.index(name), _ptr(dst), nbytes, self.stream())
         self.check(st, "nmr_copy_host_staging")
         return dst
 
@@ -244,7 +249,7 @@ class Engine:
             un = (C.c_float * 12)(*[float(v) for v in torch.as_tensor(unnorm, dtype=torch.float32)[:3, :4].reshape(-1).tolist()])
             a.unnorm = C.cast(un, C.c_void_p)
             keep.append(un)
-        for k, t in (outs or {}).items():
+        for k, t in (outs or {}).items():       # tensors, or raw (peer) addresses
             setattr(a, k, _ptr(t))
             keep.append(t)
         return a, keep
@@ -387,3 +392,37 @@ class Engine:
                                                        _ptr(grad_acc), _ptr(grad_weights), _ptr(g_raw), _ptr(g_d), self.stream())
         self.check(st, "nmr_stage_composite_backward")
         return g_raw, g_d
+
+    # -- peer-memory exchange (multi-GPU: outputs delivered into the matcher rank's memory; include/nmr.h) --------
+    def peer_alloc(self, nbytes: int):
+        ptr, hd = C.c_void_p(), (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_peer_alloc(self.h, nbytes, C.byref(ptr), C.cast(hd, C.c_void_p))
+        self.check(st, "nmr_peer_alloc")
+        return int(ptr.value), bytes(hd)
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr, hd = C.c_void_p(), (C.c_ubyte * 64)(*handle)
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_peer_open(self.h, C.cast(hd, C.c_void_p), C.byref(ptr))
+        self.check(st, "nmr_peer_open")
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int):
+        self.check(self.lib.nmr_peer_close(self.h, C.c_void_p(ptr)), "nmr_peer_close")
+
+    def peer_free(self, ptr: int):
+        self.check(self.lib.nmr_peer_free(self.h, C.c_void_p(ptr)), "nmr_peer_free")
+
+    def peer_signal(self, flag_ptr: int, value: int):
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_peer_signal(self.h, C.c_void_p(flag_ptr), value & 0xFFFFFFFF, self.stream())
+        self.check(st, "nmr_peer_signal")
+
+    def peer_wait(self, flags_ptr: int, count: int, value: int):
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_peer_wait(self.h, C.c_void_p(flags_ptr), count, value & 0xFFFFFFFF, self.stream())
+        self.check(st, "nmr_peer_wait")
+
+    def peer_wait_status(self) -> int:
+        return int(self.lib.nmr_peer_wait_status(self.h))

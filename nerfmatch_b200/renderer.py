@@ -192,8 +192,10 @@ class NerfRenderer(nn.Module):
             return raw.reshape(n, m, -1), feats.reshape(n, m, -1), None
         return out.reshape(n, m, -1)
 
-    def render_rays(self, rays, ray_id=None, validation=False, _intermediates=False, _unnorm=None):
-        """Hierarchical coarse->fine render of a ray batch (reference renderer.py:182-295)."""
+    def render_rays(self, rays, ray_id=None, validation=False, _intermediates=False, _unnorm=None, _out_ptrs=None):
+        """Hierarchical coarse->fine render of a ray batch (reference renderer.py:182-295).  ``_out_ptrs``: raw device
+        addresses (e.g. peer memory of the matcher's rank, dist.PeerBuffers) that replace the freshly allocated tensors of
+        the named outputs; those keys are then absent from the returned dict."""
         if self.pfeat_mask is not None and self.ret_pfeat:
             raise NotImplementedError("pfeat_mask is a training-validation feature (out of scope)")
         if rays.device.type != "cuda":
@@ -212,20 +214,28 @@ class NerfRenderer(nn.Module):
         else:
             t_rand, u_jit, rng_mode, seed = self._draws(n, rays.device)
         outs = eng.alloc_outputs(n, self.ret_pfeat, _unnorm is not None, intermediates=_intermediates, training=not validation)
+        if _out_ptrs:
+            outs.update(_out_ptrs)
         args, keep = eng.make_args(n, ncols, rays=rays, ray_id=ray_id, t_rand=t_rand, u_jitter=u_jit, flags=self._flags(),
                                    rng_mode=rng_mode, seed=seed, unnorm=_unnorm, outs=outs, sigma_noise_coarse=noise_c, sigma_noise_fine=noise_f)
         eng.render(args)
+        outs = {k: v for k, v in outs.items() if not isinstance(v, int)}
         preds = {}
+
+        def put(k):                          # (outputs redirected to raw addresses are not returned)
+            if k in outs:
+                preds[k] = outs[k]
+
         for key in ("coarse", "fine"):      # key order of the reference dict
             if self.ret_pfeat:
-                preds[f"feat_{key}"] = outs[f"feat_{key}"]
+                put(f"feat_{key}")
             if validation:                  # pts_* only under validation (renderer.py:276-281) ...
-                preds[f"pts_{key}"] = outs[f"pts_{key}"]
+                put(f"pts_{key}")
             elif key == "fine":             # ... s_fine / weights_fine only without it (:283-286)
-                preds["s_fine"] = outs["s_fine"]
-                preds["weights_fine"] = outs["weights_fine"]
-            preds[f"rgb_{key}"] = outs[f"rgb_{key}"]
-            preds[f"depth_{key}"] = outs[f"depth_{key}"]
+                put("s_fine")
+                put("weights_fine")
+            put(f"rgb_{key}")
+            put(f"depth_{key}")
         for k, v in outs.items():
             if k not in preds and (_intermediates or k == "pt3d"):
                 preds[k] = v

@@ -355,8 +355,10 @@ def test_edge_cases_and_errors():
         ren.predict(T(g["rays"][:, :11]), 1, 1)  # mip needs the radius column
     with pytest.raises(RuntimeError):
         ren.predict(torch.from_numpy(g["rays"]), 1, 1)  # host tensor: no CPU fallback
+    ren.pfeat_mask = torch.ones(4, dtype=torch.bool)
     with pytest.raises(NotImplementedError):
-        ren.forward(T(g["rays"]), validation=False)  # training-mode forward is out of scope
+        ren.forward(T(g["rays"]), validation=True)  # pfeat_mask (training-validation feature filter) is not built
+    ren.pfeat_mask = None
     ren.ret_pfeat = False
     assert "feat_fine" not in ren.predict(T(g["rays"]), 1, 1)
     # weights reload is picked up (state_dict is the source of truth)
