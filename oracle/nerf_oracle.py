@@ -437,6 +437,47 @@ def mlp_forward(wts: Dict[str, np.ndarray], x: np.ndarray, cfg: RenderConfig, st
     return raw, feat
 
 
+def round_bf16(x: np.ndarray) -> np.ndarray:
+    """round-to-nearest-even to bfloat16, returned as float32"""
+    u = np.ascontiguousarray(x, F32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(F32)
+
+
+def round_fp16(x: np.ndarray) -> np.ndarray:
+    """round-to-nearest-even to IEEE half, saturating at +-65504, returned as float32"""
+    return np.clip(np.ascontiguousarray(x, F32), -65504, 65504).astype(np.float16).astype(F32)
+
+
+def mlp_forward_rounded(wts: Dict[str, np.ndarray], x: np.ndarray, cfg: RenderConfig, stop_layer: Optional[int] = None, rnd=round_bf16):
+    """NeRF.forward with 16-bit tensor-core operands, as ANY implementation that feeds the 8 x 256 trunk to bf16 / fp16
+    matrix units computes it: weights and layer inputs rounded by ``rnd`` (round_bf16 | round_fp16), products accumulated in
+    fp32, biases / the sigma head / the dirs part of views_linears / rgb in fp32.  Used to measure how far 16-bit operands
+    alone move the reference's outputs (the error envelope the CUDA path is judged against), not as a reference itself."""
+    xd = cfg.xyz_dim
+    stop_layer = cfg.stop_layer if stop_layer is None else stop_layer
+    enc = rnd(x[:, :xd])
+    side = x[:, xd:]
+    W = lambda k: rnd(wts[k])
+    h, feat = enc, None
+    for i in range(cfg.layer_num):
+        w = W(f"pts_linears.{i}.weight")
+        pre = (enc @ w[:, :xd].T + h @ w[:, xd:].T) if (i - 1) in cfg.skips else h @ w.T
+        act = np.maximum(pre + wts[f"pts_linears.{i}.bias"], 0).astype(F32)
+        h = rnd(act)
+        if i == stop_layer:
+            feat = h
+    if stop_layer < 0:
+        feat = h
+    alpha = h @ wts["alpha_linear.weight"].astype(F32).T + wts["alpha_linear.bias"]
+    wv = wts["views_linears.0.weight"].astype(np.float64)
+    wfold = (wv[:, :cfg.hid_dim] @ wts["feature_linear.weight"].astype(np.float64)).astype(F32)
+    bfold = (wts["views_linears.0.bias"] + wv[:, :cfg.hid_dim] @ wts["feature_linear.bias"].astype(np.float64)).astype(F32)
+    hv = np.maximum(h @ rnd(wfold).T + (side @ wts["views_linears.0.weight"][:, cfg.hid_dim:].T + bfold), 0).astype(F32)
+    rgb = F32(1) / (F32(1) + np.exp(-(hv @ wts["rgb_linear.weight"].T + wts["rgb_linear.bias"])))
+    return np.concatenate([rgb, alpha], -1).astype(F32), feat.astype(F32)
+
+
 def encode_points(cfg: RenderConfig, pts, var, viewdirs, app_emb, S: int) -> np.ndarray:
     """renderer.py:125-164: per-sample [xyz enc | dirs enc | appearance] rows."""
     n = pts.shape[0]
@@ -530,6 +571,7 @@ def render_rays(
     validation: bool = True,
     noise_coarse: Optional[np.ndarray] = None,
     noise_fine: Optional[np.ndarray] = None,
+    mlp=None,
 ) -> Dict[str, np.ndarray]:
     """NerfRenderer.render_rays (renderer.py:182-295), chunked over rays only to bound memory (rays are independent).
     Training mode (validation=False, one chunk only because s_fine normalises over the batch): ``t_rand`` / ``u_jitter``
@@ -549,7 +591,7 @@ def render_rays(
                     None if t_rand is None else t_rand[s:e],
                     None if u_jitter is None else u_jitter[s:e],
                     None if ray_id is None else ray_id[s:e],
-                    keep_intermediates, chunk,
+                    keep_intermediates, chunk, mlp=mlp,
                 )
             )
         return {k: np.concatenate([p[k] for p in parts], 0) for k in parts[0]}
@@ -588,7 +630,7 @@ def render_rays(
             var = None
             S = z_vals.shape[1]
         x = encode_points(cfg, pts, var, viewdirs, app, S)
-        raw, feat = mlp_forward(w, x, cfg, cfg.stop_layer if key == "fine" else cfg.stop_layer_coarse)
+        raw, feat = (mlp or mlp_forward)(w, x, cfg, cfg.stop_layer if key == "fine" else cfg.stop_layer_coarse)
         raw = raw.reshape(n, S, 4)
         feat = feat.reshape(n, S, -1)
         rgb_map, disp, acc, weights, depth = volume_render(raw, z_vals, rays_d, mip, cfg.white_bg, noise_coarse if key == "coarse" else noise_fine)

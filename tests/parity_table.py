@@ -90,7 +90,22 @@ def render_cuda(ren, rays, t_rand=None, u_jitter=None, ray_id=None, unnorm=None)
     return {k: v.detach().cpu().numpy() for k, v in outs.items()}
 
 
+def emulated_oracle(cfg, sd, g, prec):
+    """The reference algorithm with 16-bit tensor-core operands (oracle.mlp_forward_rounded): what ANY correct bf16 / fp16
+    implementation of the MLP computes, up to fp32 accumulation order."""
+    import functools
+
+    rnd = O.round_fp16 if prec == "fp16" else O.round_bf16
+    out = O.render_rays(cfg, sd, g["rays"], g.get("t_rand"), g.get("u_jitter"), g.get("ray_id"), keep_intermediates=True,
+                        mlp=functools.partial(O.mlp_forward_rounded, rnd=rnd))
+    out["pt3d"] = O.unnormalize_pts(out["pts_fine"], g["unnorm_scene"])
+    return out
+
+
 def golden_rows(precisions=("fp32", "bf16", "fp16")):
+    """Per golden and precision: the CUDA path against the reference's fp32 output; for the 16-bit modes also the emulated
+    16-bit-operand oracle against the reference (the error 16-bit operands cause by themselves) and the CUDA path against
+    that emulated oracle (what the kernel adds on top: nothing but accumulation order)."""
     rows = {}
     for name in RENDER_CASES:
         g = load_golden(f"render_{name}.npz")
@@ -103,6 +118,10 @@ def golden_rows(precisions=("fp32", "bf16", "fp16")):
             row["sigma_gain"] = [float(x) for x in c["sigma_gain"]]
             row["feat_comb"] = c["feat_comb"]
             rows[f"golden/{name}/{prec}"] = row
+            if prec != "fp32":
+                emu = emulated_oracle(cfg, sd, g, prec)
+                rows[f"golden/{name}/{prec}_emulated_oracle_vs_reference"] = dict(compare(emu, g), n_rays=row["n_rays"])
+                rows[f"golden/{name}/{prec}_cuda_vs_emulated_oracle"] = dict(compare(out, emu), n_rays=row["n_rays"])
     return rows
 
 
