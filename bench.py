@@ -222,6 +222,84 @@ def run_torch_eager(args):
           "note": "informational: the reference algorithm as eager torch ops on the same GPU; not the reference arm (that is --impl reference, CPU)"})
 
 
+# --------------------------------------------------------------------------------------------
+# one step of the iNeRF pose refinement (nerfmatch_evaluator.py:334-452) on the shim's modules:
+# rays from the pose being optimised (ds=8: 60 x 80 rays), coarse pass without grad, fine pass (128 + 128 mip samples) with
+# grad, white-background volume rendering, MSE, loss.backward(), Adam step.  The glue is the evaluator's own torch code.
+# --------------------------------------------------------------------------------------------
+def inerf_step_ms(dev, precision, steps=5):
+    import torch
+
+    from nerfmatch_b200.config import build_renderer
+    from nerfmatch_b200.render_utils import rays_intersect_sphere, sample_smth_along_rays, volume_render_radiance_field
+    from nerfmatch_b200.synthetic import K_7SCENES, make_pose, make_state_dict
+
+    c = dict(embed="mip", nc=128, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=True)
+    sd = make_state_dict(21, embed_type="mip", sigma_gain=60.0, sigma_bias=(4.0, 4.0))
+    ren = build_renderer(c, sd, precision=precision, device=dev)
+    for p_ in ren.parameters():
+        p_.requires_grad_(False)
+    ren.nerf_coarse.precision = ren.nerf_fine.precision = precision      # forward of the sub-modules on this precision's kernels
+    K = torch.from_numpy(K_7SCENES).to(dev)
+    ds = 8
+    ys, xs = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    dirs = torch.stack([xs, ys, torch.ones_like(xs)], -1).float() @ torch.linalg.inv(K).T
+    img = torch.rand(len(range(ds // 2, H, ds)) * len(range(ds // 2, W, ds)), 3, device=dev)
+    cam_pose = torch.from_numpy(make_pose(21))[None].to(dev).clone().requires_grad_(True)
+    opt = torch.optim.Adam(params=[cam_pose], lr=1e-3)
+    eps = torch.tensor(torch.finfo(torch.float32).eps, device=dev)
+
+    def step():
+        with torch.enable_grad():
+            o = cam_pose[:, None, None, :3, 3].expand(-1, H, W, -1)[0]
+            d = torch.matmul(cam_pose[:, None, None, :3, :3], dirs.unsqueeze(-1))[0, :, :, :, 0]
+            v = d / d.norm(dim=-1, keepdim=True)
+            far = rays_intersect_sphere(o.reshape(-1, 3), v.reshape(-1, 3), r=1).view(H, W, 1)
+            dx = torch.sqrt(torch.sum((v[:-1] - v[1:]) ** 2, -1))
+            radii = torch.cat([dx, dx[-2:-1]], 0)[..., None] * 2 / np.sqrt(12)
+            rays = torch.cat((o, v, torch.full_like(far, 0.01), far, v, radii), -1)[ds // 2:: ds, ds // 2:: ds].reshape(-1, 12)
+            z = wts = None
+            for key, model in (("coarse", ren.nerf_coarse), ("fine", ren.nerf_fine)):
+                pts, z = sample_smth_along_rays(rays.detach(), num_pts=128, z_vals=z, weights=wts, use_disp=False, perturb=False,
+                                                embed_type="mip", model_type=key, scale_var=1)
+                vf = rays[:, None, 8:11].expand(rays.shape[0], 128, 3)
+                mu, hw = (z[..., :-1] + z[..., 1:]) / 2, (z[..., :-1] - z[..., 1:]) / 2
+                t_mean = mu + (2 * mu * hw**2) / torch.maximum(eps, 3 * mu**2 + hw**2)
+                pts_z = rays[:, None, :3].expand(rays.shape[0], 128, 3) + t_mean[:, :, None] * vf
+                x = torch.cat((ren.xyz_encoder(pts_z.contiguous().view(-1, 3), y=pts[1].contiguous().view(-1, 3))[0],
+                               ren.dirs_encoder(vf.contiguous().view(-1, 3))), -1)
+                if key == "coarse":
+                    with torch.no_grad():
+                        raw, _ = model.forward(x, ret_pfeat=1, val=True)
+                else:
+                    raw, _ = model.forward(x, ret_pfeat=1, val=True)
+                rgb_map, _, _, wts, _, _ = volume_render_radiance_field(raw.view(-1, 128, 4), z, rays[..., 3:6], noise_std=0.0, white_bg=True,
+                                                                        embed_type="mip", input_dim=4)
+            loss = torch.nn.functional.mse_loss(rgb_map, img)
+            loss.backward()
+            opt.step()
+            opt.zero_grad()
+        return loss
+
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    try:
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            loss = step()
+        b.record()
+        torch.cuda.synchronize(dev)
+    finally:
+        torch.set_grad_enabled(prev)
+    return {"ms_per_step": a.elapsed_time(b) / steps, "rays": int(img.shape[0]), "samples": "128 coarse (no grad) + 128 fine (grad), mip", "loss": float(loss),
+            "forward": precision, "backward": "fp32 dgrad chain, activations recomputed",
+            "what": "gen_rays -> sample -> encode -> NeRF -> volume render -> MSE -> backward -> Adam, as nerfmatch_evaluator.py:334-452"}
+
+
 def config_block(embed, precision, rays_per_step=H * W):
     return {"workload": f"7-Scenes {H}x{W} full-res feature render, {embed} embedding, 64 coarse + 128 fine samples "
                         f"({256 if embed == 'normal' else 128} MLP evals/ray), stop_layer=3, random-init weights",
@@ -473,6 +551,8 @@ def run_ours(args):
                        "scaling": "strong", "rays": 64 * 4800, "ms_per_batch": ms_cfg4 / args.steps, "value": 64 * 4800 * args.steps / (ms_cfg4 / 1e3), "unit": "rays/s"}
     if other is not None:
         line["other_operand_format"] = other
+    if world == 1:
+        line["inerf_step_ms"] = inerf_step_ms(dev, args.precision)
     # compositing kernel: HBM-bound side of the path (SURVEY.md 8d byte counts, bf16 | fp32 features), measured with the
     # per-sample features streamed from HBM (kernel (c) standalone); the bf16 product path composites the features tile by
     # tile inside the MLP kernel, its (small, latency-bound) compositor is reported as composite_fused.
