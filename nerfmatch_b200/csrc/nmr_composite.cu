@@ -26,6 +26,27 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sum and running sums of the n fp32 values x[0..n) in float64, spread over the warp (lane l owns a contiguous segment;
+// the lane totals are combined by a shuffle scan).  The oracle (and torch's CPU kernels) accumulate sequentially in
+// float64; the association here differs, but the result does not: every value summed in this file is an fp32 number
+// within a 2^21 dynamic range of the others (weights carry a +1e-5 or +0.01 floor and are <= ~1), so every partial sum
+// of <= 256 of them is exactly representable in a 53-bit significand - float64 addition is EXACT here and therefore
+// associative.  Returns this lane's exclusive prefix (sum of the segments before it) and the total.
+__device__ __forceinline__ void warp_prefix_f64(const float* x, int n, int lane, int& s0, int& s1, double& excl, double& total) {
+  const int seg = (n + 31) / 32;
+  s0 = min(n, lane * seg); s1 = min(n, s0 + seg);
+  double local = 0.0;
+  for (int s = s0; s < s1; ++s) local += (double)x[s];
+  double incl = local;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += up;
+  }
+  total = __shfl_sync(0xffffffffu, incl, 31);
+  excl = incl - local;
+}
+
 __device__ __forceinline__ void frustum_tmean(float t0, float t1, float* t_mean) {
   float mu = (t0 + t1) / 2.0f, hw = (t1 - t0) / 2.0f;
   float mu2 = mu * mu, hw2 = hw * hw;
@@ -294,24 +315,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
       st[s] = 0.5f * (fmaxf(wm, w0) + fmaxf(w0, wp)) + p.resample_padding;
     }
     __syncwarp();
-    float wsum = 0.f;
-    if (lane == 0) {
-      double acc = 0.0;
-      for (int s = 0; s < S; ++s) acc += (double)st[s];
-      wsum = (float)acc;
-    }
-    wsum = __shfl_sync(0xffffffffu, wsum, 0);
+    int q0, q1; double excl, total;
+    warp_prefix_f64(st, S, lane, q0, q1, excl, total);
+    const float wsum = (float)total;
     float padding = fmaxf(0.0f, 1e-5f - wsum);
     float wtot = wsum + padding;
     float padw = padding / (float)S;
+    __syncwarp();
     for (int s = lane; s < S; s += 32) st[s] = (st[s] + padw) / wtot;     // pdf
     __syncwarp();
-    if (lane == 0) {
-      double run = 0.0;
-      sa[0] = 0.0f;
-      for (int s = 0; s < S - 1; ++s) { run += (double)st[s]; sa[s + 1] = fminf(1.0f, (float)run); }
-      sa[S] = 1.0f;
-    }
+    warp_prefix_f64(st, S, lane, q0, q1, excl, total);                     // cdf: float64 running sum, each prefix rounded to fp32
+    for (int s = q0; s < q1; ++s) { excl += (double)st[s]; if (s < S - 1) sa[s + 1] = fminf(1.0f, (float)excl); }
+    if (lane == 0) { sa[0] = 0.0f; sa[S] = 1.0f; }
     __syncwarp();
     const int S1 = S + 1;
     const float sstep = (float)(1.0 / (double)S1);
@@ -340,20 +355,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     const int nb = S - 1, nw = S - 2, N = p.nf;
     for (int i = lane; i < nw; i += 32) st[i] = sw[i + 1] + 1e-5f;
     __syncwarp();
-    float wsum = 0.f;
-    if (lane == 0) {
-      double acc = 0.0;
-      for (int i = 0; i < nw; ++i) acc += (double)st[i];
-      wsum = (float)acc;
-    }
-    wsum = __shfl_sync(0xffffffffu, wsum, 0);
+    int q0, q1; double excl, total;
+    warp_prefix_f64(st, nw, lane, q0, q1, excl, total);
+    const float wsum = (float)total;
+    __syncwarp();
     for (int i = lane; i < nw; i += 32) st[i] = st[i] / wsum;            // pdf
     __syncwarp();
-    if (lane == 0) {
-      double run = 0.0;
-      sa[0] = 0.0f;
-      for (int i = 0; i < nw; ++i) { run += (double)st[i]; sa[i + 1] = (float)run; }
-    }
+    warp_prefix_f64(st, nw, lane, q0, q1, excl, total);                   // cdf
+    for (int i = q0; i < q1; ++i) { excl += (double)st[i]; sa[i + 1] = (float)excl; }
+    if (lane == 0) sa[0] = 0.0f;
     __syncwarp();
     // st is free again: hold the combined [z | samples] list there (S + N <= 2 * kMaxSamples)
     float* comb = st;   // S + N <= kMaxSamples floats (checked in nmr_create)

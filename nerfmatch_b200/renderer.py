@@ -46,8 +46,8 @@ class NerfRenderer(nn.Module):
         self.out_scr = getattr(dcfg, "out_scr", False)
         self.single_model = getattr(r, "single_model", False)
         self.appearance_embedding = getattr(e, "appearance_embed", False)
-        if self.out_scr or self.single_model or not self.use_viewdirs:
-            raise NotImplementedError("out_scr / single_model / use_viewdirs=False are outside the built hot path")
+        if self.out_scr or not self.use_viewdirs:
+            raise NotImplementedError("out_scr heads / use_viewdirs=False are outside the built hot path")
         if self.embed_type not in ("mip", "normal"):
             raise NotImplementedError(f"embedding.type={self.embed_type!r}")
         self.num_out_ch = 0
@@ -67,8 +67,9 @@ class NerfRenderer(nn.Module):
                 c["stop_layer"] = stop
             return c
 
-        self.num_pts_coarse = config.coarse_nerf.num_pts
-        self.nerf_coarse = NeRF(net_conf(config.coarse_nerf, None))       # stop_layer only reaches the fine net
+        if not self.single_model:          # renderer.py:76-87: with single_model the coarse net does not exist at all
+            self.num_pts_coarse = config.coarse_nerf.num_pts
+            self.nerf_coarse = NeRF(net_conf(config.coarse_nerf, None))   # stop_layer only reaches the fine net
         fine_conf = getattr(config, "fine_nerf", None)
         if fine_conf is None:
             raise NotImplementedError("a renderer without fine_nerf is outside the built hot path")
@@ -92,12 +93,20 @@ class NerfRenderer(nn.Module):
     def set_training_mode(self, state):
         self.training = state
 
+    def _nets(self):
+        """(coarse-pass net, fine-pass net, coarse sample count): single_model runs the fine net in both passes with
+        num_pts_fine samples each (renderer.py:191-201)."""
+        if self.single_model:
+            return self.nerf_fine, self.nerf_fine, self.num_pts_fine
+        return self.nerf_coarse, self.nerf_fine, self.num_pts_coarse
+
     def _engine_config(self) -> EngineConfig:
+        coarse, fine, sc = self._nets()
         return EngineConfig(
             embed_type=self.embed_type, xyz_num_freqs=self.xyz_encoder.num_freqs, dirs_num_freqs=self.dirs_encoder.num_freqs,
-            num_pts_coarse=self.num_pts_coarse, num_pts_fine=self.num_pts_fine,
+            num_pts_coarse=sc, num_pts_fine=self.num_pts_fine,
             app_dim=16 if self.appearance_embedding else 0,
-            stop_layer_coarse=self.nerf_coarse.stop_layer, stop_layer_fine=self.nerf_fine.stop_layer,
+            stop_layer_coarse=coarse.stop_layer, stop_layer_fine=fine.stop_layer,
             use_disp=bool(self.use_disp), precision=self.precision, mip_var_scale=float(self.mip_var_scale),
             max_chunk_points=self.max_chunk_points,
         )
@@ -109,13 +118,14 @@ class NerfRenderer(nn.Module):
         cfg = self._engine_config()
         # everything the nmr_handle fixes at creation (the reference reads these attributes live on every call)
         static = tuple(sorted((k, v) for k, v in vars(cfg).items() if k != "precision"))
-        weights = (self.nerf_coarse.weights_signature(), self.nerf_fine.weights_signature(),
+        coarse, fine, _ = self._nets()
+        weights = (coarse.weights_signature(), fine.weights_signature(),
                    None if self.embedding_a is None else (self.embedding_a.weight.data_ptr(), self.embedding_a.weight._version))
         ent = self._engines.get(key)
         if ent is None or ent[1] != (weights, static):
             eng = Engine(cfg, device) if (ent is None or ent[1][1] != static) else ent[0]
-            eng.set_weights(L.NMR_NET_COARSE, self.nerf_coarse.net_state())
-            eng.set_weights(L.NMR_NET_FINE, self.nerf_fine.net_state())
+            eng.set_weights(L.NMR_NET_COARSE, coarse.net_state())
+            eng.set_weights(L.NMR_NET_FINE, fine.net_state())
             if self.embedding_a is not None:
                 eng.set_appearance(self.embedding_a.weight)
             ent = (eng, (weights, static))
@@ -142,7 +152,7 @@ class NerfRenderer(nn.Module):
           classic  torch.rand_like [n,Sc] (:122) . randn [n,Sc] . torch.rand [n,Nf] ON THE CPU (:247, then .to(device)) . randn [n,Sc+Nf]
         ``perturb`` gates the classic sampling draws only (mip jitters regardless); ``noise_std`` <= 0 skips the noise."""
         mip = self.embed_type == "mip"
-        Sc, Nf = self.num_pts_coarse, self.num_pts_fine
+        Sc, Nf = self._nets()[2], self.num_pts_fine
         noise = lambda S: (torch.randn(n, S, device=device) * self.noise_std) if self.noise_std > 0.0 else None
         if mip:
             t_rand = torch.rand(n, Sc + 1, device=device)
@@ -166,7 +176,7 @@ class NerfRenderer(nn.Module):
             return None, None, L.NMR_RNG_PHILOX, seed
         if self.rng == "none":
             return None, None, L.NMR_RNG_NONE, 0
-        S1 = self.num_pts_coarse + 1
+        S1 = self._nets()[2] + 1
         t_rand = torch.rand(n, S1, device=device)
         u_jit = torch.empty(n, S1, device=device).uniform_(to=(1 / S1 - _EPS32))
         return t_rand, u_jit, L.NMR_RNG_NONE, 0
@@ -196,8 +206,16 @@ class NerfRenderer(nn.Module):
         """Hierarchical coarse->fine render of a ray batch (reference renderer.py:182-295).  ``_out_ptrs``: raw device
         addresses (e.g. peer memory of the matcher's rank, dist.PeerBuffers) that replace the freshly allocated tensors of
         the named outputs; those keys are then absent from the returned dict."""
+        ray_mask = None
         if self.pfeat_mask is not None and self.ret_pfeat:
-            raise NotImplementedError("pfeat_mask is a training-validation feature (out of scope)")
+            # nerf_trainer.py:45-47, renderer.py:141-146, 250-255: features are returned for the masked rays only.  The reference
+            # applies the mask inside NeRF.forward only when the tap is the last trunk layer (models/nerf.py:137-141); with
+            # stop_layer >= 0 its own shapes no longer match, so that combination is refused here as well.
+            if self._nets()[1].stop_layer >= 0:
+                raise NotImplementedError("pfeat_mask with stop_layer >= 0 fails in the reference itself (models/nerf.py:137-141)")
+            ray_mask = self.pfeat_mask.flatten().to(rays.device)
+            if ray_mask.numel() != rays.shape[0]:
+                raise ValueError(f"pfeat_mask has {ray_mask.numel()} entries for {rays.shape[0]} rays")
         if rays.device.type != "cuda":
             raise RuntimeError("NerfRenderer (nerfmatch_b200) renders CUDA ray tensors only: there is no CPU fallback")
         rays = rays.detach().float().contiguous()
@@ -224,7 +242,7 @@ class NerfRenderer(nn.Module):
 
         def put(k):                          # (outputs redirected to raw addresses are not returned)
             if k in outs:
-                preds[k] = outs[k]
+                preds[k] = outs[k][ray_mask] if (ray_mask is not None and k.startswith("feat_")) else outs[k]
 
         for key in ("coarse", "fine"):      # key order of the reference dict
             if self.ret_pfeat:

@@ -161,10 +161,10 @@ def oracle_render(cfg, sd, rays, tr, uj, unnorm):
     return ref
 
 
-def view_rows(precisions=("fp32", "bf16", "fp16"), quick=False):
+def view_rows(precisions=("fp32", "bf16", "fp16"), quick=False, specs=None):
     rows = {}
     un = make_unnorm_scene()
-    specs = {
+    specs = specs or {
         # BASELINE config 1: one 7-Scenes view at 120x160 (480x640 camera, every 4th pixel), 64 + 128 samples
         "config1_120x160/normal": dict(embed="normal", ds=4),
         "config1_120x160/mip": dict(embed="mip", ds=4),

@@ -113,9 +113,13 @@ def test_unsupported_reference_options_fail_loudly():
     from nerfmatch_b200 import NerfRenderer
 
     cfg = ref_style_config("mip")
-    cfg.render.single_model = True
+    cfg.data.out_scr = True
     with pytest.raises(NotImplementedError):
         NerfRenderer(cfg)
+    cfg = ref_style_config("mip")
+    cfg.render.single_model = True                 # built: the fine net renders both passes; no nerf_coarse.* keys (renderer.py:76-87)
+    ren = NerfRenderer(cfg, stop_layer=3)
+    assert not hasattr(ren, "nerf_coarse") and not any(k.startswith("nerf_coarse") for k in ren.state_dict())
     cfg = ref_style_config("mip")
     cfg.coarse_nerf.skips = [3]
     with pytest.raises(NotImplementedError):

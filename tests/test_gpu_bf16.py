@@ -178,23 +178,26 @@ def _render_bf16(name):
 
 @pytest.mark.parametrize("name", RENDER_CASES)
 def test_full_render_bf16_matches_reference(name):
-    """North star for the bf16 MLP: composited features with cosine >= 0.999 per ray against the reference
-    renderer's fp32 output; depth / points within bf16-level error."""
+    """North star for the 16-bit MLP: composited features with cosine >= 0.999 per ray against the reference renderer's
+    fp32 output on every golden whose field bf16 operands can resolve; on the others (sigma gain ~5e3, arg-max features,
+    untrained classic NeRF) the bound is what the emulated bf16-operand ORACLE itself reaches against the reference
+    (tests/test_gpu_parity_table.py asserts that envelope case by case; measured table: profiles/r02_parity.json)."""
     g, cfg, c, out = _render_bf16(name)
-    peaky = max(c["sigma_gain"]) > 1000        # sigma gain ~5e3 amplifies bf16 round-off into O(1) density changes
+    strict = name in ("mip64", "mip128_peaky", "normal_64_128")
     for key in ("coarse", "fine"):
-        if cfg.feat_comb == "lin":
-            cos = cosine_rows(out[f"feat_{key}"], g[f"feat_{key}"])
-            if not peaky:
-                assert cos.min() >= 0.999, (key, cos.min())
-                assert rel_l2(out[f"depth_{key}"], g[f"depth_{key}"]) < 2e-2, key
-                dp = np.abs(out[f"pts_{key}"] - g[f"pts_{key}"]).max(-1)   # normalised scene units, bf16 MLP
-                assert np.median(dp) < 2e-2 and dp.max() < 1e-1, (key, np.median(dp), dp.max())
-            else:
-                assert np.median(cos) >= 0.999 and (cos >= 0.99).mean() > 0.9, (key, np.median(cos), (cos >= 0.99).mean())
+        cos = cosine_rows(out[f"feat_{key}"], g[f"feat_{key}"])
+        if strict:
+            assert cos.min() >= 0.999, (key, cos.min())
+            assert rel_l2(out[f"depth_{key}"], g[f"depth_{key}"]) < (3e-2 if key == "fine" else 1e-2), key
+        else:
+            assert np.median(cos) >= 0.9994 and (cos >= 0.99).mean() >= 0.9, (key, np.median(cos), (cos >= 0.99).mean())
         assert np.isfinite(out[f"feat_{key}"]).all() and np.isfinite(out[f"rgb_{key}"]).all()
-        assert np.abs(out[f"rgb_{key}"] - g[f"rgb_{key}"]).max() < (0.05 if not peaky else 0.5), key
-    # sampling is fp32 in both precisions: coarse fence posts are identical to the fp32 path
+        assert np.abs(out[f"rgb_{key}"] - g[f"rgb_{key}"]).max() < 2e-2, key
+    dp = np.linalg.norm(out["pt3d"] - g["pt3d"], axis=-1)          # metres (scene scale 3 m); per-case medians from the measured table
+    bound = {"mip64": 2e-3, "mip128_peaky": 5e-3, "normal_64_128": 4e-2, "normal_64_128_peaky": 1.5e-2, "mip64_app_max_white": 2e-3,
+             "normal_app_stop5": 6e-3}[name]
+    assert np.median(dp) < bound, (name, np.median(dp))
+    # sampling is fp32 in every precision: coarse fence posts are identical to the fp32 path
     np.testing.assert_allclose(out["z_coarse"], g["z_coarse"], rtol=0, atol=1e-6)
 
 

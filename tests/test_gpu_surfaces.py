@@ -241,3 +241,36 @@ def test_render_views_sharded_two_gpus():
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "SHARDED_OK" in res.stdout
+
+
+def test_single_model_and_pfeat_mask_options():
+    """config.render.single_model (the fine net renders both passes with num_pts_fine samples, renderer.py:76-87, 191-201) and
+    NerfRenderer.pfeat_mask (features for the masked rays only, nerf_trainer.py:45-47) against the oracle."""
+    from nerfmatch_b200 import NerfRenderer
+
+    for embed, nf in (("mip", 64), ("normal", 96)):
+        cfg = ref_style_config(embed, nc=64, nf=nf)
+        cfg.render.single_model = True
+        sd = make_state_dict(85, embed_type=embed, sigma_gain=60.0, sigma_bias=(4.0, 4.0))
+        ren = NerfRenderer(cfg, training=False, stop_layer=-1, precision="fp32")
+        ren.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items() if not k.startswith("nerf_coarse")}, strict=True)
+        ren = ren.to(DEV).eval()
+        ren.ret_pfeat, ren.rng = True, "none"
+        rays = O.sample_nerf_rays(480, 640, K_7SCENES, make_pose(9), ds=40, embed_type=embed)   # 192 rays
+        sd_single = dict(sd)
+        for k in list(sd):
+            if k.startswith("nerf_fine."):
+                sd_single["nerf_coarse." + k[len("nerf_fine."):]] = sd[k]
+        ocfg = O.RenderConfig(embed_type=embed, num_pts_coarse=nf, num_pts_fine=nf, stop_layer=-1, stop_layer_coarse=-1)
+        ref = O.render_rays(ocfg, sd_single, rays)
+        out = ren.predict(T(rays), 1, 1)
+        for k in ("feat_coarse", "feat_fine", "pts_fine", "depth_fine"):
+            assert rel_l2(N(out[k]), ref[k]) < 1e-3, (embed, k, rel_l2(N(out[k]), ref[k]))
+        mask = torch.zeros(12, 16, 1, dtype=torch.bool)
+        mask[1::4, 2::4] = True                                     # init_pfeat_mask-style strided selection
+        ren.pfeat_mask = mask
+        sub = ren.forward(T(rays), validation=True)
+        sel = mask.flatten().numpy()
+        assert sub["feat_fine"].shape == (int(sel.sum()), 256) and sub["pts_fine"].shape == (192, 3)
+        assert torch.equal(sub["feat_fine"], out["feat_fine"][T(sel)]) and torch.equal(sub["pts_fine"], out["pts_fine"])
+        ren.pfeat_mask = None
