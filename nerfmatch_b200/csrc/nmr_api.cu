@@ -35,6 +35,7 @@ struct nmr_handle {
   nmr_config cfg;
   Dims d;
   int device = 0;
+  bool tc_gemm = true;          // backward pass / matcher GEMMs on the tensor cores (3 x bf16 split; NMR_GEMM_TC=0: fp32 SIMT)
   bool fuse_composite = true;   // bf16 path: composite the tapped features tile-locally inside the MLP kernel (NMR_TC_FUSE=0: off)
   NetF32 net[2];
   DevBuf wpool[2];
@@ -149,6 +150,7 @@ extern "C" int nmr_create(const nmr_config* cfg, nmr_handle** out) {
   h->d = d;
   h->device = dev;
   if (const char* fv = getenv("NMR_TC_FUSE")) h->fuse_composite = atoi(fv) != 0;
+  if (const char* gv = getenv("NMR_GEMM_TC")) h->tc_gemm = atoi(gv) != 0;
   for (int i = 0; i < 2; ++i) { memset(&h->net[i], 0, sizeof(NetF32)); h->tc[0][i] = TcNet{}; h->tc[1][i] = TcNet{}; }
   *out = h;
   return NMR_OK;
@@ -1026,7 +1028,11 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
   float* Gv = take(kHalf); float* Ga = take(kHid); float* Gb = take(kHid);
   float* Gxs = take(d.xyzp); float* Gx0 = take(d.xyzp); float* Gd = take(d.dap);
   auto gemm = [&](const GemmParams& g, const char* what) -> int {
-    launch_sgemm(g, s);
+    if (h->tc_gemm && gemm_tc_supported(g)) {
+      if (launch_gemm_tc(g, s) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "launch_gemm_tc setup failed (%s)", what);
+    } else {
+      launch_sgemm(g, s);
+    }
     return check_launch(h, what);
   };
   int r;
@@ -1128,7 +1134,11 @@ extern "C" int nmr_coarse_match(nmr_handle* h, const float* im_feat, int32_t m, 
   NMR_LAUNCHED(h, "normalize_rows", 2);
   GemmParams g{};
   g.A1 = imn; g.lda1 = dp; g.W1 = ptn; g.K1 = dp; g.C = sim; g.ldc = n; g.M = m; g.N = n; g.act = 0;
-  launch_sgemm(g, s);
+  if (h->tc_gemm && gemm_tc_supported(g)) {        // the one contraction of the matcher: tensor cores, fp32-grade (3 x bf16 split)
+    if (launch_gemm_tc(g, s) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "launch_gemm_tc setup failed (similarity)");
+  } else {
+    launch_sgemm(g, s);
+  }
   NMR_LAUNCHED(h, "similarity gemm");
   MatchParams p{};
   p.sim = sim; p.m = m; p.n = n; p.im_mask = im_mask; p.pt_mask = pt_mask; p.temperature = temperature; p.temp_div = temp_div;

@@ -138,6 +138,9 @@ struct GemmParams {        // C = act(A1*W1^T + A2*W2^T + bias [+ r1a (x) r1b] [
   const float* mask; int ldm;
 };
 void launch_sgemm(const GemmParams& p, cudaStream_t s);
+// same contract on the tensor cores (nmr_gemm_tc.cu: fp32 operands split into bf16 hi + lo, three tcgen05 MMAs per K step)
+bool gemm_tc_supported(const GemmParams& p);
+int launch_gemm_tc(const GemmParams& p, cudaStream_t s);
 
 // ---- backward pieces of the differentiable render (nmr_backward.cu) ----
 struct CompositeBwdParams {

@@ -20,6 +20,18 @@ def run(embed, seed_w, pose, ds, extra, okw, seed_d):
     cfg = O.RenderConfig(embed_type=embed, num_pts_coarse=64, num_pts_fine=128, stop_layer=3, **okw)
     ref = O.render_rays(cfg, sd, rays, tr, uj, keep_intermediates=True)
     out = PT.render_cuda(build_renderer(c, sd, precision="fp32"), rays, tr, uj)
+    if embed == "normal":
+        zc, wc = ref["z_coarse"], ref["weights_coarse"]
+        w = (wc[:, 1:-1] + np.float32(1e-5)); pdf = w / w.sum(-1, keepdims=True); cdf = np.concatenate([np.zeros((n, 1), np.float32), np.cumsum(pdf, -1)], -1)
+        inds = ref["idx_fine"].astype(np.int64)
+        below, above = np.maximum(0, inds - 1), np.minimum(cdf.shape[-1] - 1, inds)
+        denom = np.take_along_axis(cdf, above, 1) - np.take_along_axis(cdf, below, 1)
+        mind = denom.min(-1)
+        e_all = np.maximum.reduce([ray_rel_err(out[f"{q}_fine"], ref[f"{q}_fine"]) for q in ("feat", "pts", "rgb", "depth")])
+        for tau in (1e-5, 1e-4, 1e-3, 1e-2):
+            good = mind >= tau
+            print("  tau", tau, "well-conditioned rays", int(good.sum()), "max e among them", float(e_all[good].max()) if good.any() else None,
+                  "max e among the rest", float(e_all[~good].max()) if (~good).any() else None)
     for q in ("feat", "pts", "rgb", "depth"):
         e = ray_rel_err(out[f"{q}_fine"], ref[f"{q}_fine"])
         bad = e >= 1e-3

@@ -148,11 +148,17 @@ def test_stage_backward_entry_points_vs_finite_differences():
     # ---- MLP: torch autograd (float64, CPU) through the same network written with F.linear (models/nerf.py:94-144) ----
     import torch.nn.functional as F
 
-    for embed, app, stop in (("mip", 0, 3), ("normal", 16, 4), ("mip", 0, -1), ("normal", 0, 7)):
+    import os
+
+    for embed, app, stop, tc in (("mip", 0, 3, "1"), ("normal", 16, 4, "1"), ("mip", 0, -1, "0"), ("normal", 0, 7, "1"), ("normal", 16, 4, "0")):
+        # NMR_GEMM_TC (read at nmr_create): 1 = dgrad chain on the tensor cores (fp32 operands split into bf16 hi + lo, three
+        # MMAs per K step: ~2^-16 per product), 0 = fp32 SIMT GEMMs
+        os.environ["NMR_GEMM_TC"] = tc
         cfg = O.RenderConfig(embed_type=embed, app_dim=app)
         sd = make_state_dict(5, embed_type=embed, app_dim=app, num_frames=3 if app else 0, sigma_gain=40.0, sigma_bias=2.0)
         wts = O.split_state_dict(sd, "nerf_fine.")
         eng = Engine(EngineConfig(embed_type=embed, app_dim=app, precision="fp32"), torch.device(DEV))
+        os.environ.pop("NMR_GEMM_TC")
         eng.set_weights(0, {k: torch.from_numpy(v) for k, v in wts.items()})
         P, D = 300, cfg.xyz_dim + cfg.dirs_dim + app
         x = (rng.random((P, D)) * 2 - 1).astype(np.float32)
@@ -178,7 +184,7 @@ def test_stage_backward_entry_points_vs_finite_differences():
         ref = xt.grad.numpy()
         # a unit whose pre-activation is within fp32 round-off of zero can take the other ReLU branch: per-row comparison
         err = np.linalg.norm(gx - ref, axis=1) / np.linalg.norm(ref, axis=1)
-        assert np.median(err) < 1e-5 and (err < 1e-3).mean() > 0.98, (embed, stop, np.median(err), (err < 1e-3).mean())
+        assert np.median(err) < (2e-4 if tc == "1" else 1e-5) and (err < 2e-3).mean() > 0.98, (embed, stop, tc, np.median(err), (err < 2e-3).mean())
     # ---- compositing ----
     for embed in ("mip", "normal"):
         eng = Engine(EngineConfig(embed_type=embed), torch.device(DEV))

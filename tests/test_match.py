@@ -67,3 +67,31 @@ def test_cuda_coarse_match_full_size_properties():
     assert out["pred_num"] > 0.9 * m                                                 # noisy copies are recovered ...
     assert (perm[i] == j).float().mean() > 0.999                                     # ... at the right place
     assert len(torch.unique(j)) == len(j) and (i[1:] > i[:-1]).all()                 # mutual -> one-to-one, ordered
+
+
+@pytest.mark.gpu
+def test_similarity_gemm_tensor_core_vs_simt():
+    """The matcher's one contraction runs on the tensor cores (fp32 operands split into bf16 hi + lo, 3 MMAs per K step);
+    NMR_GEMM_TC=0 selects the fp32 SIMT GEMM.  Same matches, confidences equal to ~1e-4 relative (exp(10 * 2^-16))."""
+    import os
+
+    import torch
+
+    import nerfmatch_b200.matching as MM
+
+    rng = np.random.default_rng(11)
+    m, n, d = 1000, 1300, 256
+    pt = rng.standard_normal((n, d)).astype(np.float32)
+    im = (pt[rng.permutation(n)[:m]] + 0.4 * rng.standard_normal((m, d))).astype(np.float32)
+    res = {}
+    for tc in ("1", "0"):
+        os.environ["NMR_GEMM_TC"] = tc
+        MM._engines.clear()
+        try:
+            out = MM.coarse_match(torch.from_numpy(im).cuda(), torch.from_numpy(pt).cuda(), temperature=10.0, mutual=True, match_thres=0.2)
+        finally:
+            os.environ.pop("NMR_GEMM_TC")
+        res[tc] = (out["conf_matrix"][0].cpu().numpy(), out["match_ids"][1].cpu().numpy(), out["match_ids"][2].cpu().numpy())
+    MM._engines.clear()
+    np.testing.assert_allclose(res["1"][0], res["0"][0], rtol=3e-4, atol=1e-9)
+    assert np.array_equal(res["1"][1], res["0"][1]) and np.array_equal(res["1"][2], res["0"][2]) and len(res["1"][1]) > 0.8 * m
