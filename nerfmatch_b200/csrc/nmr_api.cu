@@ -491,15 +491,21 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
   const bool bf16 = c.precision != NMR_PREC_FP32;      // the tcgen05 path (bf16 or fp16 operands)
   const int tcfmt = c.precision == NMR_PREC_FP16;
   const int smax = std::max(d.sc, d.sf);
-  // fp32 path: ~3.7 KB of workspace per point; bf16 path: ~0.6 KB (raw, tiled features for the unfused tap, partials) -> larger chunks
-  const int64_t max_points = (bf16 && h->auto_chunk) ? ((int64_t)1 << 22) : c.max_chunk_points;
+  const bool pfeat = (a->flags & NMR_FLAG_RET_PFEAT) != 0;
+  // tcgen05 path: does any pass stream per-sample features to the compositor (unfused tap: 512 B per point of workspace)?
+  const bool fusable = h->fuse_composite && !(a->flags & NMR_FLAG_FEAT_MAX) && std::min(d.sc, d.sf) >= kTcMinFuseS &&
+                       !a->sigma_noise_coarse && !a->sigma_noise_fine;
+  const bool feat_tiles = pfeat && !fusable;
+  // fp32 path: ~3.7 KB of workspace per point.  tcgen05 path: 48 B per point fused (raw + per-tile partial composites), so a whole
+  // 480x640 view (59 M points, 2.8 GB) goes through in ONE chunk - no per-chunk launch ramps / partial last waves; 0.6 KB per point
+  // with the unfused tap, and the host entry keeps ~15 chunks so that the device->host copies overlap the next chunk's render.
+  const int64_t max_points = (bf16 && h->auto_chunk) ? ((feat_tiles || sink) ? ((int64_t)1 << 22) : ((int64_t)1 << 26)) : c.max_chunk_points;
   int64_t chunk_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, max_points / smax));
   if ((r = ensure_workspace(h, chunk_rays, bf16 ? 0 : chunk_rays * smax)) != NMR_OK) return r;
   if (bf16) {
     std::string terr;
-    if (tc_ensure_workspace(d, chunk_rays, &h->tcws.p, &h->tcws.cap, &terr) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc workspace: %s", terr.c_str());
+    if (tc_ensure_workspace(d, chunk_rays, &h->tcws.p, &h->tcws.cap, &terr, feat_tiles) != 0) NMR_FAIL(h, NMR_ERR_CUDA, "tc workspace: %s", terr.c_str());
   }
-  const bool pfeat = (a->flags & NMR_FLAG_RET_PFEAT) != 0;
   float* zc = (float*)h->zc.p;
   float* zf = (float*)h->zf.p;
   float* X = (float*)h->X.p;
@@ -548,7 +554,7 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
         TcRun tr{};
         tr.rays = rays; tr.n = nr; tr.ncols = a->ncols; tr.S = S; tr.z = z; tr.ray_id = rid;
         tr.app_table = app_table; tr.num_frames = h->num_frames; tr.var_scale = c.mip_var_scale;
-        tr.stop_layer = stop; tr.want_feat = want_feat; tr.ws = h->tcws.p;
+        tr.stop_layer = stop; tr.want_feat = want_feat; tr.ws = h->tcws.p; tr.ws_rays = chunk_rays; tr.ws_with_feat = feat_tiles;
         // (the in-kernel tile compositing recomputes alpha from the raw density: not with injected sigma noise)
         tr.fuse_composite = h->fuse_composite && !(a->flags & NMR_FLAG_FEAT_MAX) && !(pass == 0 ? a->sigma_noise_coarse : a->sigma_noise_fine);
         std::string terr; int nl = 0;

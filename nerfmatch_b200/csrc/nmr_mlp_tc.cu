@@ -1131,12 +1131,13 @@ void pack_chunk(std::vector<uint8_t>& out, const float* W, int rows, int ldw, in
 struct TcWs {   // carved from one device allocation
   float* raw; uint8_t* feat; float* vbias; int* error_flag; float* xfeat; float* partials;
 };
-size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep) {
+// with_feat: reserve the tiled per-sample feature buffer (512 B per point; only the unfused tap needs it)
+size_t ws_layout(int64_t points, int64_t vb_rows, TcWs* w, uint8_t* basep, bool with_feat = true) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
   int64_t tiles = (points + kTileM - 1) / kTileM + 2;
   size_t o_raw = take((size_t)tiles * kTileM * 4 * sizeof(float));
-  size_t o_feat = take((size_t)tiles * kFeatTileBytes);
+  size_t o_feat = take(with_feat ? (size_t)tiles * kFeatTileBytes : 1024);
   size_t o_vb = take((size_t)std::max<int64_t>(vb_rows, 1) * kHalf * sizeof(float));
   size_t o_err = take(1024);
   size_t o_part = take((size_t)tiles * kSeg * kHid * sizeof(float));
@@ -1363,8 +1364,8 @@ static int reserve(void** ws, size_t* cap, size_t need, std::string* err) {
   return cudaMemset(*ws, 0, 1024) == cudaSuccess ? 0 : -1;
 }
 
-int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err) {
-  size_t need = ws_layout(chunk_rays * std::max(d.sc, d.sf), chunk_rays, nullptr, nullptr);
+int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err, bool with_feat) {
+  size_t need = ws_layout(chunk_rays * std::max(d.sc, d.sf), chunk_rays, nullptr, nullptr, with_feat);
   return reserve(ws, cap, need, err);
 }
 
@@ -1375,7 +1376,7 @@ int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, con
   if (!net.set) { *err = "weights not packed"; return -1; }
   if (r.S < 1) { *err = "S < 1"; return -1; }
   TcWs w{};
-  ws_layout(r.n * std::max(d.sc, d.sf), r.n, &w, (uint8_t*)r.ws);
+  ws_layout(r.ws_rays * std::max(d.sc, d.sf), r.ws_rays, &w, (uint8_t*)r.ws, r.ws_with_feat);
   VbParams vp{};
   vp.mode = 0; vp.rays = r.rays; vp.ncols = r.ncols; vp.ray_id = r.ray_id; vp.app_table = r.app_table; vp.num_frames = r.num_frames;
   vp.mip = d.mip; vp.fd = d.fd; vp.dirs = d.dirs; vp.app = d.app; vp.dap = d.dap;
@@ -1389,6 +1390,7 @@ int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, con
   p.stop_step = r.stop_layer < 0 ? kLayers - 1 : r.stop_layer; p.want_feat = r.want_feat ? 1 : 0;
   p.raw = w.raw; p.feat_tiles = w.feat; p.debug_step = -1; p.debug_out = nullptr; p.error_flag = w.error_flag;
   const bool fuse = r.fuse_composite && r.want_feat && r.S >= kTcMinFuseS;
+  if (r.want_feat && !fuse && !r.ws_with_feat) { *err = "internal: workspace was sized without the per-sample feature tiles"; return -1; }
   p.partials = fuse ? w.partials : nullptr;
   if (launch_tc(net, p, launches, s, err) != 0) return -1;
   *raw_out = w.raw; *feat_out = w.feat; *partials_out = p.partials;

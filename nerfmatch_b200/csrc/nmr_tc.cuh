@@ -37,12 +37,13 @@ struct TcRun {
   float var_scale;
   int stop_layer; bool want_feat;
   bool fuse_composite;          // tile-local feature compositing inside the kernel (needs S >= 43, linear feat_comb)
-  void* ws;
+  void* ws;                     // workspace from tc_ensure_workspace(d, ws_rays, ..., ws_with_feat): the layout depends on both
+  int64_t ws_rays; bool ws_with_feat;
 };
 
 int tc_pack_net(const Dims& d, int skip_layer, const HostNet& hn, TcNet* out, std::string* err, int fmt = 0);
 void tc_free_net(TcNet* n);
-int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err);
+int tc_ensure_workspace(const Dims& d, int64_t chunk_rays, void** ws, size_t* cap, std::string* err, bool with_feat = true);
 // Sample rows of one pass (encode + MLP fused): writes raw [n*S,4] fp32 and either tiled bf16 features or
 // (fuse_composite) per-tile, per-ray-segment partial composites [tiles][4][256] fp32 into the workspace and
 // returns their addresses (*partials_out is null when not fused).

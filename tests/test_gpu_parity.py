@@ -271,19 +271,23 @@ def test_full_render_fp32_vs_oracle_and_chunking(embed):
     b = _render(build_renderer(c, sd, precision="fp32", max_chunk_points=192 * 37), g)  # 37-ray chunks
     for k in a:
         assert np.array_equal(a[k], b[k]), k
-    S1 = 65 if embed == "mip" else 128
     assert (a["idx_fine"] == ref["idx_fine"]).mean() > 0.998
+    # Fine pass, ray by ray.  The only source of deviation is identified: the POSITION of a fine sample drawn inside a CDF
+    # interval of (near-)zero mass.  Inverse-CDF sampling divides by that mass (floored at 1e-5 / sum w, render_utils.py:
+    # 236-262), so the ~1e-7 round-off of the coarse weights (different fp32 summation order in the MLP) moves such a sample by
+    # up to ~5e-4 inside its bin - same bin index - and an untrained classic NeRF then evaluates a different phase of its
+    # 2^14-frequency encoding there.  Rays whose sample positions agree meet the north star strictly; the others are bounded.
+    dz = np.abs(a["z_fine"] - ref["z_fine"]).max(-1)
+    same = dz <= 1e-6
+    assert dz.max() < 2e-3 and same.mean() > (0.95 if embed == "mip" else 0.4), (dz.max(), same.mean())
     for key in ("coarse", "fine"):
-        tol = 1e-4 if key == "coarse" else 1e-3
         for q in ("feat", "pts", "rgb", "depth"):
             if key == "coarse":
-                assert rel_l2(a[f"{q}_{key}"], ref[f"{q}_{key}"]) < tol, (q, key)
+                assert rel_l2(a[f"{q}_{key}"], ref[f"{q}_{key}"]) < 1e-4, (q, key)
             else:
-                # fine pass, per ray: the classic renderer's last interval is 1e10 wide (render_utils.py:205), so
-                # the last sample's alpha is a step function of sign(sigma) and a ray whose last sigma is within
-                # round-off of 0 legitimately flips; all other rays meet the north-star 1e-3.
                 e = ray_rel_err(a[f"{q}_{key}"], ref[f"{q}_{key}"])
-                assert (e < tol).mean() > 0.98 and np.median(e) < 1e-4, (q, key, (e < tol).mean(), np.median(e))
+                assert e[same].max() < 1e-3, (q, e[same].max())                                  # north star on every such ray
+                assert e.max() < 3e-2 and (e < 1e-3).mean() > 0.99 and np.median(e) < 1e-4, (q, e.max(), (e < 1e-3).mean(), np.median(e))
     assert np.all(np.diff(a["z_fine"], axis=-1) >= 0)
 
 
@@ -411,10 +415,15 @@ def test_options_use_disp_and_var_scale_fp32():
         np.testing.assert_allclose(out["z_coarse"], ref["z_coarse"], rtol=0, atol=2e-6)
         for q in ("feat", "pts", "rgb", "depth"):
             assert rel_l2(out[f"{q}_coarse"], ref[f"{q}_coarse"]) < 1e-4, (embed, q)
-            # fine pass per ray: disparity sampling puts most samples near the camera, so the few far intervals are wide
-            # and amplify fp32 round-off of sigma; the bulk meets 1e-3, everything 1e-2
+            # fine pass per ray: as in test_full_render_fp32_vs_oracle_and_chunking - rays whose fine sample positions agree with
+            # the oracle's meet 1e-3 strictly; disparity sampling leaves most CDF intervals (nearly) empty, so more rays have a
+            # sample whose position inside such an interval is ill-conditioned; those are bounded
+            dz = np.abs(out["z_fine"] - ref["z_fine"]).max(-1)
+            same = dz <= 1e-6
             e = ray_rel_err(out[f"{q}_fine"], ref[f"{q}_fine"])
-            assert (e < 1e-3).mean() > 0.8 and (e < 1e-2).mean() > 0.98 and np.median(e) < 2e-4, (embed, q, (e < 1e-3).mean(), np.median(e))
+            assert same.mean() > (0.9 if embed == "mip" else 0.25) and dz.max() < 2e-3, (embed, same.mean(), dz.max())
+            assert e[same].max() < 1e-3, (embed, q, e[same].max())
+            assert e.max() < 5e-2 and (e < 1e-3).mean() > 0.8 and np.median(e) < 2e-4, (embed, q, e.max(), (e < 1e-3).mean(), np.median(e))
 
 
 def test_cache_writer_matches_render_novel_view(tmp_path):
