@@ -252,8 +252,17 @@ def inerf_step_ms(dev, precision, steps=5):
     opt = torch.optim.Adam(params=[cam_pose], lr=1e-3)
     eps = torch.tensor(torch.finfo(torch.float32).eps, device=dev)
 
+    marks = []
+
+    def mark():
+        if marks is not None and len(marks) < 64:
+            e_ = torch.cuda.Event(enable_timing=True)
+            e_.record()
+            marks.append(e_)
+
     def step():
         with torch.enable_grad():
+            mark()
             o = cam_pose[:, None, None, :3, 3].expand(-1, H, W, -1)[0]
             d = torch.matmul(cam_pose[:, None, None, :3, :3], dirs.unsqueeze(-1))[0, :, :, :, 0]
             v = d / d.norm(dim=-1, keepdim=True)
@@ -271,6 +280,8 @@ def inerf_step_ms(dev, precision, steps=5):
                 pts_z = rays[:, None, :3].expand(rays.shape[0], 128, 3) + t_mean[:, :, None] * vf
                 x = torch.cat((ren.xyz_encoder(pts_z.contiguous().view(-1, 3), y=pts[1].contiguous().view(-1, 3))[0],
                                ren.dirs_encoder(vf.contiguous().view(-1, 3))), -1)
+                if key == "fine":
+                    mark()
                 if key == "coarse":
                     with torch.no_grad():
                         raw, _ = model.forward(x, ret_pfeat=1, val=True)
@@ -279,9 +290,12 @@ def inerf_step_ms(dev, precision, steps=5):
                 rgb_map, _, _, wts, _, _ = volume_render_radiance_field(raw.view(-1, 128, 4), z, rays[..., 3:6], noise_std=0.0, white_bg=True,
                                                                         embed_type="mip", input_dim=4)
             loss = torch.nn.functional.mse_loss(rgb_map, img)
+            mark()
             loss.backward()
+            mark()
             opt.step()
             opt.zero_grad()
+            mark()
         return loss
 
     prev = torch.is_grad_enabled()
@@ -290,6 +304,12 @@ def inerf_step_ms(dev, precision, steps=5):
         for _ in range(2):
             step()
         torch.cuda.synchronize(dev)
+        marks.clear()
+        step()                               # one instrumented step: phase boundaries
+        torch.cuda.synchronize(dev)
+        phases = {k: marks[i].elapsed_time(marks[i + 1]) for i, k in enumerate(
+            ("rays_coarse_pass_fine_sampling_encoding", "fine_mlp_render_loss", "backward", "adam"))} if len(marks) >= 5 else {}
+        marks = None
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(steps):
@@ -299,7 +319,8 @@ def inerf_step_ms(dev, precision, steps=5):
     finally:
         torch.set_grad_enabled(prev)
     return {"ms_per_step": a.elapsed_time(b) / steps, "rays": int(img.shape[0]), "samples": "128 coarse (no grad) + 128 fine (grad), mip", "loss": float(loss.detach()),
-            "forward": precision, "backward": "fp32 dgrad chain, activations recomputed",
+            "phases_ms": phases, "forward": precision,
+            "backward": "activations recomputed, dgrad chain on the tensor cores (fp32 operands split into bf16 hi + lo: 3 MMAs per K step)",
             "what": "gen_rays -> sample -> encode -> NeRF -> volume render -> MSE -> backward -> Adam, as nerfmatch_evaluator.py:334-452"}
 
 
@@ -461,6 +482,13 @@ def run_ours(args):
     ms_dev, t0, t1 = timed(step_dev, args.steps, args.warmup)
     launches = (eng.launch_count() - l0) // (args.steps + args.warmup) * args.steps
     clocks = sampler.stop(t0, t1) if rank == 0 else None
+    if args.only_dev:       # profiling runs (ncu): the device-resident arm only
+        if rank == 0:
+            emit({"metric": METRIC, "value": n * world * args.steps / (ms_dev / 1e3), "unit": "rays/s", "ms_per_step": ms_dev / args.steps,
+                  "note": "--only-dev (profiling run): not a bench line"})
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- per-stage split (separate pass, CUDA events on the launch stream inside the library) ----
     eng.set_timing(True)
     for _ in range(args.steps):
@@ -637,6 +665,7 @@ def main():
     ap.add_argument("--embed", default="normal", choices=["normal", "mip"])
     ap.add_argument("--cpu-rays", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-dev", action="store_true", help="profiling runs: time the device-resident arm and stop")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":
