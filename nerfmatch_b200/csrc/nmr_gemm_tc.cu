@@ -115,13 +115,13 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
   const int nchunks = c1 + c2;
   const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-  for (int t = 0; t < nchunks; ++t) {
-    const int st = t & 1;
+  // global -> registers for chunk t: issued one iteration AHEAD (right after chunk t-1's MMAs are queued), so the load latency
+  // overlaps the tensor core's work on the previous chunk and the wait for the stage
+  float4 ua[2], va[2], ub[4], vb[4];
+  auto load_chunk = [&](int t) {
     const float* A; const float* W; int lda, ldw, k0, K;
     if (t < c1) { A = p.A1; lda = p.lda1; W = p.W1; ldw = p.K1; k0 = t * BK; K = p.K1; }
     else { A = p.A2; lda = p.lda2; W = p.W2; ldw = p.K2; k0 = (t - c1) * BK; K = p.K2; }
-    // ---- global -> registers (issued before the stage is known to be free: latency overlaps the wait) ----
-    float4 ua[2], va[2], ub[4], vb[4];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int idx = i * kThreadsG + tid, r = idx >> 2, c = idx & 3;
@@ -140,6 +140,10 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
       ub[i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
       vb[i] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  };
+  load_chunk(0);
+  for (int t = 0; t < nchunks; ++t) {
+    const int st = t & 1;
     // ---- the MMAs that read this stage two chunks ago have retired ----
     if (t >= kStagesG) mbar_wait(bars + 8 * st, (uint32_t)((t / kStagesG) - 1) & 1u);
     const uint32_t sA_hi = base + st * kStage, sA_lo = sA_hi + kABlk, sB_hi = sA_lo + kABlk, sB_lo = sB_hi + kBBlk;
@@ -167,14 +171,20 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
       umma_commit(bars + 8 * st);                                      // stage free once these MMAs retire
       if (t == nchunks - 1) umma_commit(bars + 16);                    // accumulator complete
     }
+    if (t + 1 < nchunks) load_chunk(t + 1);
   }
 
-  // ---- epilogue: warps 0..3 own TMEM lane quarters 0..3 (row = 32 * warp + lane) ----
+  // ---- epilogue: warps 0..3 own TMEM lane quarters 0..3.  tcgen05.ld hands every thread ONE ROW (32 columns of it per
+  // chunk); touching global memory in that shape would cost 32 wavefronts per access (rows are >= 1 KB apart), so each warp
+  // transposes the chunk through shared memory (the operand stages are free by now; 33-float rows: conflict-free both ways)
+  // and then works on four rows x 128 contiguous bytes per instruction: mask / add loads and the stores are fully coalesced.
   if (warp < 4) {
     mbar_wait(bars + 16, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t r = row0 + warp * 32 + lane;
-    const float r1 = (p.r1a && r < p.M) ? p.r1a[r * p.ldr1] : 0.f;
+    float* tile = reinterpret_cast<float*>(gbase) + warp * (32 * 33);
+    const int64_t rbase = row0 + warp * 32;
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;                  // this lane's row within a group of four, and its 4 columns
+    const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       const int c0 = col0 + j * 32;
@@ -190,32 +200,44 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
             "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(tmem + ((uint32_t)(warp * 32) << 16) + j * 32) : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (r < p.M) {
-        float* out = p.C + r * p.ldc + c0;
-        const bool vec = (c0 + 32 <= p.N) && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+      __syncwarp();                                                    // the previous chunk's reads of the tile are done
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float x[4];
+      for (int c = 0; c < 32; ++c) tile[lane * 33 + c] = __uint_as_float(v[c]);
+      __syncwarp();
+      const int cc0 = c0 + c4;
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f}, r1b4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int cc = c0 + 4 * q + e;
-            float y = __uint_as_float(v[4 * q + e]);
-            if (cc < p.N) {
-              if (p.bias) y += p.bias[cc];
-              if (p.r1a) y = fmaf(r1, p.r1b[cc], y);
-              if (p.add) y += p.add[r * p.ldadd + cc];
-              y = act_of(y, p.act);
-              if (p.mask && !(p.mask[r * p.ldm + cc] > 0.f)) y = 0.f;
-            }
-            x[e] = y;
+      for (int e = 0; e < 4; ++e) {
+        if (cc0 + e < p.N) {
+          if (p.bias) bias4[e] = p.bias[cc0 + e];
+          if (p.r1a) r1b4[e] = p.r1b[cc0 + e];
+        }
+      }
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + rsub;
+        const int64_t r = rbase + rr;
+        if (r >= p.M) continue;
+        const float r1 = p.r1a ? p.r1a[r * p.ldr1] : 0.f;
+        float x[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float y = tile[rr * 33 + c4 + e] + bias4[e];
+          y = fmaf(r1, r1b4[e], y);
+          if (cc0 + e < p.N) {
+            if (p.add) y += p.add[r * p.ldadd + cc0 + e];
+            y = act_of(y, p.act);
+            if (p.mask && !(p.mask[r * p.ldm + cc0 + e] > 0.f)) y = 0.f;
           }
-          if (vec) {
-            *reinterpret_cast<float4*>(out + 4 * q) = make_float4(x[0], x[1], x[2], x[3]);
-          } else {
+          x[e] = y;
+        }
+        float* out = p.C + r * p.ldc + cc0;
+        if (vec_ok && cc0 + 4 <= p.N) {
+          *reinterpret_cast<float4*>(out) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (c0 + 4 * q + e < p.N) out[4 * q + e] = x[e];
-          }
+          for (int e = 0; e < 4; ++e)
+            if (cc0 + e < p.N) out[e] = x[e];
         }
       }
     }
