@@ -185,10 +185,48 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
     const int64_t rbase = row0 + warp * 32;
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;                  // this lane's row within a group of four, and its 4 columns
     const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+    const bool vec_in = (!p.mask || ((p.ldm % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.mask) & 15) == 0))) &&
+                        (!p.add || ((p.ldadd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.add) & 15) == 0)));
 #pragma unroll 1
     for (int j = 0; j < BN / 32; ++j) {
       const int c0 = col0 + j * 32;
       if (c0 >= p.N) break;                                            // warp-uniform
+      const int cc0 = c0 + c4;
+      const bool full = cc0 + 4 <= p.N;
+      // all global reads of this column chunk are issued FIRST (16 independent 16-byte loads per thread): their latency
+      // overlaps the TMEM load and the transposition instead of being paid once per row group
+      float4 mk[8], ad[8];
+      float r1[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t r = rbase + 4 * i + rsub;
+        mk[i] = make_float4(1.f, 1.f, 1.f, 1.f); ad[i] = make_float4(0.f, 0.f, 0.f, 0.f); r1[i] = 0.f;
+        if (r < p.M) {
+          if (p.r1a) r1[i] = __ldg(p.r1a + r * p.ldr1);
+          if (full && vec_in) {
+            if (p.mask) mk[i] = __ldg(reinterpret_cast<const float4*>(p.mask + r * p.ldm + cc0));
+            if (p.add) ad[i] = __ldg(reinterpret_cast<const float4*>(p.add + r * p.ldadd + cc0));
+          } else {
+            float m4[4] = {1.f, 1.f, 1.f, 1.f}, a4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (cc0 + e < p.N) {
+                if (p.mask) m4[e] = p.mask[r * p.ldm + cc0 + e];
+                if (p.add) a4[e] = p.add[r * p.ldadd + cc0 + e];
+              }
+            }
+            mk[i] = make_float4(m4[0], m4[1], m4[2], m4[3]); ad[i] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+          }
+        }
+      }
+      float bias4[4] = {0.f, 0.f, 0.f, 0.f}, r1b4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (cc0 + e < p.N) {
+          if (p.bias) bias4[e] = p.bias[cc0 + e];
+          if (p.r1a) r1b4[e] = p.r1b[cc0 + e];
+        }
+      }
       uint32_t v[32];
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -204,35 +242,24 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
 #pragma unroll
       for (int c = 0; c < 32; ++c) tile[lane * 33 + c] = __uint_as_float(v[c]);
       __syncwarp();
-      const int cc0 = c0 + c4;
-      float bias4[4] = {0.f, 0.f, 0.f, 0.f}, r1b4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (cc0 + e < p.N) {
-          if (p.bias) bias4[e] = p.bias[cc0 + e];
-          if (p.r1a) r1b4[e] = p.r1b[cc0 + e];
-        }
-      }
-#pragma unroll 2
       for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + rsub;
         const int64_t r = rbase + rr;
         if (r >= p.M) continue;
-        const float r1 = p.r1a ? p.r1a[r * p.ldr1] : 0.f;
+        const float m4[4] = {mk[i].x, mk[i].y, mk[i].z, mk[i].w}, a4[4] = {ad[i].x, ad[i].y, ad[i].z, ad[i].w};
         float x[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           float y = tile[rr * 33 + c4 + e] + bias4[e];
-          y = fmaf(r1, r1b4[e], y);
-          if (cc0 + e < p.N) {
-            if (p.add) y += p.add[r * p.ldadd + cc0 + e];
-            y = act_of(y, p.act);
-            if (p.mask && !(p.mask[r * p.ldm + cc0 + e] > 0.f)) y = 0.f;
-          }
+          y = fmaf(r1[i], r1b4[e], y);
+          y += a4[e];
+          y = act_of(y, p.act);
+          if (!(m4[e] > 0.f)) y = 0.f;
           x[e] = y;
         }
         float* out = p.C + r * p.ldc + cc0;
-        if (vec_ok && cc0 + 4 <= p.N) {
+        if (vec_ok && full) {
           *reinterpret_cast<float4*>(out) = make_float4(x[0], x[1], x[2], x[3]);
         } else {
 #pragma unroll
