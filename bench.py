@@ -374,6 +374,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """One process per GPU: pin this process to the CPUs next to its GPU BEFORE any pinned host buffer is allocated, so the
+    end-to-end arm's host buffers (first-touch) live on the GPU's own NUMA node instead of all eight ranks sharing node 0."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus ({cpus[0]}..{cpus[-1]})"
+    except Exception as e:      # no NVML / restricted container: run unbound
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -384,6 +403,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -580,6 +600,7 @@ def run_ours(args):
     }
     if exchange is not None:
         line["exchange"] = exchange
+        line["e2e"]["host_numa_binding_rank0"] = numa
     line["config4"] = {"workload": "64 query poses x 4800 rays (480x640, ds=8), rays of all views sharded across the ranks, pt_feat / pt3d / im_pred delivered to rank 0",
                        "scaling": "strong", "rays": 64 * 4800, "ms_per_batch": ms_cfg4 / args.steps, "value": 64 * 4800 * args.steps / (ms_cfg4 / 1e3), "unit": "rays/s"}
     if other is not None:

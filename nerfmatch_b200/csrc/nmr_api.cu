@@ -498,9 +498,25 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
   const bool feat_tiles = pfeat && !fusable;
   // fp32 path: ~3.7 KB of workspace per point.  tcgen05 path: 48 B per point fused (raw + per-tile partial composites), so a whole
   // 480x640 view (59 M points, 2.8 GB) goes through in ONE chunk - no per-chunk launch ramps / partial last waves; 0.6 KB per point
-  // with the unfused tap, and the host entry keeps ~15 chunks so that the device->host copies overlap the next chunk's render.
-  const int64_t max_points = (bf16 && h->auto_chunk) ? ((feat_tiles || sink) ? ((int64_t)1 << 22) : ((int64_t)1 << 26)) : c.max_chunk_points;
-  int64_t chunk_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, max_points / smax));
+  // with the unfused tap.  The host entry (sink) halves the remaining rays chunk by chunk (1/2, 1/4, ... of the call): the big
+  // first chunks keep the launch count low and their device->host copies ride under the rest of the render; only the small last
+  // chunk's copy (~6 % of the outputs) is exposed.
+  const int64_t max_points = (bf16 && h->auto_chunk) ? (feat_tiles ? ((int64_t)1 << 22) : ((int64_t)1 << 26)) : c.max_chunk_points;
+  const int64_t cap_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, max_points / smax));
+  std::vector<int64_t> schedule;                       // rays per chunk
+  if (sink && bf16 && h->auto_chunk && !feat_tiles) {
+    const int64_t min_chunk = 16384;
+    int64_t rem = a->n;
+    while (rem > 2 * min_chunk) {
+      const int64_t cnk = std::min(cap_rays, (rem / 2 + 1023) / 1024 * 1024);
+      schedule.push_back(cnk);
+      rem -= cnk;
+    }
+    while (rem > 0) { const int64_t cnk = std::min(cap_rays, rem); schedule.push_back(cnk); rem -= cnk; }
+  } else {
+    for (int64_t rem = a->n; rem > 0; rem -= std::min(cap_rays, rem)) schedule.push_back(std::min(cap_rays, rem));
+  }
+  const int64_t chunk_rays = *std::max_element(schedule.begin(), schedule.end());     // workspace: the largest chunk
   if ((r = ensure_workspace(h, chunk_rays, bf16 ? 0 : chunk_rays * smax)) != NMR_OK) return r;
   if (bf16) {
     std::string terr;
@@ -512,8 +528,9 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
   float* raw = (float*)h->raw.p;
   const float* app_table = (const float*)h->app.p;
 
-  for (int64_t r0 = 0; r0 < a->n; r0 += chunk_rays) {
-    const int64_t nr = std::min<int64_t>(chunk_rays, a->n - r0);
+  int64_t r0 = 0;
+  for (size_t ci = 0; ci < schedule.size(); r0 += schedule[ci], ++ci) {
+    const int64_t nr = schedule[ci];
     const float* rays = a->rays + r0 * a->ncols;
     const int64_t* rid = a->ray_id ? a->ray_id + r0 : nullptr;
     for (int pass = 0; pass < 2; ++pass) {

@@ -1,0 +1,96 @@
+"""BASELINE.json configs 3 and 4 as parity tests (config 1 / 2: tests/test_gpu_parity_table.py; config 5: scripts/sweep.py).
+
+config 3: Cambridge KingsCollege-sized 480x854 view rendered at the matcher's resolution (ds=8 -> 60 x 107 = 6420 points,
+          mip 128+128) with render_novel_view + NeRFMatch-Mini coarse matching on the rendered 3D features, against the oracle.
+config 4: a batch of query poses rendered through the batched path (all views' rays in one call, as the sharded renderer does
+          per rank) equals view-by-view rendering; the 2-GPU sharded form is tests/test_gpu_surfaces.py."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from nmr_helpers import build_renderer, cosine_rows, rel_l2  # noqa: E402
+from oracle import match_oracle as MO  # noqa: E402
+from oracle import nerf_oracle as O  # noqa: E402
+from oracle.weights import K_7SCENES, K_CAMBRIDGE, make_pose, make_state_dict, make_unnorm_scene, uniform01  # noqa: E402
+import parity_table as PT  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def test_config3_cambridge_render_and_coarse_matching():
+    from nerfmatch_b200.matching import coarse_match
+
+    c = dict(embed="mip", nc=128, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+    sd = make_state_dict(33, embed_type="mip", sigma_gain=120.0, sigma_bias=(8.0, 8.0))
+    un = make_unnorm_scene(60.0)                                    # Cambridge scenes: tens of metres
+    pose_n = make_pose(5)
+    c2w_world = un @ pose_n
+    H, W, ds = 480, 854, 8
+    rays = O.sample_nerf_rays(H, W, K_CAMBRIDGE, pose_n, ds=ds, embed_type="mip")
+    n = rays.shape[0]
+    assert n == 60 * 107
+    tr = uniform01(34, 1, n * 129).reshape(n, 129)
+    uj = (uniform01(34, 2, n * 129).reshape(n, 129) * (1 / 129 - 1.2e-7)).astype(np.float32)
+    cfg = O.RenderConfig(embed_type="mip", num_pts_coarse=128, num_pts_fine=128, stop_layer=3)
+    ref = PT.oracle_render(cfg, sd, rays, tr, uj, un)
+    res = {}
+    for prec in ("fp32", "bf16", "fp16"):
+        ren = build_renderer(c, sd, precision=prec)
+        # device ray generation from the WORLD pose, as render_novel_view does; the draws are injected for parity
+        eng = ren.engine(torch.device(DEV))
+        rays_dev, (h, w), missed = eng.raygen(K_CAMBRIDGE, np.linalg.inv(un) @ c2w_world, H, W, ds, check_far=True)
+        assert (h, w) == (60, 107) and not missed
+        np.testing.assert_allclose(N(rays_dev)[:, :11], rays[:, :11], rtol=1e-5, atol=2e-6)
+        out = PT.render_cuda(ren, rays, tr, uj, None, un)              # same rays as the oracle (device ray generation checked above)
+        res[prec] = out
+        cos = cosine_rows(out["feat_fine"], ref["feat_fine"])
+        d3 = np.linalg.norm(out["pt3d"] - ref["pt3d"], axis=-1)      # metres at scene scale 60 m
+        if prec == "fp32":
+            assert rel_l2(out["feat_fine"], ref["feat_fine"]) < 1e-3 and rel_l2(out["depth_fine"], ref["depth_fine"]) < 1e-3
+            assert d3.max() < 1e-3, d3.max()                          # 1 mm at 60 m scale
+        else:
+            assert cos.min() >= 0.999, (prec, cos.min())
+            assert d3.max() < (2e-2 if prec == "bf16" else 3e-3), (prec, d3.max())   # 60 m scene: 1 mm = 1.7e-5 normalised
+        view = ren.render_novel_view((H, W), torch.from_numpy(K_CAMBRIDGE), torch.from_numpy(c2w_world), un, DEV, downsample=ds)
+        assert view["pt_feat"].shape == (n, 256) and view["pt3d"].shape == (n, 3) and view["im_pred"].shape[-1] == 3
+    # ---- coarse matching of (noisy copies of) image features against the rendered features: same matches as the oracle ----
+    rng = np.random.default_rng(2)
+    perm = rng.permutation(n)
+    for prec in ("fp32", "bf16"):
+        pt_feat = res[prec]["feat_fine"]
+        im_feat = (pt_feat[perm] + 0.05 * pt_feat.std() * rng.standard_normal((n, 256))).astype(np.float32)
+        got = coarse_match(torch.from_numpy(im_feat).to(DEV), torch.from_numpy(pt_feat).to(DEV), temperature=10.0, temp_type="mul", mutual=True,
+                           match_thres=0.0)
+        conf_ref = MO.coarse_matching(im_feat, pt_feat, 10.0, "mul")
+        i_ref, j_ref, c_ref = MO.extract_mutual_matches(conf_ref, mutual=True, threshold=0.0)
+        i, j = N(got["match_ids"][1]), N(got["match_ids"][2])
+        same = len(set(zip(i.tolist(), j.tolist())) ^ set(zip(i_ref.tolist(), j_ref.tolist())))
+        assert same <= max(2, len(i_ref) // 200), (prec, same, len(i_ref))
+        assert (perm[i] == j).mean() > 0.98 and len(i) > 0.25 * n, (prec, (perm[i] == j).mean(), len(i))
+
+
+def test_config4_batched_views_equal_view_by_view():
+    from nerfmatch_b200.dist import render_views_sharded
+
+    c = dict(embed="normal", nc=64, nf=128, app=False, stop_layer=3, feat_comb="lin", white_bg=False)
+    sd = make_state_dict(92, embed_type="normal", sigma_gain=120.0, sigma_bias=(8.0, 8.0))
+    un = make_unnorm_scene()
+    V = 6
+    c2ws = torch.stack([torch.from_numpy(un @ make_pose(40 + v)) for v in range(V)])
+    for prec in ("fp32", "bf16"):
+        ren = build_renderer(c, sd, precision=prec)
+        out = render_views_sharded(ren, (480, 640), torch.from_numpy(K_7SCENES), c2ws, un, downsample=8)     # world size 1: one batched call
+        assert out["pt_feat"].shape == (V, 4800, 256) and out["pt3d"].shape == (V, 4800, 3)
+        for v in range(V):
+            ref = ren.render_novel_view((480, 640), torch.from_numpy(K_7SCENES), c2ws[v], un, DEV, downsample=8)
+            assert torch.equal(out["pt3d"][v], ref["pt3d"]) and torch.equal(out["im_pred"][v], ref["im_pred"].reshape(-1, 3))
+            if prec == "fp32":
+                assert torch.equal(out["pt_feat"][v], ref["pt_feat"])
+            else:        # tile boundaries of the in-kernel feature compositing depend on the first ray of the call
+                assert (out["pt_feat"][v] - ref["pt_feat"]).abs().max() <= 2e-5 * ref["pt_feat"].abs().max()
