@@ -505,7 +505,7 @@ def run_ours(args):
     if args.only_dev:       # profiling runs (ncu): the device-resident arm only
         if rank == 0:
             emit({"metric": METRIC, "value": n * world * args.steps / (ms_dev / 1e3), "unit": "rays/s", "ms_per_step": ms_dev / args.steps,
-                  "note": "--only-dev (profiling run): not a bench line"})
+                  "clocks": clocks, "note": "--only-dev (profiling run): not a bench line"})
         if world > 1:
             dist.destroy_process_group()
         return
