@@ -76,7 +76,7 @@ __device__ __forceinline__ void accum8_16(float acc[8], uint4 v, float w, int fm
   }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(CompositeParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 8) composite_kernel(CompositeParams p) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
@@ -96,14 +96,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
   } else {
     d[0] = p.rays_d[ray * 3]; d[1] = p.rays_d[ray * 3 + 1]; d[2] = p.rays_d[ray * 3 + 2];
   }
+  // This lane's raw rows (sigmoid rgb, raw sigma) of samples s = lane + 32 i, fetched ONCE as 16-byte loads and kept in
+  // registers for both the alpha and the colour loop; issued together with the z loads so that the warp pays one memory
+  // latency at its start instead of three dependent ones (ncu: the z / sigma / rgb loads were 52 % of the stall samples).
+  constexpr int kPerLane = kMaxSamples / 32;
+  float4 rv[kPerLane];
+  if (p.weights_in == nullptr) {
+    const float4* rawv = reinterpret_cast<const float4*>(p.raw) + ray * S;
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int s = lane + 32 * i;
+      rv[i] = s < S ? __ldcs(rawv + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   for (int j = lane; j < nz; j += 32) sz[j] = p.z[ray * nz + j];
   __syncwarp();
 
   if (p.weights_in == nullptr) {
     // ---- alpha and the exclusive transmittance product ------------------------------------
     const float dnorm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-    for (int s = lane; s < S; s += 32) {
-      float sraw = p.raw[(ray * S + s) * 4 + 3];
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int s = lane + 32 * i;
+      if (s >= S) break;
+      float sraw = rv[i].w;
       if (p.sigma_noise) sraw = sraw + p.sigma_noise[ray * S + s];   // training mode: relu(raw + noise) (render_utils.py:191-195)
       float sigma = fmaxf(sraw, 0.0f);
       float dist = (p.mip || s < S - 1) ? (sz[s + 1] - sz[s]) : 1e10f;
@@ -144,12 +160,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     // ---- rgb / depth / acc / points ----------------------------------------------------------
     float acc = 0.f, dep = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, p0 = 0.f, p1 = 0.f, p2 = 0.f;
     float best = -1.0f; int besti = 0x7fffffff;
-    for (int s = lane; s < S; s += 32) {
+#pragma unroll
+    for (int i = 0; i < kPerLane; ++i) {
+      const int s = lane + 32 * i;
+      if (s >= S) break;
       float w = sw[s];
-      const float* rw = p.raw + (ray * S + s) * 4;
       float zmid = p.mip ? 0.5f * (sz[s] + sz[s + 1]) : sz[s];
       acc += w; dep += w * zmid;
-      c0 += w * rw[0]; c1 += w * rw[1]; c2 += w * rw[2];
+      c0 += w * rv[i].x; c1 += w * rv[i].y; c2 += w * rv[i].z;
       if (p.pts_out || p.pt3d) {
         float q[3];
         if (p.pts_in) {
@@ -368,25 +386,64 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     // st is free again: hold the combined [z | samples] list there (S + N <= 2 * kMaxSamples)
     float* comb = st;   // S + N <= kMaxSamples floats (checked in nmr_create)
     for (int j = lane; j < S; j += 32) comb[j] = sz[j];
-    for (int j = lane; j < N; j += 32) {
+    const bool det = !(p.perturb && (p.u_jitter != nullptr || p.rng_mode == NMR_RNG_PHILOX));
+    int* iw = reinterpret_cast<int*>(sw);      // the weights are consumed: integer scratch, (S - 1) + N <= 255 entries
+    if (det) {
+      // Inference (det=True): u_j = linspace(0, 1, N) is increasing, so instead of N binary searches of u_j in the cdf the
+      // warp locates each of the S-1 cdf entries among the u's - k_i = #{j : u_j < cdf_i}, from the analytic guess
+      // ceil(cdf_i (N-1)) corrected against the exact linspace values - and fills inds_j = #{i : cdf_i <= u_j} = #{i : k_i <= j}
+      // interval by interval.  Same comparisons, same results as searchsorted(cdf, u, right=True) (render_utils.py:251).
+      int* kk = iw;                            // [nb]
+      int* indsv = iw + nb;                    // [N]
+      for (int i = lane; i < nb; i += 32) {
+        const float c = sa[i];
+        int k = (int)ceilf(c * (float)(N - 1));
+        k = min(max(k, 0), N);
+        while (k > 0 && torch_linspace(1.0f, N, k - 1) >= c) --k;
+        while (k < N && torch_linspace(1.0f, N, k) < c) ++k;
+        kk[i] = k;
+      }
+      __syncwarp();
+      for (int i = lane; i < nb; i += 32) {
+        const int j1 = (i + 1 < nb) ? kk[i + 1] : N;
+        for (int j = kk[i]; j < j1; ++j) indsv[j] = i + 1;
+      }
+      if (lane == 0) for (int j = 0; j < kk[0]; ++j) indsv[j] = 0;     // (cdf_0 = 0 = u_0: empty)
+      __syncwarp();
+    }
+    int cnt[kPerLane];                         // det: #{z <= sample} of this lane's samples
+#pragma unroll
+    for (int i8 = 0; i8 < kPerLane; ++i8) {
+      const int j = lane + 32 * i8;
+      cnt[i8] = 0;
+      if (j >= N) break;
       float u;
-      if (p.perturb && (p.u_jitter != nullptr || p.rng_mode == NMR_RNG_PHILOX))       // sample_pdf(det=False): u = torch.rand (:246-247)
+      int inds;
+      if (!det) {                              // sample_pdf(det=False): u = torch.rand (:246-247)
         u = p.u_jitter ? p.u_jitter[ray * N + j] : philox_uniform(p.seed, (uint64_t)(p.ray0 + ray) * 1024u + j, 1u);
-      else
+        inds = upper_bound(sa, nb, u);
+      } else {
         u = torch_linspace(1.0f, N, j);
-      int inds = upper_bound(sa, nb, u);
+        inds = iw[nb + j];
+      }
       int below = max(0, inds - 1), above = min(nb - 1, inds);
       float cb = sa[below], ca = sa[above];
       float bb = 0.5f * (sz[below + 1] + sz[below]), ba = 0.5f * (sz[above + 1] + sz[above]);
       float denom = ca - cb;
       if (denom < 1e-5f) denom = 1.0f;
       float t = (u - cb) / denom;
-      comb[S + j] = bb + t * (ba - bb);
+      const float v = bb + t * (ba - bb);
+      comb[S + j] = v;
       if (p.idx_out) p.idx_out[ray * N + j] = inds;
+      // the sample lies between the mid-points of bins `below` and `above`: #{z <= v} is found by a short scan from below + 1
+      int c = min(below + 1, S);
+      while (c < S && sz[c] <= v) ++c;
+      while (c > 0 && sz[c - 1] > v) --c;
+      cnt[i8] = c;
     }
     __syncwarp();
     // sort(cat(z, samples)).  Both lists are (normally) already sorted, so the stable rank of an element
-    // is its own index plus a binary search in the other list: z_i -> i + #{samples < z_i},
+    // is its own index plus its insertion point in the other list: z_i -> i + #{samples < z_i},
     // sample_j -> j + #{z <= sample_j} (ties keep the concatenation order, like a stable sort).  If fp
     // round-off ever breaks monotonicity the warp falls back to the O(T^2) counting rank, which needs no
     // assumption; torch.sort returns the same multiset either way.
@@ -395,17 +452,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(Composit
     for (int j = lane; j < T; j += 32)
       if (j != 0 && j != S && comb[j] < comb[j - 1]) mono = false;
     if (__all_sync(0xffffffffu, mono)) {
-      for (int e = lane; e < T; e += 32) {
-        float v = comb[e];
-        int rank;
-        if (e < S) {            // #{samples < v}: lower bound
-          int lo = 0, hi = N;
-          while (lo < hi) { int mid = (lo + hi) >> 1; if (comb[S + mid] < v) lo = mid + 1; else hi = mid; }
-          rank = e + lo;
-        } else {
-          rank = (e - S) + upper_bound(comb, S, v);
+      if (det) {
+        // #{samples < z_i} = #{j : cnt_j <= i} (z_i <= sample_j  <=>  i < cnt_j), filled interval by interval like inds above
+        int* cc = iw;                          // [N]   (kk / inds are consumed)
+        int* below_z = iw + N;                 // [S]   N + S <= 256 <= the 264 entries of sw
+#pragma unroll
+        for (int i8 = 0; i8 < kPerLane; ++i8) { const int j = lane + 32 * i8; if (j < N) cc[j] = cnt[i8]; }
+        __syncwarp();
+        for (int j = lane; j < N; j += 32) {
+          const int i1 = (j + 1 < N) ? cc[j + 1] : S;
+          for (int i = cc[j]; i < i1; ++i) below_z[i] = j + 1;
         }
-        p.z_next[ray * T + rank] = v;
+        if (lane == 0) for (int i = 0; i < min(cc[0], S); ++i) below_z[i] = 0;
+        __syncwarp();
+        for (int i = lane; i < S; i += 32) p.z_next[ray * T + i + below_z[i]] = comb[i];
+        for (int j = lane; j < N; j += 32) p.z_next[ray * T + j + cc[j]] = comb[S + j];
+      } else {
+        for (int e = lane; e < T; e += 32) {
+          float v = comb[e];
+          int rank;
+          if (e < S) {            // #{samples < v}: lower bound
+            int lo = 0, hi = N;
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (comb[S + mid] < v) lo = mid + 1; else hi = mid; }
+            rank = e + lo;
+          } else {
+            rank = (e - S) + upper_bound(comb, S, v);
+          }
+          p.z_next[ray * T + rank] = v;
+        }
       }
     } else {
       for (int e = lane; e < T; e += 32) {
