@@ -54,12 +54,24 @@ __device__ __forceinline__ void frustum_tmean(float t0, float t1, float* t_mean)
   *t_mean = mu + (2.0f * mu * hw2) / denom;
 }
 
-// number of entries of the non-decreasing table a[0..n) that are <= u  (searchsorted right=True)
+// number of entries of the non-decreasing table a[0..n) that are <= u  (searchsorted right=True).
+// Fixed-step, branch-free form (the warp's lanes search different keys: a data-dependent loop runs every lane for the
+// longest search and pays a branch per step): lo grows by 2^k whenever the entry that step would skip is still <= u.
+// For a sorted table this is the partition point, i.e. exactly what the bisection returns.
 __device__ __forceinline__ int upper_bound(const float* a, int n, float u) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (a[mid] <= u) lo = mid + 1; else hi = mid;
+  int lo = 0;
+  for (int step = 1 << (31 - __clz(max(n, 1))); step > 0; step >>= 1) {   // n is warp-uniform: no divergence
+    const int t = lo + step;
+    if (t <= n && a[t - 1] <= u) lo = t;
+  }
+  return lo;
+}
+// number of entries of the non-decreasing table a[0..n) that are < v  (searchsorted right=False)
+__device__ __forceinline__ int lower_bound(const float* a, int n, float v) {
+  int lo = 0;
+  for (int step = 1 << (31 - __clz(max(n, 1))); step > 0; step >>= 1) {
+    const int t = lo + step;
+    if (t <= n && a[t - 1] < v) lo = t;
   }
   return lo;
 }
@@ -76,7 +88,7 @@ __device__ __forceinline__ void accum8_16(float acc[8], uint4 v, float w, int fm
   }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 8) composite_kernel(CompositeParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) composite_kernel(CompositeParams p) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ray = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
@@ -386,64 +398,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 8) composite_kernel(Compo
     // st is free again: hold the combined [z | samples] list there (S + N <= 2 * kMaxSamples)
     float* comb = st;   // S + N <= kMaxSamples floats (checked in nmr_create)
     for (int j = lane; j < S; j += 32) comb[j] = sz[j];
-    const bool det = !(p.perturb && (p.u_jitter != nullptr || p.rng_mode == NMR_RNG_PHILOX));
-    int* iw = reinterpret_cast<int*>(sw);      // the weights are consumed: integer scratch, (S - 1) + N <= 255 entries
-    if (det) {
-      // Inference (det=True): u_j = linspace(0, 1, N) is increasing, so instead of N binary searches of u_j in the cdf the
-      // warp locates each of the S-1 cdf entries among the u's - k_i = #{j : u_j < cdf_i}, from the analytic guess
-      // ceil(cdf_i (N-1)) corrected against the exact linspace values - and fills inds_j = #{i : cdf_i <= u_j} = #{i : k_i <= j}
-      // interval by interval.  Same comparisons, same results as searchsorted(cdf, u, right=True) (render_utils.py:251).
-      int* kk = iw;                            // [nb]
-      int* indsv = iw + nb;                    // [N]
-      for (int i = lane; i < nb; i += 32) {
-        const float c = sa[i];
-        int k = (int)ceilf(c * (float)(N - 1));
-        k = min(max(k, 0), N);
-        while (k > 0 && torch_linspace(1.0f, N, k - 1) >= c) --k;
-        while (k < N && torch_linspace(1.0f, N, k) < c) ++k;
-        kk[i] = k;
-      }
-      __syncwarp();
-      for (int i = lane; i < nb; i += 32) {
-        const int j1 = (i + 1 < nb) ? kk[i + 1] : N;
-        for (int j = kk[i]; j < j1; ++j) indsv[j] = i + 1;
-      }
-      if (lane == 0) for (int j = 0; j < kk[0]; ++j) indsv[j] = 0;     // (cdf_0 = 0 = u_0: empty)
-      __syncwarp();
-    }
-    int cnt[kPerLane];                         // det: #{z <= sample} of this lane's samples
-#pragma unroll
-    for (int i8 = 0; i8 < kPerLane; ++i8) {
-      const int j = lane + 32 * i8;
-      cnt[i8] = 0;
-      if (j >= N) break;
+    for (int j = lane; j < N; j += 32) {
       float u;
-      int inds;
-      if (!det) {                              // sample_pdf(det=False): u = torch.rand (:246-247)
+      if (p.perturb && (p.u_jitter != nullptr || p.rng_mode == NMR_RNG_PHILOX))       // sample_pdf(det=False): u = torch.rand (:246-247)
         u = p.u_jitter ? p.u_jitter[ray * N + j] : philox_uniform(p.seed, (uint64_t)(p.ray0 + ray) * 1024u + j, 1u);
-        inds = upper_bound(sa, nb, u);
-      } else {
+      else
         u = torch_linspace(1.0f, N, j);
-        inds = iw[nb + j];
-      }
+      int inds = upper_bound(sa, nb, u);
       int below = max(0, inds - 1), above = min(nb - 1, inds);
       float cb = sa[below], ca = sa[above];
       float bb = 0.5f * (sz[below + 1] + sz[below]), ba = 0.5f * (sz[above + 1] + sz[above]);
       float denom = ca - cb;
       if (denom < 1e-5f) denom = 1.0f;
       float t = (u - cb) / denom;
-      const float v = bb + t * (ba - bb);
-      comb[S + j] = v;
+      comb[S + j] = bb + t * (ba - bb);
       if (p.idx_out) p.idx_out[ray * N + j] = inds;
-      // the sample lies between the mid-points of bins `below` and `above`: #{z <= v} is found by a short scan from below + 1
-      int c = min(below + 1, S);
-      while (c < S && sz[c] <= v) ++c;
-      while (c > 0 && sz[c - 1] > v) --c;
-      cnt[i8] = c;
     }
     __syncwarp();
     // sort(cat(z, samples)).  Both lists are (normally) already sorted, so the stable rank of an element
-    // is its own index plus its insertion point in the other list: z_i -> i + #{samples < z_i},
+    // is its own index plus a binary search in the other list: z_i -> i + #{samples < z_i},
     // sample_j -> j + #{z <= sample_j} (ties keep the concatenation order, like a stable sort).  If fp
     // round-off ever breaks monotonicity the warp falls back to the O(T^2) counting rank, which needs no
     // assumption; torch.sort returns the same multiset either way.
@@ -452,34 +425,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 8) composite_kernel(Compo
     for (int j = lane; j < T; j += 32)
       if (j != 0 && j != S && comb[j] < comb[j - 1]) mono = false;
     if (__all_sync(0xffffffffu, mono)) {
-      if (det) {
-        // #{samples < z_i} = #{j : cnt_j <= i} (z_i <= sample_j  <=>  i < cnt_j), filled interval by interval like inds above
-        int* cc = iw;                          // [N]   (kk / inds are consumed)
-        int* below_z = iw + N;                 // [S]   N + S <= 256 <= the 264 entries of sw
-#pragma unroll
-        for (int i8 = 0; i8 < kPerLane; ++i8) { const int j = lane + 32 * i8; if (j < N) cc[j] = cnt[i8]; }
-        __syncwarp();
-        for (int j = lane; j < N; j += 32) {
-          const int i1 = (j + 1 < N) ? cc[j + 1] : S;
-          for (int i = cc[j]; i < i1; ++i) below_z[i] = j + 1;
+      for (int e = lane; e < T; e += 32) {
+        float v = comb[e];
+        int rank;
+        if (e < S) {            // #{samples < v}
+          rank = e + lower_bound(comb + S, N, v);
+        } else {
+          rank = (e - S) + upper_bound(comb, S, v);
         }
-        if (lane == 0) for (int i = 0; i < min(cc[0], S); ++i) below_z[i] = 0;
-        __syncwarp();
-        for (int i = lane; i < S; i += 32) p.z_next[ray * T + i + below_z[i]] = comb[i];
-        for (int j = lane; j < N; j += 32) p.z_next[ray * T + j + cc[j]] = comb[S + j];
-      } else {
-        for (int e = lane; e < T; e += 32) {
-          float v = comb[e];
-          int rank;
-          if (e < S) {            // #{samples < v}: lower bound
-            int lo = 0, hi = N;
-            while (lo < hi) { int mid = (lo + hi) >> 1; if (comb[S + mid] < v) lo = mid + 1; else hi = mid; }
-            rank = e + lo;
-          } else {
-            rank = (e - S) + upper_bound(comb, S, v);
-          }
-          p.z_next[ray * T + rank] = v;
-        }
+        p.z_next[ray * T + rank] = v;
       }
     } else {
       for (int e = lane; e < T; e += 32) {
