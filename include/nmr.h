@@ -253,10 +253,17 @@ NMR_API int nmr_peer_wait_status(nmr_handle* h);   /* 0, or 1 + index of the fir
 NMR_API int nmr_stage_encode_backward(nmr_handle* h, int kind, const float* x, const float* var, int64_t P,
                                       const float* grad_out, float* grad_x, void* stream);
 /* NeRF.forward backwards (models/nerf.py:94-144): x as in nmr_stage_mlp, grad_raw [P,4] w.r.t. (sigmoid rgb, raw sigma),
- * grad_feat [P,256] w.r.t. the tapped activations (or NULL) -> grad_x [P, xyz+dirs+app].  The forward activations are
- * recomputed chunk by chunk (nothing is kept between the forward and the backward call). */
+ * grad_feat [P,256] w.r.t. the tapped activations (or NULL) -> grad_x [P, xyz+dirs+app].  Either the forward activations are
+ * recomputed chunk by chunk from x (raw_fwd = masks = NULL: nothing is kept between the forward and the backward call), or the
+ * forward was nmr_stage_mlp_masks and its outputs raw_fwd [P,4] and masks are handed back (x may then be NULL). */
 NMR_API int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer,
-                                   const float* grad_raw, const float* grad_feat, float* grad_x, void* stream);
+                                   const float* grad_raw, const float* grad_feat, const float* raw_fwd, const uint32_t* masks,
+                                   float* grad_x, void* stream);
+/* nmr_stage_mlp on the tcgen05 path (NMR_PREC_BF16 / NMR_PREC_FP16) that also emits the ReLU masks of the nine layers for
+ * nmr_stage_mlp_backward: masks [ceil(P/128) * 9216] uint32 (per 128-point tile: [layer 0..8][32-column chunk][row], one bit per
+ * activation; 288 bytes per point instead of the 8.5 KB of fp32 activations). */
+NMR_API int nmr_stage_mlp_masks(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, float* raw,
+                                float* feat, uint32_t* masks, void* stream);
 /* volume_render_radiance_field backwards (render_utils.py:176-230): inputs as nmr_stage_composite; incoming gradients of
  * rgb_map [n,3], depth_map [n], acc_map [n], weights [n,S] (each optional) -> grad_raw [n,S,4] and, optionally,
  * grad_rays_d [n,3] (through delta = dz * |rays_d|).  z is a constant. */

@@ -82,7 +82,8 @@ SYMBOLS = {
     "nmr_stage_mlp": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp, _vp]),
     "nmr_stage_composite": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32] + [_vp] * 10),
     "nmr_stage_encode_backward": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp, _vp, _vp]),
-    "nmr_stage_mlp_backward": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "nmr_stage_mlp_backward": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nmr_stage_mlp_masks": (C.c_int, [_vp, C.c_int, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "nmr_stage_composite_backward": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _u32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nmr_peer_alloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp), _vp]),
     "nmr_peer_free": (C.c_int, [_vp, _vp]),

@@ -34,26 +34,37 @@ class EncodeFn(torch.autograd.Function):
 
 
 class MlpFn(torch.autograd.Function):
-    """NeRF.forward on x [P,in_dim] -> (raw [P,4], feat [P,256]); backward: nmr_stage_mlp_backward (fp32, activations
-    recomputed)."""
+    """NeRF.forward on x [P,in_dim] -> (raw [P,4], feat [P,256]); backward: nmr_stage_mlp_backward.  On the tensor-core
+    precisions the forward kernel emits the nine layers' ReLU masks (one bit per activation) and the backward is the dgrad
+    chain alone; on the fp32 path the activations are recomputed in the backward."""
 
     @staticmethod
     def forward(ctx, x, eng, which, stop_layer):
         xf = x.detach().float().contiguous()
         ctx.eng, ctx.which, ctx.stop_layer = eng, which, stop_layer
-        ctx.save_for_backward(xf)
         ctx.set_materialize_grads(False)
-        raw, feat = eng.stage_mlp(which, xf, stop_layer, want_feat=True)
+        if eng.cfg.precision in ("bf16", "fp16"):
+            raw, feat, masks = eng.stage_mlp_masks(which, xf, stop_layer)
+            ctx.with_masks = True
+            ctx.save_for_backward(raw, masks)
+        else:
+            raw, feat = eng.stage_mlp(which, xf, stop_layer, want_feat=True)
+            ctx.with_masks = False
+            ctx.save_for_backward(xf)
         return raw, feat
 
     @staticmethod
     def backward(ctx, g_raw, g_feat):
-        (xf,) = ctx.saved_tensors
         if g_raw is None and g_feat is None:
             return None, None, None, None
-        g_raw = torch.zeros(xf.shape[0], 4, device=xf.device) if g_raw is None else g_raw.float().contiguous()
+        saved = ctx.saved_tensors
+        P, dev = saved[0].shape[0], saved[0].device
+        g_raw = torch.zeros(P, 4, device=dev) if g_raw is None else g_raw.float().contiguous()
         g_feat = None if g_feat is None else g_feat.float().contiguous()
-        return ctx.eng.stage_mlp_backward(ctx.which, xf, ctx.stop_layer, g_raw, g_feat), None, None, None
+        if ctx.with_masks:
+            raw, masks = saved
+            return ctx.eng.stage_mlp_backward(ctx.which, None, ctx.stop_layer, g_raw, g_feat, raw_fwd=raw, masks=masks), None, None, None
+        return ctx.eng.stage_mlp_backward(ctx.which, saved[0], ctx.stop_layer, g_raw, g_feat), None, None, None
 
 
 class CompositeFn(torch.autograd.Function):

@@ -885,8 +885,24 @@ extern "C" int nmr_stage_encode(nmr_handle* h, int kind, const float* x, const f
   return NMR_OK;
 }
 
+static int stage_mlp_impl(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, float* raw, float* feat,
+                          uint32_t* masks, void* stream);
+
 extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, float* raw,
                              float* feat, void* stream) {
+  return stage_mlp_impl(h, which, x, P, stop_layer, raw, feat, nullptr, stream);
+}
+
+extern "C" int nmr_stage_mlp_masks(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, float* raw,
+                                   float* feat, uint32_t* masks, void* stream) {
+  if (!h) return NMR_ERR_INVALID;
+  if (!masks) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_masks: masks is NULL");
+  if (h->cfg.precision == NMR_PREC_FP32) NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_stage_mlp_masks: the fp32 path keeps no masks (nmr_stage_mlp_backward recomputes the activations)");
+  return stage_mlp_impl(h, which, x, P, stop_layer, raw, feat, masks, stream);
+}
+
+static int stage_mlp_impl(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, float* raw, float* feat,
+                          uint32_t* masks, void* stream) {
   if (!h) return NMR_ERR_INVALID;
   if (which != 0 && which != 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp: which=%d", which);
   if (P < 0 || (P > 0 && (!x || !raw))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp: null argument");
@@ -896,7 +912,7 @@ extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P
   NMR_CUDA(h, cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   const Dims& d = h->d;
-  const int64_t chunk = std::min<int64_t>(P, h->cfg.max_chunk_points);
+  const int64_t chunk = std::min<int64_t>(P, std::max<int64_t>(128, h->cfg.max_chunk_points / 128 * 128));   // whole tiles per chunk
   int r;
   if ((r = ensure_workspace(h, 1, chunk)) != NMR_OK) return r;
   for (int64_t p0 = 0; p0 < P; p0 += chunk) {
@@ -909,7 +925,7 @@ extern "C" int nmr_stage_mlp(nmr_handle* h, int which, const float* x, int64_t P
       if (!tcn.set) NMR_FAIL(h, NMR_ERR_UNSUPPORTED, "nmr_stage_mlp: this configuration / these weights are not built for the tcgen05 path");
       std::string terr; int nl = 0;
       if (tc_run_rows(d, tcn, (const float*)h->X.p, np, stop_layer, raw + p0 * 4, feat ? feat + p0 * kHid : nullptr,
-                      &h->tcws.p, &h->tcws.cap, &nl, s, &terr) != 0)
+                      &h->tcws.p, &h->tcws.cap, &nl, s, &terr, 0, nullptr, masks ? masks + (p0 / 128) * kTcMaskWordsPerTile : nullptr) != 0)
         NMR_FAIL(h, NMR_ERR_CUDA, "tc_run_rows: %s", terr.c_str());
       NMR_LAUNCHED(h, "tcgen05 mlp rows", nl);
     } else {
@@ -1025,10 +1041,12 @@ extern "C" int nmr_stage_composite_backward(nmr_handle* h, const float* raw, con
 // fp32 throughout.  Each chunk of points is re-evaluated forward with every activation kept (the ReLU masks), then the
 // dgrad chain runs on the same GEMM kernel with transposed panels: g_in = (g_out * W) [* mask of the layer below].
 extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, const float* grad_raw,
-                                      const float* grad_feat, float* grad_x, void* stream) {
+                                      const float* grad_feat, const float* raw_fwd, const uint32_t* masks, float* grad_x, void* stream) {
   if (!h) return NMR_ERR_INVALID;
   if (which != 0 && which != 1) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_backward: which=%d", which);
-  if (P < 0 || (P > 0 && (!x || !grad_raw || !grad_x))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_backward: null argument");
+  if (P < 0 || (P > 0 && (!grad_raw || !grad_x))) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_backward: null argument");
+  const bool have_masks = masks != nullptr && raw_fwd != nullptr;      // from nmr_stage_mlp_masks: no re-forward needed
+  if (P > 0 && !have_masks && !x) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_backward: x is needed to recompute the activations");
   if (stop_layer >= kLayers) NMR_FAIL(h, NMR_ERR_INVALID, "nmr_stage_mlp_backward: stop_layer=%d", stop_layer);
   if (!h->net[which].set) NMR_FAIL(h, NMR_ERR_STATE, "nmr_stage_mlp_backward: weights not set");
   if (P == 0) return NMR_OK;
@@ -1063,6 +1081,10 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
     const int64_t np = std::min<int64_t>(C, P - p0);
     const float* gr = grad_raw + p0 * 4;
     const float* gf = grad_feat ? grad_feat + p0 * kHid : nullptr;
+    auto set_mask = [&](GemmParams& g, int layer) {                    // ReLU mask of trunk layer `layer`'s output
+      if (have_masks) { g.mask_bits = masks; g.mask_row0 = p0; g.mask_step = layer; } else { g.mask = H[layer]; g.ldm = kHid; }
+    };
+    if (!have_masks) {
     // ---- forward, every activation kept ----
     launch_repack_input(d, x + p0 * d.in_dim, np, X, s);
     NMR_LAUNCHED(h, "repack_input");
@@ -1091,8 +1113,9 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
       c.A1 = V; c.lda1 = kHalf; c.W1 = n.Wrgb; c.K1 = kHalf; c.bias = n.brgb; c.C = rawc; c.ldc = 4; c.M = np; c.N = 3; c.act = 2;
       if ((r = gemm(c, "bwd: rgb forward")) != NMR_OK) return r;
     }
+    }
     // ---- backward ----
-    launch_rgb_head_backward(gr, rawc, V, n.Wrgb, np, Gv, s);
+    launch_rgb_head_backward(gr, have_masks ? raw_fwd + p0 * 4 : rawc, have_masks ? nullptr : V, masks, p0, n.Wrgb, np, Gv, s);
     NMR_LAUNCHED(h, "rgb_head_backward");
     {
       GemmParams g{};   // d feature = d views_pre * Wview[:, :256]
@@ -1105,7 +1128,7 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
       t.A1 = Ga; t.lda1 = kHid; t.W1 = n.Wtfeat; t.K1 = kHid; t.C = Gb; t.ldc = kHid; t.M = np; t.N = kHid;
       t.r1a = gr + 3; t.ldr1 = 4; t.r1b = n.Walpha;
       if (gf && tap == kLayers - 1) { t.add = gf; t.ldadd = kHid; }
-      t.mask = H[7]; t.ldm = kHid;
+      set_mask(t, 7);
       if ((r = gemm(t, "bwd: d h7")) != NMR_OK) return r;
     }
     float* gin = Gb; float* gout = Ga;
@@ -1118,7 +1141,7 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
       GemmParams g{};
       g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wt[i]; g.K1 = kHid; g.C = gout; g.ldc = kHid; g.M = np; g.N = kHid;
       if (gf && tap == i - 1) { g.add = gf; g.ldadd = kHid; }
-      g.mask = H[i - 1]; g.ldm = kHid;
+      set_mask(g, i - 1);
       if ((r = gemm(g, "bwd: d h")) != NMR_OK) return r;
       std::swap(gin, gout);
     }

@@ -15,7 +15,8 @@ namespace nmr {
 // ---- rgb head: d raw[:, 0:3] (after sigmoid) -> d (views hidden, pre-ReLU)  (models/nerf.py:114-117 backwards) -------------
 // Gv[p, j] = (sum_c g_c * rgb_c * (1 - rgb_c) * Wrgb[c, j]) * [V[p, j] > 0]
 __global__ void rgb_head_backward_kernel(const float* __restrict__ grad_raw, const float* __restrict__ raw, const float* __restrict__ V,
-                                         const float* __restrict__ wrgb, int64_t P, float* __restrict__ Gv) {
+                                         const uint32_t* __restrict__ mask_bits, int64_t row0, const float* __restrict__ wrgb, int64_t P,
+                                         float* __restrict__ Gv) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * kHalf) return;
   const int64_t p = i >> 7;
@@ -24,12 +25,13 @@ __global__ void rgb_head_backward_kernel(const float* __restrict__ grad_raw, con
   const float4 r = *reinterpret_cast<const float4*>(raw + p * 4);
   const float a0 = g.x * (r.x * (1.0f - r.x)), a1 = g.y * (r.y * (1.0f - r.y)), a2 = g.z * (r.z * (1.0f - r.z));
   const float v = a0 * wrgb[j] + a1 * wrgb[kHalf + j] + a2 * wrgb[2 * kHalf + j];
-  Gv[i] = V[i] > 0.0f ? v : 0.0f;
+  const bool on = V ? V[i] > 0.0f : ((mask_bits[mask_word_index(row0 + p, 8, j >> 5)] >> (j & 31)) & 1u) != 0;
+  Gv[i] = on ? v : 0.0f;
 }
-void launch_rgb_head_backward(const float* grad_raw, const float* raw, const float* V, const float* wrgb, int64_t P, float* Gv,
-                              cudaStream_t s) {
+void launch_rgb_head_backward(const float* grad_raw, const float* raw, const float* V, const uint32_t* mask_bits, int64_t row0,
+                              const float* wrgb, int64_t P, float* Gv, cudaStream_t s) {
   if (P == 0) return;
-  rgb_head_backward_kernel<<<(unsigned)((P * kHalf + 255) / 256), 256, 0, s>>>(grad_raw, raw, V, wrgb, P, Gv);
+  rgb_head_backward_kernel<<<(unsigned)((P * kHalf + 255) / 256), 256, 0, s>>>(grad_raw, raw, V, mask_bits, row0, wrgb, P, Gv);
 }
 
 // ---- padded gradient rows [P, kx] -> reference column order [P, in_dim] --------------------------------------------------------

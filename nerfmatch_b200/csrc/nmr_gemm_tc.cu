@@ -197,12 +197,14 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
       // overlaps the TMEM load and the transposition instead of being paid once per row group
       float4 mk[8], ad[8];
       float r1[8];
+      uint32_t mb[8];                                                  // bit-mask form: this lane's 4 bits of the row's word
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int64_t r = rbase + 4 * i + rsub;
-        mk[i] = make_float4(1.f, 1.f, 1.f, 1.f); ad[i] = make_float4(0.f, 0.f, 0.f, 0.f); r1[i] = 0.f;
+        mk[i] = make_float4(1.f, 1.f, 1.f, 1.f); ad[i] = make_float4(0.f, 0.f, 0.f, 0.f); r1[i] = 0.f; mb[i] = 0xfu;
         if (r < p.M) {
           if (p.r1a) r1[i] = __ldg(p.r1a + r * p.ldr1);
+          if (p.mask_bits) mb[i] = (__ldg(p.mask_bits + mask_word_index(p.mask_row0 + r, p.mask_step, c0 >> 5)) >> c4) & 0xfu;
           if (full && vec_in) {
             if (p.mask) mk[i] = __ldg(reinterpret_cast<const float4*>(p.mask + r * p.ldm + cc0));
             if (p.add) ad[i] = __ldg(reinterpret_cast<const float4*>(p.add + r * p.ldadd + cc0));
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
           y = fmaf(r1[i], r1b4[e], y);
           y += a4[e];
           y = act_of(y, p.act);
-          if (!(m4[e] > 0.f)) y = 0.f;
+          if (!(m4[e] > 0.f) || !((mb[i] >> e) & 1u)) y = 0.f;
           x[e] = y;
         }
         float* out = p.C + r * p.ldc + cc0;

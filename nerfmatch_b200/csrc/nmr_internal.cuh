@@ -136,7 +136,13 @@ struct GemmParams {        // C = act(A1*W1^T + A2*W2^T + bias [+ r1a (x) r1b] [
   const float* r1a; int ldr1; const float* r1b;
   const float* add; int ldadd;
   const float* mask; int ldm;
+  // ... or that mask as the bits the tcgen05 forward kernel emitted (nmr_tc.cuh: kTcMaskWordsPerTile words per 128-point tile):
+  // output row r is point mask_row0 + r, output column c is bit (c & 31) of word [tile][mask_step][c >> 5][row]
+  const uint32_t* mask_bits; int64_t mask_row0; int mask_step;
 };
+__host__ __device__ inline int64_t mask_word_index(int64_t pt, int step, int chunk) {
+  return ((pt >> 7) * 9 + step) * 1024 + chunk * 128 + (pt & 127);
+}
 void launch_sgemm(const GemmParams& p, cudaStream_t s);
 // same contract on the tensor cores (nmr_gemm_tc.cu: fp32 operands split into bf16 hi + lo, three tcgen05 MMAs per K step)
 bool gemm_tc_supported(const GemmParams& p);
@@ -152,8 +158,9 @@ struct CompositeBwdParams {
 void launch_composite_backward(const CompositeBwdParams& p, cudaStream_t s);
 void launch_encode_backward(int kind, const Dims& d, const float* x, const float* var, const float* gout, int64_t P, float* gx,
                             cudaStream_t s);
-void launch_rgb_head_backward(const float* grad_raw, const float* raw, const float* V, const float* wrgb, int64_t P, float* Gv,
-                              cudaStream_t s);
+// V: views hidden activations (mask = V > 0) or null -> mask_bits (step 8 of the forward kernel's masks, rows from row0)
+void launch_rgb_head_backward(const float* grad_raw, const float* raw, const float* V, const uint32_t* mask_bits, int64_t row0,
+                              const float* wrgb, int64_t P, float* Gv, cudaStream_t s);
 void launch_unpack_grad(const Dims& d, const float* Gx, const float* Gd, int ldgd, int64_t P, float* out, cudaStream_t s);
 
 // peer-memory exchange (nmr_peer.cu)

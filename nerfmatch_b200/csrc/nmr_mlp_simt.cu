@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(kThreads) sgemm_kernel(GemmParams p) {
         }
         x = apply_act(x, p.act);
         if (p.mask && cc < p.N && !(p.mask[r * p.ldm + cc] > 0.f)) x = 0.f;
+        if (p.mask_bits && cc < p.N && !((p.mask_bits[mask_word_index(p.mask_row0 + r, p.mask_step, cc >> 5)] >> (cc & 31)) & 1u)) x = 0.f;
         v[j] = x;
       }
       float* out = p.C + r * p.ldc + c;

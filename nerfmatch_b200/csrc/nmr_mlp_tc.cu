@@ -99,6 +99,7 @@ struct TcParams {
   float* raw; uint8_t* feat_tiles;
   float* partials;         // fused local compositing (mode 0, S >= 43): [tile][kSeg][256] fp32 instead of feat_tiles
   int debug_step; float* debug_out;
+  uint32_t* masks;         // optional ReLU masks for the backward pass: [tile][9 steps][8 chunks][128 rows] words, bit c = column 32 j + c active
   int* error_flag;
   long long* timeline;   // optional clock64 trace of CTA 0 (NMR_TC_TIMELINE=1): [it][step][4]
 };
@@ -380,7 +381,9 @@ __device__ __forceinline__ void encode_row_ipe(const float m[3], const float var
 // bf16x2 conversions (F2FP.RELU) and ONE tcgen05.st: the packed activations go back into TMEM, over the first 16 of the
 // slice's own 32 accumulator columns, where the next layer's MMAs read them as their A operand (no shared-memory
 // round trip).  Only the tapped layer (stop_layer) also stages its slice in shared memory for the bulk store home.
+static_assert(kTcMaskWordsPerTile == kSteps * 8 * kTileM, "mask layout");
 struct EpiCtx {
+  int64_t tile;                        // tile index of the row (ReLU-mask output)
   uint32_t tap_st; int r; int s;       // tap_st: this row's 64-byte segment in the warp's staging buffer 0
   uint32_t tap_bars; uint32_t tap_n;   // this warp's TAPFULL barrier pair; running count of staged chunks
   int* error_flag;
@@ -417,6 +420,12 @@ __device__ __forceinline__ void epi_trunk(EpiCtx& e, const uint32_t* v, uint32_t
     else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(__uint_as_float(v[2 * i + 1])), "f"(__uint_as_float(v[2 * i])));
   }
   tmem_st16(t_chunk, w);
+  if (p.masks) {                       // which of the 32 activations are non-zero: the backward pass's ReLU mask
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m |= ((w[i] & 0xffffu) ? 1u : 0u) << (2 * i) | ((w[i] >> 16) ? 2u : 0u) << (2 * i);
+    p.masks[(e.tile * kSteps + e.s) * (8 * kTileM) + j * kTileM + e.r] = m;
+  }
   if (p.debug_out && e.s == p.debug_step && valid) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) p.debug_out[pt * kHid + j * 32 + i] = fmaxf(__uint_as_float(v[i]), 0.f);
@@ -434,7 +443,7 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { u
 // Slices [j0, j0 + NS) of the 128 views columns; returns this warp's partial rgb dot products.
 // Math of one 32-column slice jj of the views layer, accumulator values already in registers.
 __device__ __forceinline__ void epi_view_slice(const float* tab, const float* vbrow, const uint32_t* v, int jj, uint64_t& q0, uint64_t& q1,
-                                               uint64_t& q2, const TcParams& p, bool valid, int64_t pt) {
+                                               uint64_t& q2, const TcParams& p, bool valid, int64_t pt, int64_t tile, int r) {
   float x[32];
   const float4* w0 = reinterpret_cast<const float4*>(tab + jj * 32);
   const float4* w1 = w0 + kHalf / 4;
@@ -451,6 +460,12 @@ __device__ __forceinline__ void epi_view_slice(const float* tab, const float* vb
     q0 = fma2(xb, pk2(a.z, a.w), fma2(xa, pk2(a.x, a.y), q0));
     q1 = fma2(xb, pk2(b.z, b.w), fma2(xa, pk2(b.x, b.y), q1));
     q2 = fma2(xb, pk2(c.z, c.w), fma2(xa, pk2(c.x, c.y), q2));
+  }
+  if (p.masks) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) m |= (x[i] > 0.f ? 1u : 0u) << i;
+    p.masks[(tile * kSteps + kViewStep) * (8 * kTileM) + jj * kTileM + r] = m;
   }
   if (p.debug_out && p.debug_step == kViewStep && valid) {
 #pragma unroll
@@ -666,6 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       const int64_t tile = (int64_t)it * G + blockIdx.x;
       const int64_t pt = tile * kTileM + r;
       const bool valid = pt < p.P;
+      e.tile = tile;
       for (int s = 0; s < kViewStep; ++s, ++gstep) {
         e.s = s;
         const int ab = gstep & 1;
@@ -731,8 +747,8 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
         tc_fence_before();
         warp_arrive_leader<CG>(bars + 8 * (BAR_VEMPTY + (it & 1)), rank, lane);
         uint64_t q0 = 0, q1 = 0, q2 = 0;                 // (even, odd) partial sums of the three rgb dot products
-        epi_view_slice(tab, vbrow, va, g, q0, q1, q2, p, valid, pt);
-        epi_view_slice(tab, vbrow, vb, g + 2, q0, q1, q2, p, valid, pt);
+        epi_view_slice(tab, vbrow, va, g, q0, q1, q2, p, valid, pt, tile, r);
+        epi_view_slice(tab, vbrow, vb, g + 2, q0, q1, q2, p, valid, pt, tile, r);
         float c0, c1, c2, d0, d1, d2;
         upk2(q0, c0, d0); upk2(q1, c1, d1); upk2(q2, c2, d2);
         // sigma = h7 . (w_hi + w_lo), accumulated in fp32 by the tensor core
@@ -844,6 +860,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       const int g0 = t * kSteps, ab = g0 & 1;                          // layer 0 of tile t is global step 9 t
       const int64_t pt = ((int64_t)t * G + blockIdx.x) * kTileM + r;
       EpiCtx e0;
+      e0.tile = (int64_t)t * G + blockIdx.x;
       e0.r = r; e0.s = 0; e0.tap_st = 0; e0.tap_bars = 0; e0.tap_n = 0; e0.error_flag = p.error_flag;
       const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + ab * 256;
       mbar_wait(bars + 8 * BAR_S0FULL, (uint32_t)t & 1u, p.error_flag, 310 + ab);
@@ -1398,7 +1415,7 @@ int tc_run(const Dims& d, const TcNet& net, const TcRun& r, float** raw_out, con
 }
 
 int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int stop_layer, float* raw, float* feat,
-                void** ws, size_t* cap, int* launches, cudaStream_t s, std::string* err, int debug_steps, float* debug_out) {
+                void** ws, size_t* cap, int* launches, cudaStream_t s, std::string* err, int debug_steps, float* debug_out, uint32_t* masks) {
   if (!net.set) { *err = "weights not packed"; return -1; }
   size_t need = ws_layout(P, P, nullptr, nullptr);
   if (reserve(ws, cap, need, err) != 0) return -1;
@@ -1416,6 +1433,7 @@ int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int 
   p.P = P;
   p.stop_step = stop_layer < 0 ? kLayers - 1 : stop_layer; p.want_feat = feat ? 1 : 0;
   p.raw = w.raw; p.feat_tiles = w.feat; p.error_flag = w.error_flag;
+  p.masks = masks;
   p.debug_step = debug_steps > 0 ? debug_steps - 1 : -1; p.debug_out = debug_steps > 0 ? debug_out : nullptr;
   if (launch_tc(net, p, launches, s, err) != 0) return -1;
   cudaError_t e = cudaMemcpyAsync(raw, w.raw, (size_t)P * 4 * sizeof(float), cudaMemcpyDeviceToDevice, s);

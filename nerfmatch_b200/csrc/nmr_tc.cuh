@@ -55,7 +55,11 @@ constexpr int kTcMinFuseS = 43; // at most 4 rays touch a tile when S >= 43
 // dumps the post-activation output of step (debug_steps-1) into debug_out [P,256] (unit tests).
 int tc_run_rows(const Dims& d, const TcNet& net, const float* X, int64_t P, int stop_layer, float* raw, float* feat,
                 void** ws, size_t* cap, int* launches, cudaStream_t s, std::string* err, int debug_steps = 0,
-                float* debug_out = nullptr);
+                float* debug_out = nullptr, uint32_t* masks = nullptr);
+// ReLU masks the kernel can emit for the backward pass (nmr_stage_mlp_backward): per 128-point tile kTcMaskWordsPerTile words,
+// [step 0..8][32-column chunk 0..7][row 0..127], bit c of a word = column 32 * chunk + c of that step's output is non-zero
+// (steps 0..7: pts_linears.i after ReLU; step 8: views_linears.0 after ReLU, chunks 0..3).
+constexpr int kTcMaskWordsPerTile = 9 * 8 * 128;
 
 // code recorded by a bounded barrier wait before trapping (mapped host memory), 0 = none
 int tc_trap_code();

@@ -374,13 +374,26 @@ class Engine:
         self.check(st, "nmr_stage_encode_backward")
         return gx
 
-    def stage_mlp_backward(self, which: int, x, stop_layer: int, grad_raw, grad_feat=None):
-        P = x.shape[0]
-        gx = torch.empty(P, x.shape[1], device=self.device)
+    def stage_mlp_backward(self, which: int, x, stop_layer: int, grad_raw, grad_feat=None, raw_fwd=None, masks=None):
+        """x [P,in_dim] (recompute form) or raw_fwd + masks from ``stage_mlp_masks`` (x may be None)."""
+        P = grad_raw.shape[0]
+        gx = torch.empty(P, self.cfg.in_dim, device=self.device)
         with torch.cuda.device(self.device):
-            st = self.lib.nmr_stage_mlp_backward(self.h, which, _ptr(x), P, stop_layer, _ptr(grad_raw), _ptr(grad_feat), _ptr(gx), self.stream())
+            st = self.lib.nmr_stage_mlp_backward(self.h, which, _ptr(x), P, stop_layer, _ptr(grad_raw), _ptr(grad_feat), _ptr(raw_fwd),
+                                                 _ptr(masks), _ptr(gx), self.stream())
         self.check(st, "nmr_stage_mlp_backward")
         return gx
+
+    def stage_mlp_masks(self, which: int, x, stop_layer: int):
+        """Forward on the tcgen05 path that also returns the ReLU masks for ``stage_mlp_backward`` (int32 [tiles, 9216])."""
+        P = x.shape[0]
+        raw = torch.empty(P, 4, device=self.device)
+        feat = torch.empty(P, 256, device=self.device)
+        masks = torch.empty((P + 127) // 128, 9 * 8 * 128, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            st = self.lib.nmr_stage_mlp_masks(self.h, which, _ptr(x), P, stop_layer, _ptr(raw), _ptr(feat), _ptr(masks), self.stream())
+        self.check(st, "nmr_stage_mlp_masks")
+        return raw, feat, masks
 
     def stage_composite_backward(self, raw, z, rays_d, flags=0, grad_rgb=None, grad_depth=None, grad_acc=None, grad_weights=None,
                                  want_rays_d=True):

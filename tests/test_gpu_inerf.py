@@ -83,9 +83,15 @@ def _setup(tag):
     return g, sd, ren
 
 
-@pytest.mark.parametrize("tag", ["smooth", "peaky"])
-def test_inerf_fine_pass_gradient_matches_reference_autograd(tag):
+@pytest.mark.parametrize("tag,prec", [("smooth", "fp32"), ("peaky", "fp32"), ("smooth", "fp16"), ("smooth", "bf16")])
+def test_inerf_fine_pass_gradient_matches_reference_autograd(tag, prec):
+    """prec = fp32: the parity path (activations recomputed in the backward).  fp16 / bf16: the sub-module's forward runs on the
+    tcgen05 kernel, which emits the ReLU masks, and the backward is the dgrad chain alone - same gradient up to the operand
+    rounding of the forward (the masks and rgb it differentiates belong to the 16-bit forward)."""
     g, sd, ren = _setup(tag)
+    if prec != "fp32":
+        ren.nerf_fine.precision = prec
+    tol = {"fp32": 1.0, "fp16": 8.0, "bf16": 60.0}[prec]
     H, W, ds = [int(v) for v in g[f"{tag}.hwds"]]
     K = T(g[f"{tag}.K"])
     img = T(g[f"{tag}.img"])
@@ -101,14 +107,16 @@ def test_inerf_fine_pass_gradient_matches_reference_autograd(tag):
             loss.backward()
     finally:
         torch.set_grad_enabled(True)
-    assert abs(loss.item() - float(g[f"{tag}.loss"])) < 2e-5 * max(1.0, abs(loss.item()))
-    np.testing.assert_allclose(N(rgb_map), g[f"{tag}.rgb_map"], rtol=0, atol=5e-5)
-    assert rel_l2(N(raw_outs.grad), g[f"{tag}.grad_raw"]) < 5e-4
-    assert rel_l2(N(inputs.grad)[:1024], g[f"{tag}.grad_inputs_head"]) < 3e-3
+    assert abs(loss.item() - float(g[f"{tag}.loss"])) < 2e-5 * tol * max(1.0, abs(loss.item()))
+    np.testing.assert_allclose(N(rgb_map), g[f"{tag}.rgb_map"], rtol=0, atol=5e-5 * tol)
+    assert rel_l2(N(raw_outs.grad), g[f"{tag}.grad_raw"]) < 5e-4 * tol
+    assert rel_l2(N(inputs.grad)[:1024], g[f"{tag}.grad_inputs_head"]) < 3e-3 * (1.0 if prec == "fp32" else (3.0 if prec == "fp16" else 15.0))
     ref = g[f"{tag}.grad_pose"]
     got = N(cam_pose.grad[0])
     assert np.abs(got[3]).max() == 0
-    assert np.abs(got[:3] - ref[:3]).max() < 1e-2 * np.abs(ref).max(), (got[:3], ref[:3])
+    assert np.abs(got[:3] - ref[:3]).max() < (1e-2 if prec == "fp32" else (2e-2 if prec == "fp16" else 8e-2)) * np.abs(ref).max(), (got[:3], ref[:3])
+    if prec != "fp32":
+        return
     # one Adam step (nerfmatch_evaluator.py:334, 450-452): the reference's pose update from the reference's gradient
     cam2 = T(g[f"{tag}.pose"])[None].clone().requires_grad_(True)
     opt = torch.optim.Adam(params=[cam2], lr=0.001)
