@@ -39,6 +39,7 @@ struct nmr_handle {
   bool fuse_composite = true;   // bf16 path: composite the tapped features tile-locally inside the MLP kernel (NMR_TC_FUSE=0: off)
   NetF32 net[2];
   DevBuf wpool[2];
+  DevBuf ppool[2];              // dgrad panels pre-split into bf16 hi + lo chunk streams (tensor-core GEMM, nmr_gemm_tc.cu)
   TcNet tc[2][2];               // [operand format: 0 bf16, 1 fp16][coarse, fine]
   DevBuf app;
   int num_frames = 0;
@@ -162,7 +163,7 @@ extern "C" void nmr_destroy(nmr_handle* h) {
   for (auto& ev : h->event_pool) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->peer_status) cudaFreeHost(h->peer_status);
-  for (int i = 0; i < 2; ++i) { h->wpool[i].release(); tc_free_net(&h->tc[0][i]); tc_free_net(&h->tc[1][i]); }
+  for (int i = 0; i < 2; ++i) { h->wpool[i].release(); h->ppool[i].release(); tc_free_net(&h->tc[0][i]); tc_free_net(&h->tc[1][i]); }
   h->app.release(); h->X.release(); h->raw.release(); h->zc.release(); h->zf.release(); h->misc.release();
   h->rays_view.release(); h->tcws.release(); h->match.release(); h->bwd.release();
   for (auto& b : h->B) b.release();
@@ -277,6 +278,23 @@ extern "C" int nmr_set_weights(nmr_handle* h, int which, const nmr_weight_ptrs* 
   n.Wview_f = base + oWvf; n.Wview_d = base + oWvd; n.bview = base + obv; n.Wrgb = base + oWr; n.brgb = base + obr;
   for (int i = 0; i < kLayers; ++i) n.Wt[i] = base + oWt[i];
   n.Wtskip_x = base + oWtsx; n.Wtfeat = base + oWtf; n.Wtview_f = base + oWtvf; n.Wtview_d = base + oWtvd;
+  {  // the same panels pre-split for the tensor-core GEMM: [N, K] fp32 -> K/32 chunks of (bf16 hi | bf16 lo) swizzled blocks
+    struct Panel { size_t src; int N, K; const uint8_t** dst; };
+    std::vector<Panel> panels;
+    for (int i = 0; i < kLayers; ++i) panels.push_back({oWt[i], i == 0 ? d.xyzp : kHid, kHid, &n.Pt[i]});
+    panels.push_back({oWtsx, d.xyzp, kHid, &n.Ptskip_x});
+    panels.push_back({oWtf, kHid, kHid, &n.Ptfeat});
+    panels.push_back({oWtvf, kHid, kHalf, &n.Ptview_f});
+    panels.push_back({oWtvd, d.dap, kHalf, &n.Ptview_d});
+    size_t total = 0;
+    std::vector<size_t> offs;
+    for (auto& pn : panels) { offs.push_back(total); total += packed_panel_bytes(pn.K); }
+    std::vector<uint8_t> packed(total);
+    for (size_t i = 0; i < panels.size(); ++i) pack_split_panel(&pool[panels[i].src], panels[i].N, panels[i].K, packed.data() + offs[i]);
+    NMR_CUDA(h, h->ppool[which].reserve(total));
+    NMR_CUDA(h, cudaMemcpy(h->ppool[which].p, packed.data(), total, cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < panels.size(); ++i) *panels[i].dst = (const uint8_t*)h->ppool[which].p + offs[i];
+  }
   n.set = true;
   // 16-bit UMMA-major tiles for the tcgen05 path, in both operand formats (nmr_set_precision switches on a live handle)
   for (int fmt = 0; fmt < 2; ++fmt) {
@@ -1119,13 +1137,13 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
     NMR_LAUNCHED(h, "rgb_head_backward");
     {
       GemmParams g{};   // d feature = d views_pre * Wview[:, :256]
-      g.A1 = Gv; g.lda1 = kHalf; g.W1 = n.Wtview_f; g.K1 = kHalf; g.C = Ga; g.ldc = kHid; g.M = np; g.N = kHid;
+      g.A1 = Gv; g.lda1 = kHalf; g.W1 = n.Wtview_f; g.W1p = n.Ptview_f; g.K1 = kHalf; g.C = Ga; g.ldc = kHid; g.M = np; g.N = kHid;
       if ((r = gemm(g, "bwd: d feature")) != NMR_OK) return r;
       GemmParams q{};   // d [dirs | app] = d views_pre * Wview[:, 256:]
-      q.A1 = Gv; q.lda1 = kHalf; q.W1 = n.Wtview_d; q.K1 = kHalf; q.C = Gd; q.ldc = d.dap; q.M = np; q.N = d.dap;
+      q.A1 = Gv; q.lda1 = kHalf; q.W1 = n.Wtview_d; q.W1p = n.Ptview_d; q.K1 = kHalf; q.C = Gd; q.ldc = d.dap; q.M = np; q.N = d.dap;
       if ((r = gemm(q, "bwd: d dirs")) != NMR_OK) return r;
       GemmParams t{};   // d h7 = d feature * Wfeat + d sigma (x) w_alpha (+ d feat if h7 is the tapped layer), masked by h7 > 0
-      t.A1 = Ga; t.lda1 = kHid; t.W1 = n.Wtfeat; t.K1 = kHid; t.C = Gb; t.ldc = kHid; t.M = np; t.N = kHid;
+      t.A1 = Ga; t.lda1 = kHid; t.W1 = n.Wtfeat; t.W1p = n.Ptfeat; t.K1 = kHid; t.C = Gb; t.ldc = kHid; t.M = np; t.N = kHid;
       t.r1a = gr + 3; t.ldr1 = 4; t.r1b = n.Walpha;
       if (gf && tap == kLayers - 1) { t.add = gf; t.ldadd = kHid; }
       set_mask(t, 7);
@@ -1135,11 +1153,11 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
     for (int i = kLayers - 1; i >= 1; --i) {
       if (i == skipl) {   // the skip connection's xyz part: d x += d pre_5 * W5[:, :xyz]
         GemmParams g{};
-        g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wtskip_x; g.K1 = kHid; g.C = Gxs; g.ldc = d.xyzp; g.M = np; g.N = d.xyzp;
+        g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wtskip_x; g.W1p = n.Ptskip_x; g.K1 = kHid; g.C = Gxs; g.ldc = d.xyzp; g.M = np; g.N = d.xyzp;
         if ((r = gemm(g, "bwd: d x (skip)")) != NMR_OK) return r;
       }
       GemmParams g{};
-      g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wt[i]; g.K1 = kHid; g.C = gout; g.ldc = kHid; g.M = np; g.N = kHid;
+      g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wt[i]; g.W1p = n.Pt[i]; g.K1 = kHid; g.C = gout; g.ldc = kHid; g.M = np; g.N = kHid;
       if (gf && tap == i - 1) { g.add = gf; g.ldadd = kHid; }
       set_mask(g, i - 1);
       if ((r = gemm(g, "bwd: d h")) != NMR_OK) return r;
@@ -1147,7 +1165,7 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
     }
     {
       GemmParams g{};
-      g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wt[0]; g.K1 = kHid; g.C = Gx0; g.ldc = d.xyzp; g.M = np; g.N = d.xyzp;
+      g.A1 = gin; g.lda1 = kHid; g.W1 = n.Wt[0]; g.W1p = n.Pt[0]; g.K1 = kHid; g.C = Gx0; g.ldc = d.xyzp; g.M = np; g.N = d.xyzp;
       g.add = Gxs; g.ldadd = d.xyzp;
       if ((r = gemm(g, "bwd: d x")) != NMR_OK) return r;
     }

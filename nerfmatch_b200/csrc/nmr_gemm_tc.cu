@@ -15,6 +15,8 @@
 // (tcgen05.commit frees a stage when its MMAs have retired); warps 0-3 then read the accumulator (tcgen05.ld) and apply
 // the epilogue (bias, rank-1 term, added matrix, activation, ReLU mask).  Two CTAs fit an SM (96 KB + 256 TMEM columns
 // each), so one CTA's loads overlap the other's MMAs.
+#include <cstring>
+
 #include "nmr_internal.cuh"
 
 namespace nmr {
@@ -92,14 +94,14 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;                 // the swizzled UMMA tiles need a 1024-byte aligned window
   uint8_t* gbase = smem_raw + (base - raw);
-  const uint32_t bars = base + kStagesG * kStage;               // empty[0], empty[1], accfull, tmem slot
+  const uint32_t bars = base + kStagesG * kStage;               // empty[0], empty[1], accfull, tmem slot, bfull[0], bfull[1]
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + kStagesG * kStage + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * BM;
   const int col0 = blockIdx.y * BN;
 
   if (tid == 0) {
-    mbar_init(bars + 0, 1); mbar_init(bars + 8, 1); mbar_init(bars + 16, 1);
+    mbar_init(bars + 0, 1); mbar_init(bars + 8, 1); mbar_init(bars + 16, 1); mbar_init(bars + 40, 1); mbar_init(bars + 48, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -131,6 +133,7 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
       ua[i] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
       va[i] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if ((t < c1 ? p.W1p : p.W2p) != nullptr) return;               // pre-split panel: fetched by a bulk copy (below)
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = i * kThreadsG + tid, r = idx >> 2, c = idx & 3;
@@ -141,6 +144,18 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
       vb[i] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
+  // pre-split W chunk t -> both B blocks of its stage with one 32 KB bulk copy (thread 0; completes on bfull[stage])
+  auto fetch_packed = [&](int t) {
+    const uint8_t* Wp = t < c1 ? p.W1p : p.W2p;
+    if (Wp == nullptr) return;
+    const int st = t & 1, kc = t < c1 ? t : t - c1;
+    const uint32_t bar = bars + 40 + 8 * st;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * kBBlk) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(base + st * kStage + 2 * kABlk), "l"(Wp + (size_t)kc * (2 * kBBlk)), "r"(2 * kBBlk), "r"(bar) : "memory");
+  };
+  uint32_t bfull_phase = 0;                                          // bit st: parity of the next completion of bfull[st] (thread 0)
+  if (tid == 0) fetch_packed(0);
   load_chunk(0);
   for (int t = 0; t < nchunks; ++t) {
     const int st = t & 1;
@@ -152,14 +167,18 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
       const int idx = i * kThreadsG + tid, r = idx >> 2, c = idx & 3;
       split_store(ua[i], va[i], sA_hi + sw64_off(r, c), sA_lo + sw64_off(r, c));
     }
+    const bool packed = (t < c1 ? p.W1p : p.W2p) != nullptr;
+    if (!packed) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int idx = i * kThreadsG + tid, r = idx >> 2, c = idx & 3;
-      split_store(ub[i], vb[i], sB_hi + sw64_off(r, c), sB_lo + sw64_off(r, c));
+      for (int i = 0; i < 4; ++i) {
+        const int idx = i * kThreadsG + tid, r = idx >> 2, c = idx & 3;
+        split_store(ub[i], vb[i], sB_hi + sw64_off(r, c), sB_lo + sw64_off(r, c));
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's async proxy
     __syncthreads();
     if (tid == 0) {
+      if (packed) { mbar_wait(bars + 40 + 8 * st, (bfull_phase >> st) & 1u); bfull_phase ^= 1u << st; }
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t ah = desc_lo(sA_hi), al = desc_lo(sA_lo), bh = desc_lo(sB_hi), bl = desc_lo(sB_lo);
 #pragma unroll
@@ -170,6 +189,11 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
       }
       umma_commit(bars + 8 * st);                                      // stage free once these MMAs retire
       if (t == nchunks - 1) umma_commit(bars + 16);                    // accumulator complete
+      if (t + 1 < nchunks && ((t + 1 < c1 ? p.W1p : p.W2p) != nullptr)) {
+        // the next chunk's stage was last read by the MMAs of chunk t - 1: once they have retired its B blocks may be refilled
+        if (t + 1 >= kStagesG) mbar_wait(bars + 8 * ((t + 1) & 1), (uint32_t)(((t + 1) / kStagesG) - 1) & 1u);
+        fetch_packed(t + 1);
+      }
     }
     if (t + 1 < nchunks) load_chunk(t + 1);
   }
@@ -280,6 +304,31 @@ __global__ void __launch_bounds__(kThreadsG, 2) gemm3_tc_kernel(const GemmParams
 }
 
 }  // namespace
+
+static uint16_t f2bf_host(float f) {
+  uint32_t u; memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+size_t packed_panel_bytes(int K) { return (size_t)((K + BK - 1) / BK) * 2 * kBBlk; }
+void pack_split_panel(const float* W, int N, int K, uint8_t* out) {
+  const int nch = (K + BK - 1) / BK;
+  memset(out, 0, packed_panel_bytes(K));
+  for (int ch = 0; ch < nch; ++ch)
+    for (int n = 0; n < N && n < BN; ++n)
+      for (int k = 0; k < BK; ++k) {
+        const int kk = ch * BK + k;
+        if (kk >= K) continue;
+        const float x = W[(size_t)n * K + kk];
+        const uint16_t hi = f2bf_host(x);
+        uint32_t hu = (uint32_t)hi << 16; float hf; memcpy(&hf, &hu, 4);
+        const uint16_t lo = f2bf_host(x - hf);
+        const size_t off = (size_t)(n >> 3) * 512 + (n & 7) * 64 + (((k >> 3) ^ ((n & 7) >> 1)) << 4) + (k & 7) * 2;
+        memcpy(out + (size_t)ch * 2 * kBBlk + off, &hi, 2);
+        memcpy(out + (size_t)ch * 2 * kBBlk + kBBlk + off, &lo, 2);
+      }
+}
 
 // Requirements beyond launch_sgemm's: rows of A / W 16-byte aligned (lda, K multiples of 4 floats), K multiples of 8.
 bool gemm_tc_supported(const GemmParams& p) {

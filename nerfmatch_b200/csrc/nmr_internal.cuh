@@ -53,6 +53,8 @@ struct NetF32 {
   float* Wtfeat;       // [256, 256]
   float* Wtview_f;     // [256, 128]
   float* Wtview_d;     // [dap, 128]
+  // the same five kinds of dgrad panels pre-split into bf16 hi + lo chunk streams for the tensor-core GEMM (device, may be null)
+  const uint8_t* Pt[kLayers]; const uint8_t* Ptskip_x; const uint8_t* Ptfeat; const uint8_t* Ptview_f; const uint8_t* Ptview_d;
   bool set;
 };
 
@@ -139,7 +141,14 @@ struct GemmParams {        // C = act(A1*W1^T + A2*W2^T + bias [+ r1a (x) r1b] [
   // ... or that mask as the bits the tcgen05 forward kernel emitted (nmr_tc.cuh: kTcMaskWordsPerTile words per 128-point tile):
   // output row r is point mask_row0 + r, output column c is bit (c & 31) of word [tile][mask_step][c >> 5][row]
   const uint32_t* mask_bits; int64_t mask_row0; int mask_step;
+  // tensor-core kernel only: W1 / W2 already split into bf16 hi + lo and laid out chunk by chunk in the UMMA K-major
+  // SWIZZLE_64B form (pack_split_panel): fetched with one bulk copy per K-chunk instead of being converted by every CTA
+  const uint8_t* W1p; const uint8_t* W2p;
 };
+// Host-side packing of an fp32 panel W [N, K] (row-major, ld = K; N <= 256, K % 8 == 0) for GemmParams::W1p / W2p:
+// ceil(K / 32) chunks of 32 KB, each [256 x 32] bf16 hi block (16 KB) followed by the lo block, rows >= N and columns >= K zero.
+size_t packed_panel_bytes(int K);
+void pack_split_panel(const float* W, int N, int K, uint8_t* out);
 __host__ __device__ inline int64_t mask_word_index(int64_t pt, int step, int chunk) {
   return ((pt >> 7) * 9 + step) * 1024 + chunk * 128 + (pt & 127);
 }
