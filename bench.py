@@ -320,7 +320,8 @@ def inerf_step_ms(dev, precision, steps=5):
         torch.set_grad_enabled(prev)
     return {"ms_per_step": a.elapsed_time(b) / steps, "rays": int(img.shape[0]), "samples": "128 coarse (no grad) + 128 fine (grad), mip", "loss": float(loss.detach()),
             "phases_ms": phases, "forward": precision,
-            "backward": "activations recomputed, dgrad chain on the tensor cores (fp32 operands split into bf16 hi + lo: 3 MMAs per K step)",
+            "backward": "ReLU masks from the tcgen05 forward kernel (no re-forward); dgrad chain on the tensor cores (fp32 gradients split into bf16 hi + lo, pre-split weight panels: 3 MMAs per K step)" if precision != "fp32"
+                        else "activations recomputed in fp32, dgrad chain on the tensor cores (3 x bf16 split)",
             "what": "gen_rays -> sample -> encode -> NeRF -> volume render -> MSE -> backward -> Adam, as nerfmatch_evaluator.py:334-452"}
 
 
