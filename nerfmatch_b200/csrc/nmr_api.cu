@@ -518,12 +518,12 @@ static int render_device(nmr_handle* h, const nmr_render_args* a, cudaStream_t s
   // 480x640 view (59 M points, 2.8 GB) goes through in ONE chunk - no per-chunk launch ramps / partial last waves; 0.6 KB per point
   // with the unfused tap.  The host entry (sink) halves the remaining rays chunk by chunk (1/2, 1/4, ... of the call): the big
   // first chunks keep the launch count low and their device->host copies ride under the rest of the render; only the small last
-  // chunk's copy (~6 % of the outputs) is exposed.
+  // chunk's copy (~3-5 % of the outputs) is exposed.
   const int64_t max_points = (bf16 && h->auto_chunk) ? (feat_tiles ? ((int64_t)1 << 22) : ((int64_t)1 << 26)) : c.max_chunk_points;
   const int64_t cap_rays = std::max<int64_t>(1, std::min<int64_t>(a->n, max_points / smax));
   std::vector<int64_t> schedule;                       // rays per chunk
   if (sink && bf16 && h->auto_chunk && !feat_tiles) {
-    const int64_t min_chunk = 16384;
+    const int64_t min_chunk = 8192;
     int64_t rem = a->n;
     while (rem > 2 * min_chunk) {
       const int64_t cnk = std::min(cap_rays, (rem / 2 + 1023) / 1024 * 1024);
@@ -1056,8 +1056,10 @@ extern "C" int nmr_stage_composite_backward(nmr_handle* h, const float* raw, con
 }
 
 // NeRF.forward backwards (models/nerf.py:94-144): d raw [P,4] (+ d feat [P,256] at the tapped layer) -> d x [P,in_dim].
-// fp32 throughout.  Each chunk of points is re-evaluated forward with every activation kept (the ReLU masks), then the
-// dgrad chain runs on the same GEMM kernel with transposed panels: g_in = (g_out * W) [* mask of the layer below].
+// fp32 gradients.  The ReLU masks come either from the tcgen05 forward kernel (nmr_stage_mlp_masks: one bit per activation, no
+// re-forward) or from re-evaluating each chunk of points forward with every activation kept; the dgrad chain
+// g_in = (g_out * W) [* mask of the layer below] then runs on the GEMM kernels with transposed panels (tensor cores:
+// nmr_gemm_tc.cu with pre-split panels; NMR_GEMM_TC=0: fp32 SIMT).
 extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, int64_t P, int32_t stop_layer, const float* grad_raw,
                                       const float* grad_feat, const float* raw_fwd, const uint32_t* masks, float* grad_x, void* stream) {
   if (!h) return NMR_ERR_INVALID;

@@ -4,8 +4,8 @@
 //     -> fine NeRF MLP                                              (models/nerf.py:94-144)
 //     -> volume_render_radiance_field                               (render_utils.py:176-230)
 //   with the sample positions z and the Gaussian variances held constant (taken from detached rays).
-// Here: the input gradients of those three stages.  The MLP's dgrad GEMM chain itself runs on the GEMM kernels (fp32
-// SIMT, nmr_mlp_simt.cu) with the mask / rank-1 / add epilogue; this file holds the non-GEMM pieces.
+// Here: the input gradients of those three stages.  The MLP's dgrad GEMM chain itself runs on the GEMM kernels (tensor
+// cores: nmr_gemm_tc.cu; fp32 SIMT: nmr_mlp_simt.cu) with the mask / rank-1 / add epilogue; this file holds the non-GEMM pieces.
 // Compiled with -fmad=false like the forward sampling / compositing kernels.
 #include "nmr_internal.cuh"
 #include "nmr_encode.cuh"

@@ -11,7 +11,8 @@
 // bf16's 2^-8, i.e. the accuracy class of TF32x3 / fp32 for well-conditioned sums.
 //
 // One CTA computes a 128 x 256 tile: all 256 threads stream fp32 K-chunks (32 wide) of A and W from global memory, split
-// them and store the four bf16 blocks in the UMMA K-major SWIZZLE_64B layout (double buffered); one thread issues the MMAs
+// them and store the four bf16 blocks in the UMMA K-major SWIZZLE_64B layout (double buffered, the next chunk prefetched; weight
+// panels that were pre-split on the host arrive by one 32 KB bulk copy per chunk instead); one thread issues the MMAs
 // (tcgen05.commit frees a stage when its MMAs have retired); warps 0-3 then read the accumulator (tcgen05.ld) and apply
 // the epilogue (bias, rank-1 term, added matrix, activation, ReLU mask).  Two CTAs fit an SM (96 KB + 256 TMEM columns
 // each), so one CTA's loads overlap the other's MMAs.
