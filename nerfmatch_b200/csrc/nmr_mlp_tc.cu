@@ -23,7 +23,8 @@
 //     live in uniform registers.  Inside an `if (lane == 0)` region every UTCHMMA / UTCBAR is wrapped in R2UR
 //     moves and an ELECT ... BRA.U.ANY loop, ~110 instructions per K=32 chunk on one thread, which starved
 //     the tensor core (36.6 K -> 28.0 K cycles per tile from this change alone; tools/mma_rate.cu);
-//   * weights stream from L2 through a 6-stage ring of 16 KB shared-memory stages filled by the bulk-copy
+//   * weights stream from L2 through a 3-stage ring of 32 KB shared-memory stages (two K=32 chunks per stage: a stage
+//     round trip costs ~320 cycles whatever its size, more than one chunk of MMAs) filled by the bulk-copy
 //     (TMA) engine (cp.async.bulk + mbarrier complete_tx); they are pre-swizzled on the host, so no tensor
 //     map is needed;
 //   * the tapped feature tile (stop_layer) is read back from TMEM after the hand-over (off the critical path) and
@@ -112,6 +113,15 @@ __host__ __device__ constexpr int step_chunks_h(int s) { return s == 0 ? 0 : 8; 
 __host__ __device__ constexpr int step_bias_chunk(int s) { return (s >= 1 && s <= 7 && s != 5) ? 1 : 0; }
 constexpr int kViewN = 160;   // 128 views outputs + sigma head (alpha_linear weights as bf16 hi/lo rows) + padding to a multiple of 32
 __host__ __device__ constexpr int step_chunk_bytes(int s) { return s == kViewStep ? kViewN * 64 : 16384; }
+// position of step s's first chunk in the tile's chunk sequence, chunks per tile, bytes of the ci-th chunk of a tile
+__host__ __device__ constexpr int step_first_chunk(int s) {
+  int n = 0;
+  for (int i = 0; i < s; ++i) n += step_chunks_e(i) + step_chunks_h(i) + step_bias_chunk(i);
+  return n;
+}
+constexpr int kTileChunks = step_first_chunk(kSteps);
+static_assert(kTileChunks % 2 == 0 && step_first_chunk(kViewStep) % 2 == 0, "chunk pairs must not mix 16 KB and views chunks");
+__host__ __device__ constexpr uint32_t tile_chunk_bytes(int ci) { return ci < step_first_chunk(kViewStep) ? 16384u : (uint32_t)(kViewN * 64); }
 __host__ __device__ inline int64_t step_offset(int s) {   // byte offset of step s in the weight stream
   int64_t off = 0;
   for (int i = 0; i < s; ++i) off += (int64_t)(step_chunks_e(i) + step_chunks_h(i) + step_bias_chunk(i)) * step_chunk_bytes(i);
@@ -479,11 +489,15 @@ __device__ __forceinline__ void epi_view_slice(const float* tab, const float* vb
 // columns) - the per-SM weight delivery from L2, which bounds the single-CTA kernel, is halved.
 template <int CG, int F16>
 __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_constant__ TcParams p) {
-  constexpr int kStages = CG == 2 ? kMaxStages : kMaxStages / 2;
-  constexpr int kStageB = kRingBytes / kStages;      // 8 KB half chunks | 16 KB chunks
-  // Ring stages are released one by one (one tcgen05.commit per K=32 chunk).  Releasing them in groups of 2-4 was
-  // measured slower (24.2 K cycles per tile with per-stage release, 25.5 K in groups of 2, 25.8 K in groups of 3).
-  constexpr int kGroup = 1;
+  // Weight ring.  A stage costs a fixed ~310-400 cycles of round trip (tcgen05.commit -> empty barrier -> producer ->
+  // cp.async.bulk -> full barrier) whatever its size: with one 16 KB chunk (256 cycles of MMAs) per stage the ring, not
+  // the tensor core, set the pace - 76 stages x ~320 cycles = the whole 24 K-cycle tile (tools/mma_issue.cu: the bare loop
+  // reaches 63 % of the MMA rate with 16 KB stages and 95 % with 32 KB stages).  Single CTAs therefore move TWO consecutive
+  // chunks per stage: one bulk copy, one barrier pair, 512 cycles of MMAs; three 32 KB stages.  (A tile has 76 chunks = 38
+  // pairs; the 8 views chunks are 10 KB each and pair up among themselves.)  CTA pairs keep 12 stages of 8 KB half chunks.
+  constexpr int kCps = CG == 2 ? 1 : 2;                 // chunks per stage
+  constexpr int kStages = CG == 2 ? kMaxStages : 3;
+  constexpr int kStageB = kRingBytes / kStages;         // 8 KB half chunks | 32 KB chunk pairs
   const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -544,14 +558,25 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
       int stage = 0; uint32_t phase = 0;
       for (int it = 0; it < p.n_iters; ++it) {
         const uint8_t* src = p.chunks;
-        for (int s = 0; s < kSteps; ++s) {
-          const int nch = step_chunks_e(s) + step_chunks_h(s) + step_bias_chunk(s);
-          const uint32_t bytes = step_chunk_bytes(s) / CG;      // CTA pair: this CTA's half of the chunk's output rows
-          for (int c = 0; c < nch; ++c) {
-            if (stage % kGroup == 0) mbar_wait(bars + 8 * (BAR_WEMPTY + stage / kGroup), phase ^ 1, p.error_flag, 100 + stage);
+        if (CG == 2) {
+          for (int s = 0; s < kSteps; ++s) {
+            const int nch = step_chunks_e(s) + step_chunks_h(s) + step_bias_chunk(s);
+            const uint32_t bytes = step_chunk_bytes(s) / 2;       // this CTA's half of the chunk's output rows
+            for (int c = 0; c < nch; ++c) {
+              mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
+              mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
+              bulk_g2s(base + OFF_W + stage * kStageB, src + rank * bytes, bytes, bars + 8 * (BAR_WFULL + stage));
+              src += bytes * 2;
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          for (int ci = 0; ci < kTileChunks; ci += 2) {           // chunks ci, ci + 1: contiguous in the stream, one copy
+            const uint32_t bytes = tile_chunk_bytes(ci) + tile_chunk_bytes(ci + 1);
+            mbar_wait(bars + 8 * (BAR_WEMPTY + stage), phase ^ 1, p.error_flag, 100 + stage);
             mbar_arrive_expect_tx(bars + 8 * (BAR_WFULL + stage), bytes);
-            bulk_g2s(base + OFF_W + stage * kStageB, src + rank * bytes, bytes, bars + 8 * (BAR_WFULL + stage));
-            src += bytes * CG;
+            bulk_g2s(base + OFF_W + stage * kStageB, src, bytes, bars + 8 * (BAR_WFULL + stage));
+            src += bytes;
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -601,39 +626,50 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
           mbar_wait(bars + 8 * BAR_TAPREAD, (uint32_t)(it - tap_dt) & 1u, p.error_flag, 260);
         if (tl_on && it < 8) p.timeline[(it * kSteps + s) * 4 + 0] = clock64();
         uint32_t accumulate = 0;
-        if (step_bias_chunk(s)) {                                // + bias: ones columns of the encoded tile x (lo, hi) bias rows
+        const int ci0 = step_first_chunk(s);                     // position of this step's chunks in the tile's sequence: chunk ci lives
+        if (step_bias_chunk(s)) {                                // in stage slot ci % kCps (compile-time after unrolling)
+          // + bias: ones columns of the encoded tile x (lo, hi) bias rows.
           // Issued FIRST so the tensor core has work while the epilogue hands over chunk 0.  It overwrites the other
           // accumulator buffer, last read by the epilogue two layers back: for s >= 2 the previous layer's hand-over
           // waits already ordered that; for s == 1 it is the previous TILE's view epilogue, which signals VEMPTY.
+          const bool first = ci0 % kCps == 0, last = ci0 % kCps == kCps - 1;
+          const uint32_t boff = first ? 0u : (tile_chunk_bytes(ci0 - 1) >> 4);
           if (s == 1 && it > 0) mbar_wait(bars + 8 * (BAR_VEMPTY + ((it - 1) & 1)), ((it - 1) >> 1) & 1, p.error_flag, 240);
-          mbar_wait(bars + 8 * (BAR_WFULL + stage), wphase, p.error_flag, 220 + stage);
-          if (CG == 2) mbar_wait(bars + 8 * (BAR_PFULL + stage), wphase, p.error_flag, 250 + stage);
+          if (first) {
+            mbar_wait(bars + 8 * (BAR_WFULL + stage), wphase, p.error_flag, 220 + stage);
+            if (CG == 2) mbar_wait(bars + 8 * (BAR_PFULL + stage), wphase, p.error_flag, 250 + stage);
+          }
           tc_fence_after();
           if (elect_one()) {
-            mma_ss<CG>(d_tmem, mk_desc(e_desc + 2 * (kBlk >> 4) + 2), mk_desc(w_desc0 + stage * (kStageB >> 4) + 2), idesc, 0u);
-            if ((stage + 1) % kGroup == 0) mma_commit<CG>(bars + 8 * (BAR_WEMPTY + stage / kGroup));
+            mma_ss<CG>(d_tmem, mk_desc(e_desc + 2 * (kBlk >> 4) + 2), mk_desc(w_desc0 + stage * (kStageB >> 4) + boff + 2), idesc, 0u);
+            if (last) mma_commit<CG>(bars + 8 * (BAR_WEMPTY + stage));
           }
           __syncwarp();
-          if (++stage == kStages) { stage = 0; wphase ^= 1; }
+          if (last) { if (++stage == kStages) { stage = 0; wphase ^= 1; } }
           accumulate = 1;
         }
 #pragma unroll
         for (int c = 0; c < ne + nh; ++c) {
+          const int ci = ci0 + step_bias_chunk(s) + c;
+          const bool first = ci % kCps == 0, last = ci % kCps == kCps - 1;
+          const uint32_t boff = first ? 0u : (tile_chunk_bytes(ci - 1) >> 4);
           const uint32_t wbar = bars + 8 * (BAR_WFULL + stage), pbar = bars + 8 * (BAR_PFULL + stage);
           if (c < ne) {
-            mbar_wait(wbar, wphase, p.error_flag, 220 + stage);
-            if (CG == 2) mbar_wait(pbar, wphase, p.error_flag, 250 + stage);
+            if (first) {
+              mbar_wait(wbar, wphase, p.error_flag, 220 + stage);
+              if (CG == 2) mbar_wait(pbar, wphase, p.error_flag, 250 + stage);
+            }
           } else {
             // chunk (c-ne) of the previous layer's output: packed by the epilogue into that layer's accumulator buffer
             const uint32_t hbar = bars + 8 * (BAR_HREADY + (c - ne));
-            const bool ok_h = mbar_try_wait(hbar, hphase), ok_w = mbar_try_wait(wbar, wphase);   // all probes in flight
-            const bool ok_p = CG == 2 ? mbar_try_wait(pbar, wphase) : true;
+            const bool ok_h = mbar_try_wait(hbar, hphase), ok_w = first ? mbar_try_wait(wbar, wphase) : true;   // all probes in flight
+            const bool ok_p = (CG == 2 && first) ? mbar_try_wait(pbar, wphase) : true;
             if (!ok_h) mbar_wait_slow(hbar, hphase, p.error_flag, 230 + (c - ne));
             if (!ok_w) mbar_wait_slow(wbar, wphase, p.error_flag, 220 + stage);
             if (!ok_p) mbar_wait_slow(pbar, wphase, p.error_flag, 250 + stage);
           }
           tc_fence_after();
-          const uint32_t b0 = w_desc0 + stage * (kStageB >> 4);
+          const uint32_t b0 = w_desc0 + stage * (kStageB >> 4) + boff;
           if (elect_one()) {
             if (c < ne) {
               const uint32_t a0 = e_desc + c * (kBlk >> 4);
@@ -643,11 +679,11 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_tc_kernel(const __grid_c
               mma_ts<CG>(d_tmem, a_tmem + (c - ne) * 32, mk_desc(b0), idesc, accumulate);
               mma_ts<CG>(d_tmem, a_tmem + (c - ne) * 32 + 8, mk_desc(b0 + 2), idesc, 1u);
             }
-            if ((stage + 1) % kGroup == 0) mma_commit<CG>(bars + 8 * (BAR_WEMPTY + stage / kGroup));   // group free (in both CTAs) once these MMAs retire
+            if (last) mma_commit<CG>(bars + 8 * (BAR_WEMPTY + stage));   // stage free (in both CTAs) once these MMAs retire
           }
           __syncwarp();
           accumulate = 1;
-          if (++stage == kStages) { stage = 0; wphase ^= 1; }
+          if (last) { if (++stage == kStages) { stage = 0; wphase ^= 1; } }
         }
         if (tl_on && it < 8) p.timeline[(it * kSteps + s) * 4 + 1] = clock64();
         if (elect_one()) {

@@ -23,11 +23,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __global__ void __launch_bounds__(160, 1) fill_kernel(const uint8_t* __restrict__ src, int total_bytes, int chunk, int stages, int iters, int mode,
                                                        const __grid_constant__ CUtensorMap tmap, long long* cycles, int* sink) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bars[16];
+  __shared__ __align__(8) uint64_t bars[32];
   const uint32_t sb = (smem_u32(smem) + 1023u) & ~1023u;
   uint8_t* sg = smem + (sb - smem_u32(smem));
   const int nchunks = total_bytes / chunk;
-  if (threadIdx.x == 0) { for (int i = 0; i < stages; ++i) mbar_init(smem_u32(&bars[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  if (threadIdx.x == 0) { for (int i = 0; i < 32; ++i) mbar_init(smem_u32(&bars[i]), 1); asm volatile("fence.mbarrier_init.release.cluster;"); }
   __syncthreads();
   long long t0 = clock64();
   int acc = 0;
@@ -56,6 +56,30 @@ __global__ void __launch_bounds__(160, 1) fill_kernel(const uint8_t* __restrict_
         mbar_wait(smem_u32(&bars[st]), (phase_bits >> st) & 1);
         phase_bits ^= 1u << st;
         acc += sg[st * chunk + (done & 1023)];
+        ++done;
+      }
+    }
+  } else if (mode >= 4) {
+    // mode 4 + P: P independent producer threads (one per warp), each keeping `stages` bulk copies in flight in its own
+    // slice of the ring; chunk order rotated per CTA so the SMs do not all ask L2 for the same lines at the same time
+    const int P = mode - 4 + 1;
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && w < P) {
+      int issued = 0, done = 0; const int total = nchunks * iters / P;
+      uint32_t phase_bits = 0;
+      while (done < total) {
+        while (issued < total && issued - done < stages) {
+          int st = w * stages + issued % stages;
+          uint32_t bar = smem_u32(&bars[st]);
+          mbar_expect(bar, chunk);
+          int c = (issued * P + w + blockIdx.x * 5) % nchunks;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(sb + st * chunk), "l"(src + (size_t)c * chunk), "r"(chunk), "r"(bar) : "memory");
+          ++issued;
+        }
+        int st = w * stages + done % stages;
+        mbar_wait(smem_u32(&bars[st]), (phase_bits >> (done % stages)) & 1);
+        phase_bits ^= 1u << (done % stages);
         ++done;
       }
     }
@@ -123,7 +147,9 @@ int main(int argc, char** argv) {
   cudaFuncSetAttribute(fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   struct Cfg { int mode, chunk, stages; const char* name; } cfgs[] = {
       {0, 16384, 3, "bulk1d 16K x3"}, {0, 16384, 6, "bulk1d 16K x6"}, {0, 4096, 24, "bulk1d 4K x24"}, {0, 2048, 48, "bulk1d 2K x48"},
-      {0, 8192, 12, "bulk1d 8K x12"}, {1, 16384, 6, "LDGSTS 16K x6"}, {2, 16384, 6, "LDG+STS 16K"}, {3, 16384, 6, "tensor2d 16K x6"}, {3, 16384, 3, "tensor2d 16K x3"}};
+      {0, 8192, 12, "bulk1d 8K x12"},
+      {4, 16384, 6, "rot 1 thr 16K x6"}, {4, 8192, 12, "rot 1 thr 8K x12"}, {4, 32768, 3, "rot 1 thr 32K x3"}, {4, 32768, 2, "rot 1 thr 32K x2"},
+      {5, 16384, 3, "rot 2 thr 16K x3"}, {5, 8192, 6, "rot 2 thr 8K x6"}, {7, 8192, 3, "rot 4 thr 8K x3"}, {7, 4096, 6, "rot 4 thr 4K x6"}, {7, 16384, 1, "rot 4 thr 16K x1"}, {1, 16384, 6, "LDGSTS 16K x6"}, {2, 16384, 6, "LDG+STS 16K"}, {3, 16384, 6, "tensor2d 16K x6"}, {3, 16384, 3, "tensor2d 16K x3"}};
   for (auto& c : cfgs) {
     if (c.mode == 3 && cr != CUDA_SUCCESS) continue;
     const int iters = 40;
