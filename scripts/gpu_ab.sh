@@ -10,7 +10,7 @@ for v in new ${VARIANTS:-base}; do
   if [ $v = new ]; then cp /tmp/libnmr_new.so nerfmatch_b200/libnmr.so; else cp build_ab/libnmr_$v.so nerfmatch_b200/libnmr.so; fi
   echo "=== variant $v"
   if [ $v != base ]; then
-    timeout 900 python -m pytest tests/test_gpu_bf16.py -x -q > $O/ab_pytest_bf16_$v.log 2>&1; echo "bf16 pytest exit $?"; tail -2 $O/ab_pytest_bf16_$v.log
+    timeout 900 python -m pytest tests/test_gpu_bf16.py tests/test_gpu_inerf.py -x -q > $O/ab_pytest_bf16_$v.log 2>&1; echo "bf16 pytest exit $?"; tail -2 $O/ab_pytest_bf16_$v.log
     python -c "
 from nerfmatch_b200 import _lib as L
 print('trap code', L.load().nmr_debug_trap_code())"

@@ -25,6 +25,7 @@ for _ in range(2):
     ren.predict(rays, 1, 1)
 torch.cuda.synchronize()
 buf = (C.c_longlong * (8 * 9 * 4 + 64))()
+FINE = 8 * 9 * 4 + 16
 n = L.load().nmr_debug_timeline(buf, len(buf))
 t = np.array(buf[:8 * 9 * 4], dtype=np.int64).reshape(8, 9, 4)
 t0 = t[1:6]
@@ -42,3 +43,13 @@ print("encoder warps, iterations 2..5 (cycles): encode next tile, wait for the v
 for i in range(4):
     print(f"{i + 2:4d} {en[i, 1] - en[i, 0]:8d} {en[i, 2] - en[i, 1]:8d} {en[i, 3] - en[i, 2]:8d}")
 print("iteration period:", np.diff(t[1:7, 0, 0]).mean())
+
+fine = np.array(buf[FINE:FINE + 36], dtype=np.int64).reshape(9, 4)
+if not fine[1:8].all():
+    sys.exit(0)          # this build carries no fine-grained stamps
+print("iteration 3, hand-over of layer s -> s+1 (cycles): epilogue wake -> first slice in registers -> chunk 0 handed over -> MMA warp has it;"
+      " chunk 0 -> chunk 7 seen by the MMA warp; last MMA issue of layer s -> epilogue wake")
+for s_ in range(1, 8):
+    wake = t[3, s_, 2]
+    print(f"{s_:4d}  ld {fine[s_, 0] - wake:6d}  cvt+st+arrive {fine[s_, 1] - fine[s_, 0]:6d}  seen {fine[s_ + 1, 2] - fine[s_, 1]:6d}"
+          f"  | chunks 0->7 {fine[s_ + 1, 3] - fine[s_ + 1, 2]:6d}  | last issue -> wake {wake - t[3, s_, 1]:6d}  | first issue(s+1) - wake {t[3, s_ + 1, 0] - wake:6d}")

@@ -221,6 +221,113 @@ static void run_stream(int N, int stages, int grid, const uint8_t* src) {
   cudaFree(d);
 }
 
+// ---- TMEM port contention: the bare MMA loop (TS form, 2 MMAs + commit per iteration, operands resident) while `nld` other
+// warps read accumulator-sized slices with tcgen05.ld.32x32b.x32 as fast as they can (the epilogue's access pattern), each
+// optionally writing 16 columns back with tcgen05.st (the packed activations).
+__global__ void __launch_bounds__(416, 1) kt(int N, int iters, int nld, int with_st, int pace, long long* cyc, unsigned long long* nloads) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint32_t tslot;
+  __shared__ __align__(8) uint64_t bar[32];
+  __shared__ volatile int done;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    done = 0;
+    for (int i = 0; i < 32; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tslot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < 120 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tb = tslot;
+  if (warp == 1) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t w_desc0 = desc_lo(smem_u32(smem));
+    const uint32_t bars = smem_u32(&bar[0]);
+    const uint32_t a_tmem = tb + 256;
+    long long t0 = clock64();
+    int stage = 0; uint32_t acc = 0;
+    for (int i = 0; i < iters; ++i) {
+      const uint32_t b0 = w_desc0 + stage * (16384 >> 4);
+      if (elect_one()) {
+        mma_ts(tb, a_tmem + (i & 7) * 32, mk_desc(b0), idesc, acc);
+        mma_ts(tb, a_tmem + (i & 7) * 32 + 8, mk_desc(b0 + 2), idesc, 1u);
+        commit(bars + 8 * stage);
+      }
+      __syncwarp();
+      acc = 1;
+      if (++stage == kStages) stage = 0;
+    }
+    if (elect_one()) commit(bars + 8 * 20);
+    __syncwarp();
+    while (!try_wait(bars + 8 * 20, 0)) { }
+    long long t2 = clock64();
+    done = 1;
+    if (lane == 0) { cyc[blockIdx.x * 2] = t2 - t0; cyc[blockIdx.x * 2 + 1] = t2 - t0; }
+  } else if (warp >= 4 && warp < 4 + nld) {
+    const uint32_t t_lane = tb + ((uint32_t)((warp & 3) * 32) << 16) + 256;     // read the OTHER buffer (no data hazard with D)
+    unsigned long long n = 0; uint32_t x = 0;
+    while (!done) {
+      uint32_t v[32];
+      const uint32_t ta = t_lane + ((uint32_t)n & 7) * 32;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(ta) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x ^= v[i];
+      if (with_st) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                     ::"r"(tb + ((uint32_t)((warp & 3) * 32) << 16) + 480), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                       "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      ++n;
+      if (pace) { const long long t = clock64(); while (clock64() - t < pace) { } }
+    }
+    if (lane == 0) { atomicAdd(nloads, n); if (x == 0x12345678u) cyc[0] = 0; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tb), "r"(512));
+  }
+}
+static void run_tmem(int N, int nld, int with_st, int pace, int grid) {
+  const int iters = 3072;
+  long long* d; unsigned long long* nl;
+  cudaMalloc(&d, grid * 2 * sizeof(long long)); cudaMemset(d, 0, grid * 2 * sizeof(long long));
+  cudaMalloc(&nl, 8); cudaMemset(nl, 0, 8);
+  const int smem = 120 * 1024;
+  cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  kt<<<grid, 416, smem>>>(N, iters, nld, with_st, pace, d, nl);
+  cudaMemset(nl, 0, 8);
+  kt<<<grid, 416, smem>>>(N, iters, nld, with_st, pace, d, nl);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); exit(1); }
+  long long h[2 * 160]; unsigned long long hn = 0;
+  cudaMemcpy(h, d, grid * 2 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemcpy(&hn, nl, 8, cudaMemcpyDeviceToHost);
+  double tot = 0; int cnt = 0;
+  for (int i = 0; i < grid; ++i) if (h[2 * i] > 0) { tot += h[2 * i]; ++cnt; }
+  const double cyc_per_cta = tot / cnt;
+  printf("TMEM contention: N=%3d MMAs + %d warps of tcgen05.ld.x32%s (pace %4d): %.1f cycles/iteration (floor %d); loads: %.1f B/cycle/SM\n", N, nld,
+         with_st ? " + st.x16" : "", pace, cyc_per_cta / iters, N, (double)hn / cnt * 4096.0 / cyc_per_cta);
+  cudaFree(d); cudaFree(nl);
+}
+
 template <int PAT, int NM>
 static void run(int N, int grid) {
   const int iters = 1536;   // multiple of kStages
@@ -251,6 +358,10 @@ int main() {
   run_stream<1, 2>(256, 3, sms, src); run_stream<2, 2>(256, 3, sms, src);
   run_stream<1, 2>(160, 3, sms, src); run_stream<1, 2>(128, 6, sms, src); run_stream<1, 4>(128, 3, sms, src); run_stream<2, 4>(128, 3, sms, src);
   run_stream<1, 3>(256, 2, sms, src);
+  for (int N : {256, 128}) {
+    run_tmem(N, 0, 0, 0, sms); run_tmem(N, 4, 0, 0, sms); run_tmem(N, 8, 0, 0, sms); run_tmem(N, 8, 1, 0, sms);
+    run_tmem(N, 8, 1, 200, sms); run_tmem(N, 8, 1, 400, sms); run_tmem(N, 8, 1, 800, sms);
+  }
   if (getenv("MMA_ISSUE_STREAM_ONLY")) return 0;
   for (int N : {256, 160, 128, 64, 32}) {
     run<0, 2>(N, sms); run<1, 2>(N, sms); run<2, 2>(N, sms); run<3, 2>(N, sms);
