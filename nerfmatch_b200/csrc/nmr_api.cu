@@ -1076,7 +1076,10 @@ extern "C" int nmr_stage_mlp_backward(nmr_handle* h, int which, const float* x, 
   const NetF32& n = h->net[which];
   const int skipl = h->cfg.skip_layer + 1;
   const int tap = stop_layer < 0 ? kLayers - 1 : stop_layer;
-  const int64_t C = std::min<int64_t>(P, 65536);
+  // points per pass: a whole number of rounds of 128-row GEMM tiles over the SMs (the persistent GEMM deals tiles round-robin)
+  int sms = 0;
+  NMR_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+  const int64_t C = std::min<int64_t>(P, (int64_t)std::max(sms, 1) * 128 * 4);
   // workspace layout (floats per point): X kx | H 8 x 256 | F 256 | V 128 | raw 4 | Gv 128 | Ga 256 | Gb 256 | Gxs xyzp | Gx0 xyzp | Gd dap
   const size_t per_pt = (size_t)d.kx + 8 * kHid + kHid + kHalf + 4 + kHalf + 2 * kHid + 2 * d.xyzp + d.dap;
   NMR_CUDA(h, h->bwd.reserve(per_pt * C * sizeof(float)));
