@@ -594,7 +594,7 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "NeRF MLP (coarse + fine nets)", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                      "frac": achieved / pk["tf_sust"], "frac_of_burst_peak": achieved / pk["tf_burst"], "frac_of_nominal_2250": achieved / 2250.0,
-                     "tensor_pipe_active_pct_ncu": 74.6, "traffic": tr["bytes"], "traffic_source": "static: ncu --set full capture committed under profiles/ (not re-measured in this run)",
+                     "tensor_pipe_active_pct_ncu": 71.9, "traffic": tr["bytes"], "traffic_source": "static: ncu --set full capture committed under profiles/ (not re-measured in this run)",
                      "traffic_note": tr["note"], "peak_source": pk["src"] + " sustained bf16 (MEASURED_PEAKS.json)",
                      "flops_per_launch_set": flops_step, "ms_per_step": mlp_s * 1e3},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
@@ -656,7 +656,7 @@ def ncu_traffic(name):
         return {"bytes": None, "note": "no ncu capture in profiles/"}
     if found < 2:
         return {"bytes": None, "note": "no ncu capture in profiles/"}
-    return {"bytes": tot, "note": "DRAM read+write of ONE fine-pass launch (the whole 480x640 view in one chunk: 58,982,400 sample rows = 460,800 tiles, 44 ms) from profiles/" + name +
+    return {"bytes": tot, "note": "DRAM read+write of ONE fine-pass launch (the whole 480x640 view in one chunk: 58,982,400 sample rows = 460,800 tiles, 46 ms under ncu) from profiles/" + name +
             "; algorithmic bytes of that launch: 16 B raw per row (0.94 GB) + one 1 KB locally composited feature vector per ray segment of a tile "
             "(~1.7 per tile, 0.8 GB) written, z / rays / view bias / 1.2 MB of weights read (0.4 GB) - the per-sample features stay on chip; "
             "tensor_pipe_active_pct_ncu is sm__pipe_tensor_cycles_active of the same launch, single-pass capture (profiles/r02_mlp_tensor_single_pass.csv)"}
