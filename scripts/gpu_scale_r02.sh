@@ -13,7 +13,7 @@ for N in 1 2 4 8; do
   else
     timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N --no-cpu > $O/scale_n$N.json 2> $O/scale_n$N.err
     P=$((P+1))
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P scripts/sweep.py --min-rays 1e6 --max-rays 1e8 --out $O/sweep_n$N.jsonl > $O/sweep_n$N.log 2> $O/sweep_n$N.err
+    [ "${SWEEP:-1}" = 1 ] && timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P scripts/sweep.py --min-rays 1e6 --max-rays 1e8 --out $O/sweep_n$N.jsonl > $O/sweep_n$N.log 2> $O/sweep_n$N.err
     P=$((P+1))
   fi
   echo "N=$N: $(python -c "
